@@ -1,0 +1,197 @@
+/* melvin_b200.h -- C ABI of libmelvin_b200.so
+ *
+ * B200-native (sm_100a) implementation of the per-timestep pseudo-spectral hot
+ * path of Melvin.py.  The reference has no FFI: its extension point is the `xp`
+ * array module injected into every class plus the operator slots bound in the
+ * constructors.  Each entry point below therefore cites the
+ * reference *method* it replaces (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error (MLV_ERR_*);
+ *     mlv_last_error() returns a thread-local description of the last failure.
+ *   - all array arguments are DEVICE pointers owned by the caller (the Python
+ *     layer allocates them through torch); the library never frees or retains
+ *     them beyond the stream work it enqueues.  The context owns only plans:
+ *     twiddle tables, stencil-symbol tables, banded-solve factors and a small
+ *     reduction scratch.
+ *   - all work is enqueued on the context's stream (mlv_set_stream) and the
+ *     calls return immediately; nothing synchronises.
+ *   - complex128 = interleaved (re, im) doubles.  Layouts:
+ *       S  spectral  (2nn+1, nm), rows n = 0..nn,-nn..-1   (melvin/ArrayFactory.py:8-45)
+ *       Sf spectral, FDM-z mode (nn, nz)                   (melvin/Parameters.py:76-78)
+ *       P  physical  (nx, nz) float64                      (melvin/ArrayFactory.py:47-62)
+ *       I  private x-transformed intermediate (nx, ipitch) complex128
+ *   - one host thread per context; distinct contexts are independent.
+ */
+#ifndef MELVIN_B200_H
+#define MELVIN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MLV_OK 0
+#define MLV_ERR_INVALID (-1)
+#define MLV_ERR_UNSUPPORTED (-2)
+#define MLV_ERR_CUDA (-3)
+#define MLV_ERR_NOMEM (-4)
+
+/* diagonal spectral operators g(n, m) applied to a spectral array */
+#define MLV_OP_IDENT 0
+#define MLV_OP_PSI 1    /* (-w)/lap, lap(0,0):=1    LaplacianSolver.py:58-68 + utility.py:65 */
+#define MLV_OP_UX 2     /* -(i kz m) psi(w)          utility.py:71                            */
+#define MLV_OP_UZ 3     /*  (i kx n) psi(w)          utility.py:78                            */
+#define MLV_OP_DDX 4    /* SpatialDifferentiator.py:50  */
+#define MLV_OP_DDZ 5    /* SpatialDifferentiator.py:55  */
+#define MLV_OP_D2DX2 6  /* SpatialDifferentiator.py:60  */
+#define MLV_OP_D2DZ2 7  /* SpatialDifferentiator.py:65  */
+#define MLV_OP_LAP 8    /* Variable.py:111-113 (spectral snabla2) */
+#define MLV_OP_INVLAP 9 /* LaplacianSolver.py:58-68 */
+
+/* multiplier symbols of the forward x pass */
+#define MLV_SYM_ONE 0
+#define MLV_SYM_FDX 1   /* Fourier symbol of the central x stencil, SpatialDifferentiator.py:76,130 */
+#define MLV_SYM_FDZ 2   /* Fourier symbol of the central z stencil, SpatialDifferentiator.py:91,157 */
+
+/* integrator schemes */
+#define MLV_SCHEME_SEMI_IMPLICIT_LAP 0   /* Integrator.py:58-63, L = lcoef * lap symbol */
+#define MLV_SCHEME_SEMI_IMPLICIT_ARR 1   /* Integrator.py:58-63, L = caller's real array */
+#define MLV_SCHEME_EXPLICIT 2            /* Integrator.py:53-56 */
+
+/* elementwise / reduction op codes (array-namespace surface) */
+#define MLV_EW_ADD 0
+#define MLV_EW_SUB 1
+#define MLV_EW_MUL 2
+#define MLV_EW_DIV 3
+#define MLV_EW_COPY 4
+#define MLV_EW_POW 5
+#define MLV_KIND_REAL 0
+#define MLV_KIND_CPLX 1
+#define MLV_KIND_SCALAR 2
+#define MLV_RED_SUM 0
+#define MLV_RED_MAX 1
+#define MLV_RED_MIN 2
+#define MLV_RED_SUMSQ 3
+#define MLV_RED_SUMPROD 4
+
+typedef struct mlv_ctx mlv_ctx;
+
+/* melvin/Parameters.py:63-92 + melvin/BasisFunctions.py:26-59 (derived on the host
+ * by the Python layer so the constants are bit-identical to the reference's) */
+typedef struct mlv_params {
+    int32_t nx, nz;        /* power of two, 16..8192, along every transformed axis */
+    int32_t fdm_z;         /* 0: ["spectral","spectral"]   1: ["spectral","fdm"] */
+    int32_t fd_order;      /* spatial_derivative_order: 2 or 4 */
+    double lx, lz;
+    double kx0, kz0;       /* |i 2 pi / lx|, |i 2 pi / lz| */
+    double d2x, d2z;       /* -(2 pi)^2/lx^2, -(2 pi)^2/lz^2 */
+} mlv_params;
+
+typedef struct mlv_info {
+    int32_t nn, nm;                 /* truncation (nm = -1 in FDM-z mode) */
+    int32_t spec_rows, spec_cols;   /* spectral_shape */
+    int32_t ipitch;                 /* row pitch (complex elements) of I buffers */
+    int32_t reserved;
+    int64_t ibytes;                 /* bytes of one I buffer */
+} mlv_info;
+
+typedef struct mlv_view {           /* 2-D strided view, strides in elements */
+    void* ptr;
+    int64_t row_stride, col_stride;
+} mlv_view;
+
+typedef struct mlv_lin_terms {      /* sum_i (cre_i + i cim_i) * op_i(src_i) */
+    int32_t n;
+    int32_t op[4];
+    const void* src[4];
+    double cre[4], cim[4];
+} mlv_lin_terms;
+
+typedef struct mlv_integ {          /* melvin/Integrator.py:5-18,53-63; TimeDerivative.py:9-45 */
+    int32_t ab_order;               /* 2 | 4 */
+    int32_t scheme;                 /* MLV_SCHEME_* */
+    double dt, alpha, lcoef;
+    const double* larr;             /* scheme ARR: real spectral-shaped linear operator */
+    const void* q_in;               /* state (may equal q_out) */
+    void* q_out;
+    void* f0;                       /* history level curr_idx (read; rewritten if lin.n > 0) */
+    const void* fm1;                /* curr_idx-1 .. curr_idx-3 (ring order) */
+    const void* fm2;
+    const void* fm3;
+} mlv_integ;
+
+typedef struct mlv_xfwd {           /* forward x pass + epilogue */
+    int32_t nf;                     /* 1..4 input I buffers */
+    int32_t mode;                   /* 0: dst = value   1: f0 = value + lin, then integrate */
+    const void* src[4];
+    int32_t sym[4];                 /* MLV_SYM_* */
+    double coef[4];
+    void* dst;                      /* mode 0 */
+    mlv_lin_terms lin;              /* mode 1 */
+    mlv_integ integ;                /* mode 1 */
+} mlv_xfwd;
+
+typedef struct mlv_ew {             /* out = a (op) b on (rows, cols) views */
+    int32_t op, rows, cols;
+    int32_t out_kind, a_kind, b_kind;
+    mlv_view out, a, b;
+    double a_re, a_im, b_re, b_im;
+} mlv_ew;
+
+/* ---- context ------------------------------------------------------------- */
+int mlv_create(const mlv_params* p, mlv_ctx** ctx);
+int mlv_destroy(mlv_ctx* ctx);
+int mlv_set_stream(mlv_ctx* ctx, void* cuda_stream);
+int mlv_get_info(const mlv_ctx* ctx, mlv_info* out);
+const char* mlv_last_error(void);
+int mlv_abi_version(void);
+
+/* ---- transforms: SpectralTransformer.to_physical / to_spectral ------------
+ * (melvin/SpectralTransformer.py:33-88 1-D, :90-199 2-D, COMPLEX_EXP bases) */
+int mlv_to_physical(mlv_ctx* ctx, const void* spec, void* iscratch, double* phys);
+int mlv_to_spectral(mlv_ctx* ctx, const double* phys, void* iscratch, void* spec);
+
+/* the two passes of the 2-D transforms, exposed so that callers can fuse around
+ * the private intermediate (fully spectral mode only) */
+int mlv_x_inverse(mlv_ctx* ctx, int nf, const void* const* spec, const int32_t* op,
+                  void* const* idst);                       /* S -> I with prologue op  */
+int mlv_z_inverse(mlv_ctx* ctx, const void* isrc, double* phys);   /* I -> P             */
+int mlv_z_forward(mlv_ctx* ctx, const double* phys, void* idst);   /* P -> I             */
+int mlv_x_forward(mlv_ctx* ctx, const mlv_xfwd* d);                /* I -> S + epilogue  */
+
+/* ---- nonlinear term: Variable.vec_dot_nabla (melvin/Variable.py:119-128) ---
+ * fused physical-space stage on x-transformed operands:
+ *   ia = Fz[ux*q], ib = Fz[uz*q]; red4 (device, 4 doubles) = max ux, max uz,
+ *   sum ux^2, sum uz^2 (Integrator.py:35-44, utility.py:42-59). */
+int mlv_advect_z(mlv_ctx* ctx, const void* iux, const void* iuz, const void* iq,
+                 void* ia, void* ib, double* red4);
+/* materialised physical operands: out = pddx(ux*q) + pddz(uz*q) */
+int mlv_advect_phys(mlv_ctx* ctx, const double* ux, const double* uz, const double* q,
+                    double* out);
+
+/* ---- SpatialDifferentiator ------------------------------------------------
+ * spectral: sddx/sddz/sd2dx2/sd2dz2/calc_lap (:50-74) through mlv_spec_lincomb;
+ * physical: pddx/pddz/pd2dz2 (:76-185) through mlv_stencil. */
+int mlv_spec_lincomb(mlv_ctx* ctx, const mlv_lin_terms* t, void* out);
+int mlv_lap_array(mlv_ctx* ctx, double coef, double* out);
+int mlv_stencil(mlv_ctx* ctx, const void* in, void* out, int rows, int cols, int ncomp,
+                int axis, int order, int periodic, int second, double h);
+
+/* ---- LaplacianSolver.solve (melvin/LaplacianSolver.py:58-79) --------------
+ * fully spectral: mlv_spec_lincomb with MLV_OP_INVLAP; FDM-z: batched tridiagonal */
+int mlv_solve_fdm(mlv_ctx* ctx, const void* rhs, void* out);
+
+/* ---- Integrator.integrate (melvin/Integrator.py:53-63) -------------------- */
+int mlv_integrate(mlv_ctx* ctx, const mlv_lin_terms* extra, const mlv_integ* g);
+
+/* ---- array-namespace surface (xp.max / xp.sum / xp.mean, arithmetic, slicing) */
+int mlv_elementwise(mlv_ctx* ctx, const mlv_ew* d);
+int mlv_reduce(mlv_ctx* ctx, int op, int rows, int cols, const mlv_view* a,
+               const mlv_view* b, double* out_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MELVIN_B200_H */

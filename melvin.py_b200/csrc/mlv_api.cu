@@ -1,0 +1,674 @@
+// melvin-b200: C ABI (include/melvin_b200.h) -- context, plan tables, launch logic.
+#include "../../include/melvin_b200.h"
+
+#include "mlv_kernels_pw.cuh"
+#include "mlv_rt.h"
+
+#include <stdarg.h>
+#include <new>
+#include <vector>
+
+namespace mlv {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// ------------------------------------------------------------------ context
+struct Plan {            // twiddle tables of one line length
+    int log2n = 0;
+    cplx* dev = nullptr; // one allocation, tables back to back
+    FftTw tw{};
+};
+
+}  // namespace mlv
+
+struct mlv_ctx {
+    mlv_params p;
+    int nn, nm, spec_rows, spec_cols, ipitch;
+    int log2nx, log2nz;
+    double dx, dz;
+    mlv::SpecConsts k;
+    mlv::Plan planx, planz;
+    double* symx = nullptr;     // [nx]
+    double* symz = nullptr;     // [nm]
+    double* tri_cp = nullptr;   // FDM-z: (nn, nz)
+    double* tri_inv = nullptr;
+    double* red = nullptr;      // reduction partials
+    size_t red_cap = 0;
+    mlv::stream_t stream = 0;
+};
+
+namespace mlv {
+
+static int ilog2_exact(int n) {
+    int l = 0;
+    while ((1 << l) < n) ++l;
+    return ((1 << l) == n) ? l : -1;
+}
+
+template <int LOG2N>
+static void build_tables(std::vector<cplx>& host, size_t (&offs)[MLV_MAX_PASS]) {
+    typedef FftCfg<LOG2N> F;
+    for (int p = 0; p < MLV_MAX_PASS; ++p) offs[p] = (size_t)-1;
+    for (int p = 0; p < F::NPASS; ++p) {
+        const int n3 = F::n3(p), r = F::radix(p);
+        if (n3 <= 1) continue;
+        offs[p] = host.size();
+        const long double ncur = (long double)r * n3;
+        for (int d = 1; d < r; ++d)
+            for (int n = 0; n < n3; ++n) {
+                // exp(-2 pi i n d / ncur), argument reduced exactly in integers
+                const long long e = ((long long)n * d) % (long long)ncur;
+                const long double ang = -2.0L * 3.14159265358979323846264338327950288L * (long double)e / ncur;
+                host.push_back(mk((double)cosl(ang), (double)sinl(ang)));
+            }
+    }
+}
+
+static int make_plan(Plan& plan, int log2n, stream_t s) {
+    std::vector<cplx> host;
+    size_t offs[MLV_MAX_PASS];
+    switch (log2n) {
+#define MLV_CASE(L) case L: build_tables<L>(host, offs); break;
+        MLV_CASE(4) MLV_CASE(5) MLV_CASE(6) MLV_CASE(7) MLV_CASE(8) MLV_CASE(9)
+        MLV_CASE(10) MLV_CASE(11) MLV_CASE(12) MLV_CASE(13)
+#undef MLV_CASE
+        default:
+            set_error("unsupported transform length 2^%d (supported: 16..8192)", log2n);
+            return MLV_ERR_UNSUPPORTED;
+    }
+    plan.log2n = log2n;
+    int rc = rt_malloc((void**)&plan.dev, (host.size() + 1) * sizeof(cplx));
+    if (rc) return rc;
+    if (!host.empty()) {
+        rc = rt_h2d(plan.dev, host.data(), host.size() * sizeof(cplx), s);
+        if (rc) return rc;
+    }
+    for (int p = 0; p < MLV_MAX_PASS; ++p)
+        plan.tw.p[p] = (offs[p] == (size_t)-1) ? nullptr : plan.dev + offs[p];
+    return 0;
+}
+
+// imaginary part of the Fourier symbol of the reference's central stencils
+// (SpatialDifferentiator.py:76-104 order 2, :130-185 order 4); SURVEY F2.
+static double stencil_symbol(int order, long long mode, long long npts, double h) {
+    const long double th = 2.0L * 3.14159265358979323846264338327950288L * (long double)mode / (long double)npts;
+    if (order == 2) return (double)(sinl(th) / (long double)h);
+    return (double)((8.0L * sinl(th) - sinl(2.0L * th)) / (6.0L * (long double)h));
+}
+
+// per-size launch geometry
+static constexpr int xcols(int log2n) {          // adjacent columns per x-pass CTA
+    return log2n >= 13 ? 1 : ((512 >> (log2n - 4)) > 32 ? 32 : (512 >> (log2n - 4)));
+}
+static constexpr int zlines(int log2n) {         // row pairs per z-pass CTA
+    return log2n >= 12 ? 1 : ((256 >> (log2n - 4)) > 16 ? 16 : (256 >> (log2n - 4)));
+}
+
+#define MLV_SWITCH_LOG2(L, MACRO)                                                         \
+    switch (L) {                                                                          \
+        case 4: MACRO(4); break;                                                          \
+        case 5: MACRO(5); break;                                                          \
+        case 6: MACRO(6); break;                                                          \
+        case 7: MACRO(7); break;                                                          \
+        case 8: MACRO(8); break;                                                          \
+        case 9: MACRO(9); break;                                                          \
+        case 10: MACRO(10); break;                                                        \
+        case 11: MACRO(11); break;                                                        \
+        case 12: MACRO(12); break;                                                        \
+        case 13: MACRO(13); break;                                                        \
+        default: set_error("unsupported transform length 2^%d", (L)); return MLV_ERR_UNSUPPORTED; \
+    }
+
+static unsigned grid1d(size_t total, unsigned block = 256) {
+    size_t g = (total + block - 1) / block;
+    const size_t cap = 148 * 16;                 // grid-stride: a few waves of 148 SMs
+    if (g > cap) g = cap;
+    if (g == 0) g = 1;
+    return (unsigned)g;
+}
+
+static int ensure_red(mlv_ctx* c, size_t n) {
+    if (n <= c->red_cap) return 0;
+    if (c->red) rt_free(c->red);
+    c->red = nullptr;
+    c->red_cap = 0;
+    int rc = rt_malloc((void**)&c->red, n * sizeof(double));
+    if (rc) return rc;
+    c->red_cap = n;
+    return 0;
+}
+
+static int need_2d(const mlv_ctx* c, const char* fn) {
+    if (c->p.fdm_z) {
+        set_error("%s: only available in fully spectral mode", fn);
+        return MLV_ERR_INVALID;
+    }
+    return 0;
+}
+
+static void fill_lin(LinTerms& o, const mlv_lin_terms* t) {
+    o.n = 0;
+    if (!t) return;
+    o.n = t->n;
+    for (int i = 0; i < t->n && i < MLV_MAXLIN; ++i) {
+        o.src[i] = (const cplx*)t->src[i];
+        o.op[i] = t->op[i];
+        o.cre[i] = t->cre[i];
+        o.cim[i] = t->cim[i];
+    }
+}
+
+static int check_lin(const mlv_ctx* c, const mlv_lin_terms* t, const char* fn) {
+    if (!t) return 0;
+    if (t->n < 0 || t->n > MLV_MAXLIN) {
+        set_error("%s: at most %d linear terms", fn, MLV_MAXLIN);
+        return MLV_ERR_INVALID;
+    }
+    for (int i = 0; i < t->n; ++i) {
+        const int op = t->op[i];
+        if (op < MLV_OP_IDENT || op > MLV_OP_INVLAP) {
+            set_error("%s: bad operator code %d", fn, op);
+            return MLV_ERR_INVALID;
+        }
+        if (c->p.fdm_z && !(op == MLV_OP_IDENT || op == MLV_OP_DDX || op == MLV_OP_D2DX2)) {
+            set_error("%s: operator %d needs a spectral z axis", fn, op);
+            return MLV_ERR_INVALID;
+        }
+        if (!t->src[i]) { set_error("%s: null source", fn); return MLV_ERR_INVALID; }
+    }
+    return 0;
+}
+
+static void fill_integ(IntegArgs& o, const mlv_integ* g) {
+    o.ab_order = g->ab_order;
+    o.scheme = g->scheme;
+    o.dt = g->dt;
+    o.alpha = g->alpha;
+    o.lcoef = g->lcoef;
+    o.larr = g->larr;
+    o.q_in = (const cplx*)g->q_in;
+    o.q_out = (cplx*)g->q_out;
+    o.f0 = (cplx*)g->f0;
+    o.fm1 = (const cplx*)g->fm1;
+    o.fm2 = (const cplx*)g->fm2;
+    o.fm3 = (const cplx*)g->fm3;
+}
+
+static int check_integ(const mlv_ctx* c, const mlv_integ* g, const char* fn) {
+    if (!g || !g->q_in || !g->q_out || !g->f0) { set_error("%s: null pointer", fn); return MLV_ERR_INVALID; }
+    if (g->ab_order != 2 && g->ab_order != 4) { set_error("%s: integrator_order must be 2 or 4", fn); return MLV_ERR_INVALID; }
+    if (!g->fm1 || (g->ab_order == 4 && (!g->fm2 || !g->fm3))) { set_error("%s: missing history level", fn); return MLV_ERR_INVALID; }
+    if (g->scheme < 0 || g->scheme > 2) { set_error("%s: bad scheme", fn); return MLV_ERR_INVALID; }
+    if (g->scheme == MLV_SCHEME_SEMI_IMPLICIT_ARR && !g->larr) { set_error("%s: null linear operator", fn); return MLV_ERR_INVALID; }
+    if (g->scheme == MLV_SCHEME_SEMI_IMPLICIT_LAP && c->p.fdm_z) { set_error("%s: symbolic Laplacian needs fully spectral mode", fn); return MLV_ERR_INVALID; }
+    return 0;
+}
+
+// ----------------------------------------------------------- launch helpers
+template <int L>
+static int launch_xinv(mlv_ctx* c, XInvArgs& a) {
+    constexpr int C = xcols(L);
+    typedef FftCfg<L> F;
+    auto kfn = k_xinv<L, C>;
+    const size_t smem = (size_t)F::XSLOTS * C * sizeof(cplx);
+    const unsigned grid = (unsigned)((a.nm + C - 1) / C);
+    MLV_LAUNCH(kfn, grid, (unsigned)(C * F::T), smem, c->stream, a);
+    return 0;
+}
+
+template <int L>
+static int launch_xfwd(mlv_ctx* c, XFwdArgs& a) {
+    constexpr int C = xcols(L);
+    typedef FftCfg<L> F;
+    auto kfn = k_xfwd<L, C>;
+    size_t smem = (size_t)F::XSLOTS * C * sizeof(cplx);
+    if (a.nf > 1) smem += (size_t)(2 * a.nn + 1) * C * sizeof(cplx);
+    const unsigned grid = (unsigned)((a.nm + C - 1) / C);
+    MLV_LAUNCH(kfn, grid, (unsigned)(C * F::T), smem, c->stream, a);
+    return 0;
+}
+
+template <int L>
+static int launch_zc2r(mlv_ctx* c, ZArgs& a) {
+    constexpr int LPC = zlines(L);
+    typedef FftCfg<L> F;
+    auto kfn = k_z_c2r<L, LPC>;
+    const size_t smem = (size_t)F::XSLOTS * LPC * sizeof(double);
+    const unsigned grid = (unsigned)((a.nx / 2 + LPC - 1) / LPC);
+    MLV_LAUNCH(kfn, grid, (unsigned)(LPC * F::T), smem, c->stream, a);
+    return 0;
+}
+
+template <int L>
+static int launch_zr2c(mlv_ctx* c, ZArgs& a) {
+    constexpr int LPC = zlines(L);
+    typedef FftCfg<L> F;
+    auto kfn = k_z_r2c<L, LPC>;
+    const size_t smem = (size_t)F::XSLOTS * LPC * sizeof(double);
+    const unsigned grid = (unsigned)((a.nx / 2 + LPC - 1) / LPC);
+    MLV_LAUNCH(kfn, grid, (unsigned)(LPC * F::T), smem, c->stream, a);
+    return 0;
+}
+
+template <int L>
+static int launch_zadv(mlv_ctx* c, ZAdvArgs& a, unsigned& grid_out) {
+    constexpr int LPC = zlines(L);
+    typedef FftCfg<L> F;
+    auto kfn = k_z_advect<L, LPC>;
+    const size_t smem = (size_t)LPC * (F::XSLOTS * sizeof(double) + (size_t)F::N * sizeof(cplx));
+    const unsigned grid = (unsigned)((a.nx / 2 + LPC - 1) / LPC);
+    grid_out = grid;
+    int rc = ensure_red(c, (size_t)grid * 4);
+    if (rc) return rc;
+    a.red = c->red;
+    MLV_LAUNCH(kfn, grid, (unsigned)(LPC * F::T), smem, c->stream, a);
+    return 0;
+}
+
+template <int L>
+static int launch_x1d(mlv_ctx* c, X1dArgs& a, bool inverse) {
+    constexpr int C = xcols(L);
+    typedef FftCfg<L> F;
+    const size_t smem = (size_t)F::XSLOTS * C * sizeof(cplx);
+    const unsigned grid = (unsigned)(((a.nz + 1) / 2 + C - 1) / C);
+    if (inverse) {
+        auto kfn = k_x1d_c2r<L, C>;
+        MLV_LAUNCH(kfn, grid, (unsigned)(C * F::T), smem, c->stream, a);
+    } else {
+        auto kfn = k_x1d_r2c<L, C>;
+        MLV_LAUNCH(kfn, grid, (unsigned)(C * F::T), smem, c->stream, a);
+    }
+    return 0;
+}
+
+static int reduce_final(mlv_ctx* c, const double* partial, int n, int stride, int off, int op,
+                        double* out) {
+    auto kfn = k_reduce_final;
+    MLV_LAUNCH(kfn, 1u, 256u, 256 * sizeof(double), c->stream, partial, n, stride, off, op, out);
+    return 0;
+}
+
+}  // namespace mlv
+
+using namespace mlv;
+
+// =========================================================================== ABI
+extern "C" {
+
+int mlv_abi_version(void) { return 1; }
+
+const char* mlv_last_error(void) { return g_err; }
+
+int mlv_create(const mlv_params* p, mlv_ctx** out) {
+    if (!p || !out) { set_error("mlv_create: null argument"); return MLV_ERR_INVALID; }
+    *out = nullptr;
+    if (p->fd_order != 2 && p->fd_order != 4) {
+        set_error("mlv_create: spatial_derivative_order must be 2 or 4");
+        return MLV_ERR_INVALID;
+    }
+    const int lx = ilog2_exact(p->nx);
+    const int lz = ilog2_exact(p->nz);
+    if (lx < 4 || lx > 13) {
+        set_error("mlv_create: nx=%d unsupported (power of two, 16..8192)", p->nx);
+        return MLV_ERR_UNSUPPORTED;
+    }
+    if (!p->fdm_z && (lz < 4 || lz > 13)) {
+        set_error("mlv_create: nz=%d unsupported (power of two, 16..8192)", p->nz);
+        return MLV_ERR_UNSUPPORTED;
+    }
+    if (p->fdm_z && p->nz < 5) { set_error("mlv_create: nz too small"); return MLV_ERR_INVALID; }
+    mlv_ctx* c = new (std::nothrow) mlv_ctx();
+    if (!c) { set_error("out of host memory"); return MLV_ERR_NOMEM; }
+    c->p = *p;
+    c->log2nx = lx;
+    c->log2nz = lz;
+    c->nn = (p->nx - 1) / 3;                       // Parameters.py:67-70
+    c->nm = p->fdm_z ? -1 : (p->nz - 1) / 3;
+    c->spec_rows = p->fdm_z ? c->nn : 2 * c->nn + 1;
+    c->spec_cols = p->fdm_z ? p->nz : c->nm;
+    c->ipitch = p->fdm_z ? 0 : ((c->nm + 1) & ~1);  // even pitch: 32-byte aligned column pairs
+    c->dx = p->lx / p->nx;
+    c->dz = p->lz / p->nz;
+    c->k.kx0 = p->kx0; c->k.kz0 = p->kz0; c->k.d2x = p->d2x; c->k.d2z = p->d2z;
+    int rc = make_plan(c->planx, lx, c->stream);
+    if (!rc && !p->fdm_z) rc = make_plan(c->planz, lz, c->stream);
+    if (!rc) {
+        std::vector<double> sx(p->nx);
+        for (int kk = 0; kk < p->nx; ++kk) {
+            const long long n = kk <= p->nx / 2 ? kk : kk - p->nx;
+            sx[kk] = stencil_symbol(p->fd_order, n, p->nx, c->dx);
+        }
+        rc = rt_malloc((void**)&c->symx, sx.size() * sizeof(double));
+        if (!rc) rc = rt_h2d(c->symx, sx.data(), sx.size() * sizeof(double), c->stream);
+    }
+    if (!rc && !p->fdm_z) {
+        std::vector<double> sz(c->nm > 0 ? c->nm : 1);
+        for (int m = 0; m < c->nm; ++m) sz[m] = stencil_symbol(p->fd_order, m, p->nz, c->dz);
+        rc = rt_malloc((void**)&c->symz, sz.size() * sizeof(double));
+        if (!rc) rc = rt_h2d(c->symz, sz.data(), sz.size() * sizeof(double), c->stream);
+    }
+    if (!rc && p->fdm_z) {
+        // Thomas factors of the nn tridiagonal systems (LaplacianSolver.py:22-49)
+        const size_t tot = (size_t)c->nn * p->nz;
+        std::vector<double> cp(tot), inv(tot);
+        const double off = 1.0 / (c->dz * c->dz);
+        for (int n = 0; n < c->nn; ++n) {
+            const double kx = n * p->kx0;
+            const double b = -(kx * kx + 2.0 / (c->dz * c->dz));
+            double* cpr = &cp[(size_t)n * p->nz];
+            double* ivr = &inv[(size_t)n * p->nz];
+            cpr[0] = 0.0; ivr[0] = 1.0;                       // identity first row
+            for (int i = 1; i < p->nz - 1; ++i) {
+                const double den = b - off * cpr[i - 1];
+                ivr[i] = 1.0 / den;
+                cpr[i] = off / den;
+            }
+            cpr[p->nz - 1] = 0.0; ivr[p->nz - 1] = 1.0;       // identity last row
+        }
+        rc = rt_malloc((void**)&c->tri_cp, tot * sizeof(double));
+        if (!rc) rc = rt_malloc((void**)&c->tri_inv, tot * sizeof(double));
+        if (!rc) rc = rt_h2d(c->tri_cp, cp.data(), tot * sizeof(double), c->stream);
+        if (!rc) rc = rt_h2d(c->tri_inv, inv.data(), tot * sizeof(double), c->stream);
+    }
+    if (!rc) rc = ensure_red(c, 148 * 16 * 4);
+    if (rc) { mlv_destroy(c); return rc; }
+    *out = c;
+    return MLV_OK;
+}
+
+int mlv_destroy(mlv_ctx* c) {
+    if (!c) return MLV_OK;
+    if (c->planx.dev) rt_free(c->planx.dev);
+    if (c->planz.dev) rt_free(c->planz.dev);
+    if (c->symx) rt_free(c->symx);
+    if (c->symz) rt_free(c->symz);
+    if (c->tri_cp) rt_free(c->tri_cp);
+    if (c->tri_inv) rt_free(c->tri_inv);
+    if (c->red) rt_free(c->red);
+    delete c;
+    return MLV_OK;
+}
+
+int mlv_set_stream(mlv_ctx* c, void* s) {
+    if (!c) { set_error("null context"); return MLV_ERR_INVALID; }
+    c->stream = (stream_t)s;
+    return MLV_OK;
+}
+
+int mlv_get_info(const mlv_ctx* c, mlv_info* o) {
+    if (!c || !o) { set_error("null argument"); return MLV_ERR_INVALID; }
+    o->nn = c->nn; o->nm = c->nm;
+    o->spec_rows = c->spec_rows; o->spec_cols = c->spec_cols;
+    o->ipitch = c->ipitch; o->reserved = 0;
+    o->ibytes = (int64_t)c->p.nx * c->ipitch * (int64_t)sizeof(cplx);
+    return MLV_OK;
+}
+
+// ---------------------------------------------------------------- transforms
+int mlv_x_inverse(mlv_ctx* c, int nf, const void* const* spec, const int32_t* op, void* const* idst) {
+    if (!c || !spec || !op || !idst) { set_error("mlv_x_inverse: null argument"); return MLV_ERR_INVALID; }
+    if (int rc = need_2d(c, "mlv_x_inverse")) return rc;
+    if (nf < 1 || nf > MLV_XMAXF) { set_error("mlv_x_inverse: 1..%d fields", MLV_XMAXF); return MLV_ERR_INVALID; }
+    XInvArgs a;
+    a.nn = c->nn; a.nm = c->nm; a.spitch = c->nm; a.ipitch = c->ipitch; a.nf = nf;
+    for (int f = 0; f < nf; ++f) {
+        if (!spec[f] || !idst[f] || op[f] < MLV_OP_IDENT || op[f] > MLV_OP_INVLAP) {
+            set_error("mlv_x_inverse: bad field %d", f);
+            return MLV_ERR_INVALID;
+        }
+        a.src[f] = (const cplx*)spec[f]; a.op[f] = op[f]; a.dst[f] = (cplx*)idst[f];
+    }
+    a.k = c->k; a.tw = c->planx.tw;
+#define MLV_GO(L) return launch_xinv<L>(c, a)
+    MLV_SWITCH_LOG2(c->log2nx, MLV_GO)
+#undef MLV_GO
+    return MLV_OK;
+}
+
+int mlv_z_inverse(mlv_ctx* c, const void* isrc, double* phys) {
+    if (!c || !isrc || !phys) { set_error("mlv_z_inverse: null argument"); return MLV_ERR_INVALID; }
+    if (int rc = need_2d(c, "mlv_z_inverse")) return rc;
+    ZArgs a{};
+    a.nx = c->p.nx; a.nm = c->nm; a.ipitch = c->ipitch;
+    a.I = (const cplx*)isrc; a.P = phys; a.tw = c->planz.tw;
+#define MLV_GO(L) return launch_zc2r<L>(c, a)
+    MLV_SWITCH_LOG2(c->log2nz, MLV_GO)
+#undef MLV_GO
+    return MLV_OK;
+}
+
+int mlv_z_forward(mlv_ctx* c, const double* phys, void* idst) {
+    if (!c || !idst || !phys) { set_error("mlv_z_forward: null argument"); return MLV_ERR_INVALID; }
+    if (int rc = need_2d(c, "mlv_z_forward")) return rc;
+    ZArgs a{};
+    a.nx = c->p.nx; a.nm = c->nm; a.ipitch = c->ipitch;
+    a.Pin = phys; a.Iout = (cplx*)idst; a.tw = c->planz.tw;
+#define MLV_GO(L) return launch_zr2c<L>(c, a)
+    MLV_SWITCH_LOG2(c->log2nz, MLV_GO)
+#undef MLV_GO
+    return MLV_OK;
+}
+
+int mlv_x_forward(mlv_ctx* c, const mlv_xfwd* d) {
+    if (!c || !d) { set_error("mlv_x_forward: null argument"); return MLV_ERR_INVALID; }
+    if (int rc = need_2d(c, "mlv_x_forward")) return rc;
+    if (d->nf < 1 || d->nf > MLV_XMAXF) { set_error("mlv_x_forward: 1..%d fields", MLV_XMAXF); return MLV_ERR_INVALID; }
+    XFwdArgs a;
+    a.nn = c->nn; a.nm = c->nm; a.spitch = c->nm; a.ipitch = c->ipitch; a.nf = d->nf;
+    for (int f = 0; f < d->nf; ++f) {
+        if (!d->src[f] || d->sym[f] < MLV_SYM_ONE || d->sym[f] > MLV_SYM_FDZ) {
+            set_error("mlv_x_forward: bad field %d", f);
+            return MLV_ERR_INVALID;
+        }
+        a.src[f] = (const cplx*)d->src[f]; a.sym[f] = d->sym[f]; a.coef[f] = d->coef[f];
+    }
+    a.symx = c->symx; a.symz = c->symz;
+    a.scale = 1.0 / ((double)c->p.nx * (double)c->p.nz);      // SpectralTransformer.py:191
+    a.mode = d->mode;
+    a.dst = (cplx*)d->dst;
+    a.lin.n = 0;
+    if (d->mode == 0) {
+        if (!d->dst) { set_error("mlv_x_forward: null destination"); return MLV_ERR_INVALID; }
+        memset(&a.integ, 0, sizeof(a.integ));
+    } else if (d->mode == 1) {
+        if (int rc = check_lin(c, &d->lin, "mlv_x_forward")) return rc;
+        if (int rc = check_integ(c, &d->integ, "mlv_x_forward")) return rc;
+        fill_lin(a.lin, &d->lin);
+        fill_integ(a.integ, &d->integ);
+    } else {
+        set_error("mlv_x_forward: bad mode %d", d->mode);
+        return MLV_ERR_INVALID;
+    }
+    a.k = c->k; a.tw = c->planx.tw;
+#define MLV_GO(L) return launch_xfwd<L>(c, a)
+    MLV_SWITCH_LOG2(c->log2nx, MLV_GO)
+#undef MLV_GO
+    return MLV_OK;
+}
+
+int mlv_to_physical(mlv_ctx* c, const void* spec, void* iscratch, double* phys) {
+    if (!c || !spec || !phys) { set_error("mlv_to_physical: null argument"); return MLV_ERR_INVALID; }
+    if (c->p.fdm_z) {
+        X1dArgs a{};
+        a.nn = c->nn; a.nz = c->p.nz; a.S = (const cplx*)spec; a.P = phys; a.tw = c->planx.tw;
+#define MLV_GO(L) return launch_x1d<L>(c, a, true)
+        MLV_SWITCH_LOG2(c->log2nx, MLV_GO)
+#undef MLV_GO
+        return MLV_OK;
+    }
+    if (!iscratch) { set_error("mlv_to_physical: null scratch"); return MLV_ERR_INVALID; }
+    const void* s[1] = {spec};
+    const int32_t op[1] = {MLV_OP_IDENT};
+    void* d[1] = {iscratch};
+    if (int rc = mlv_x_inverse(c, 1, s, op, d)) return rc;
+    return mlv_z_inverse(c, iscratch, phys);
+}
+
+int mlv_to_spectral(mlv_ctx* c, const double* phys, void* iscratch, void* spec) {
+    if (!c || !spec || !phys) { set_error("mlv_to_spectral: null argument"); return MLV_ERR_INVALID; }
+    if (c->p.fdm_z) {
+        X1dArgs a{};
+        a.nn = c->nn; a.nz = c->p.nz; a.Pin = phys; a.Sout = (cplx*)spec;
+        a.scale = 1.0 / (double)c->p.nx;                        // SpectralTransformer.py:85
+        a.tw = c->planx.tw;
+#define MLV_GO(L) return launch_x1d<L>(c, a, false)
+        MLV_SWITCH_LOG2(c->log2nx, MLV_GO)
+#undef MLV_GO
+        return MLV_OK;
+    }
+    if (!iscratch) { set_error("mlv_to_spectral: null scratch"); return MLV_ERR_INVALID; }
+    if (int rc = mlv_z_forward(c, phys, iscratch)) return rc;
+    mlv_xfwd d;
+    memset(&d, 0, sizeof(d));
+    d.nf = 1; d.mode = 0; d.src[0] = iscratch; d.sym[0] = MLV_SYM_ONE; d.coef[0] = 1.0; d.dst = spec;
+    return mlv_x_forward(c, &d);
+}
+
+// ------------------------------------------------------------ nonlinear term
+int mlv_advect_z(mlv_ctx* c, const void* iux, const void* iuz, const void* iq, void* ia, void* ib,
+                 double* red4) {
+    if (!c || !iux || !iuz || !iq || !ia || !ib) { set_error("mlv_advect_z: null argument"); return MLV_ERR_INVALID; }
+    if (int rc = need_2d(c, "mlv_advect_z")) return rc;
+    ZAdvArgs a{};
+    a.nx = c->p.nx; a.nm = c->nm; a.ipitch = c->ipitch;
+    a.Iux = (const cplx*)iux; a.Iuz = (const cplx*)iuz; a.Iq = (const cplx*)iq;
+    a.IA = (cplx*)ia; a.IB = (cplx*)ib; a.tw = c->planz.tw;
+    unsigned grid = 0;
+    int rc = 0;
+#define MLV_GO(L) rc = launch_zadv<L>(c, a, grid)
+    MLV_SWITCH_LOG2(c->log2nz, MLV_GO)
+#undef MLV_GO
+    if (rc) return rc;
+    if (red4) {
+        for (int w = 0; w < 4; ++w)
+            if ((rc = reduce_final(c, c->red, (int)grid, 4, w, w < 2 ? RED_MAX : RED_SUM, red4 + w)))
+                return rc;
+    }
+    return MLV_OK;
+}
+
+int mlv_advect_phys(mlv_ctx* c, const double* ux, const double* uz, const double* q, double* out) {
+    if (!c || !ux || !uz || !q || !out) { set_error("mlv_advect_phys: null argument"); return MLV_ERR_INVALID; }
+    AdvectArgs a;
+    a.ux = ux; a.uz = uz; a.q = q; a.out = out;
+    a.nx = c->p.nx; a.nz = c->p.nz; a.order = c->p.fd_order; a.z_periodic = !c->p.fdm_z;
+    a.dx = c->dx; a.dz = c->dz;
+    auto kfn = k_advect_phys;
+    MLV_LAUNCH(kfn, grid1d((size_t)a.nx * a.nz), 256u, 0, c->stream, a);
+    return MLV_OK;
+}
+
+// ------------------------------------------------------ spectral pointwise
+int mlv_spec_lincomb(mlv_ctx* c, const mlv_lin_terms* t, void* out) {
+    if (!c || !t || !out) { set_error("mlv_spec_lincomb: null argument"); return MLV_ERR_INVALID; }
+    if (int rc = check_lin(c, t, "mlv_spec_lincomb")) return rc;
+    SpecLinArgs a;
+    a.rows = c->spec_rows; a.cols = c->spec_cols; a.nn = c->nn; a.fdm = c->p.fdm_z;
+    fill_lin(a.lin, t);
+    a.out = (cplx*)out; a.k = c->k;
+    auto kfn = k_spec_lincomb;
+    MLV_LAUNCH(kfn, grid1d((size_t)a.rows * a.cols), 256u, 0, c->stream, a);
+    return MLV_OK;
+}
+
+int mlv_lap_array(mlv_ctx* c, double coef, double* out) {
+    if (!c || !out) { set_error("mlv_lap_array: null argument"); return MLV_ERR_INVALID; }
+    if (int rc = need_2d(c, "mlv_lap_array")) return rc;
+    auto kfn = k_lap_array;
+    MLV_LAUNCH(kfn, grid1d((size_t)c->spec_rows * c->spec_cols), 256u, 0, c->stream, out,
+               c->spec_rows, c->spec_cols, c->nn, c->k, coef);
+    return MLV_OK;
+}
+
+int mlv_stencil(mlv_ctx* c, const void* in, void* out, int rows, int cols, int ncomp, int axis,
+                int order, int periodic, int second, double h) {
+    if (!c || !in || !out) { set_error("mlv_stencil: null argument"); return MLV_ERR_INVALID; }
+    if ((order != 2 && order != 4) || (ncomp != 1 && ncomp != 2) || (axis != 0 && axis != 1) ||
+        rows < 1 || cols < 1) {
+        set_error("mlv_stencil: bad argument");
+        return MLV_ERR_INVALID;
+    }
+    if (second && axis != 1) { set_error("mlv_stencil: second derivative only along z"); return MLV_ERR_INVALID; }
+    StencilArgs a;
+    a.in = (const double*)in; a.out = (double*)out; a.rows = rows; a.cols = cols; a.ncomp = ncomp;
+    a.axis = axis; a.order = order; a.periodic = periodic; a.second = second; a.h = h;
+    auto kfn = k_stencil;
+    MLV_LAUNCH(kfn, grid1d((size_t)rows * cols * ncomp), 256u, 0, c->stream, a);
+    return MLV_OK;
+}
+
+int mlv_solve_fdm(mlv_ctx* c, const void* rhs, void* out) {
+    if (!c || !rhs || !out) { set_error("mlv_solve_fdm: null argument"); return MLV_ERR_INVALID; }
+    if (!c->p.fdm_z) { set_error("mlv_solve_fdm: context is fully spectral"); return MLV_ERR_INVALID; }
+    TriArgs a;
+    a.rhs = (const cplx*)rhs; a.out = (cplx*)out; a.cp = c->tri_cp; a.inv = c->tri_inv;
+    a.nn = c->nn; a.nz = c->p.nz; a.off = 1.0 / (c->dz * c->dz);
+    constexpr int ROWS = 8, CHUNK = 128;
+    auto kfn = k_tridiag<ROWS, CHUNK>;
+    const size_t smem = (size_t)ROWS * (CHUNK + 1) * sizeof(cplx);
+    MLV_LAUNCH(kfn, (unsigned)((a.nn + ROWS - 1) / ROWS), 256u, smem, c->stream, a);
+    return MLV_OK;
+}
+
+int mlv_integrate(mlv_ctx* c, const mlv_lin_terms* extra, const mlv_integ* g) {
+    if (!c) { set_error("mlv_integrate: null context"); return MLV_ERR_INVALID; }
+    if (int rc = check_lin(c, extra, "mlv_integrate")) return rc;
+    if (int rc = check_integ(c, g, "mlv_integrate")) return rc;
+    IntegKArgs a;
+    a.rows = c->spec_rows; a.cols = c->spec_cols; a.nn = c->nn; a.fdm = c->p.fdm_z;
+    fill_lin(a.lin, extra);
+    fill_integ(a.integ, g);
+    a.k = c->k;
+    auto kfn = k_integrate;
+    MLV_LAUNCH(kfn, grid1d((size_t)a.rows * a.cols), 256u, 0, c->stream, a);
+    return MLV_OK;
+}
+
+// -------------------------------------------------------- array namespace
+int mlv_elementwise(mlv_ctx* c, const mlv_ew* d) {
+    if (!c || !d || !d->out.ptr) { set_error("mlv_elementwise: null argument"); return MLV_ERR_INVALID; }
+    if (d->rows < 0 || d->cols < 0 || d->op < MLV_EW_ADD || d->op > MLV_EW_POW) {
+        set_error("mlv_elementwise: bad argument");
+        return MLV_ERR_INVALID;
+    }
+    if (d->rows == 0 || d->cols == 0) return MLV_OK;
+    EwArgs a;
+    a.op = d->op; a.rows = d->rows; a.cols = d->cols;
+    a.out.p = d->out.ptr; a.out.rs = d->out.row_stride; a.out.cs = d->out.col_stride; a.out_kind = d->out_kind;
+    a.a.p = d->a.ptr; a.a.rs = d->a.row_stride; a.a.cs = d->a.col_stride; a.a_kind = d->a_kind;
+    a.b.p = d->b.ptr; a.b.rs = d->b.row_stride; a.b.cs = d->b.col_stride; a.b_kind = d->b_kind;
+    a.a_re = d->a_re; a.a_im = d->a_im; a.b_re = d->b_re; a.b_im = d->b_im;
+    auto kfn = k_elementwise;
+    MLV_LAUNCH(kfn, grid1d((size_t)a.rows * a.cols), 256u, 0, c->stream, a);
+    return MLV_OK;
+}
+
+int mlv_reduce(mlv_ctx* c, int op, int rows, int cols, const mlv_view* av, const mlv_view* bv,
+               double* out_dev) {
+    if (!c || !av || !av->ptr || !out_dev) { set_error("mlv_reduce: null argument"); return MLV_ERR_INVALID; }
+    if (op < MLV_RED_SUM || op > MLV_RED_SUMPROD || rows < 1 || cols < 1) {
+        set_error("mlv_reduce: bad argument");
+        return MLV_ERR_INVALID;
+    }
+    if (op == MLV_RED_SUMPROD && (!bv || !bv->ptr)) { set_error("mlv_reduce: second operand missing"); return MLV_ERR_INVALID; }
+    RedArgs a;
+    a.op = op; a.rows = rows; a.cols = cols;
+    a.a.p = av->ptr; a.a.rs = av->row_stride; a.a.cs = av->col_stride;
+    a.b.p = bv ? bv->ptr : nullptr; a.b.rs = bv ? bv->row_stride : 0; a.b.cs = bv ? bv->col_stride : 0;
+    const unsigned grid = grid1d((size_t)rows * cols);
+    if (int rc = ensure_red(c, grid)) return rc;
+    a.partial = c->red;
+    auto kfn = k_reduce;
+    MLV_LAUNCH(kfn, grid, 256u, 256 * sizeof(double), c->stream, a);
+    const int fop = (op == MLV_RED_MAX) ? RED_MAX : (op == MLV_RED_MIN ? RED_MIN : RED_SUM);
+    return reduce_final(c, c->red, (int)grid, 1, 0, fop, out_dev);
+}
+
+}  // extern "C"

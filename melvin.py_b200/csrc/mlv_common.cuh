@@ -1,0 +1,74 @@
+// melvin-b200: common device helpers.
+//
+// The kernels in this directory are written for sm_100a (B200).  For
+// development without a GPU the same sources can be compiled by a host C++
+// compiler with -DMLV_EMU: every CUDA thread of a CTA becomes a fiber and
+// __syncthreads() a yield to the fiber scheduler (tests/emu/).  MLV_EMU is a TEST HARNESS for
+// index logic only -- it is never built into libmelvin_b200.so and there is no
+// CPU fallback in the product.
+#pragma once
+
+#include <stdint.h>
+#include <math.h>
+
+#include "../../include/melvin_b200.h"   // MLV_OK / MLV_ERR_* codes
+
+#ifdef MLV_EMU
+// ------------------------------------------------------------------ emulation
+#include <cstring>
+#include <functional>
+#include <vector>
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define __restrict__
+#define MLV_UNROLL
+struct double2 { double x, y; };
+static inline double2 make_double2(double x, double y) { return double2{x, y}; }
+struct emu_dim3 { unsigned x = 1, y = 1, z = 1; };
+// CTAs run one at a time, their threads as fibers of one OS thread (tests/emu/emu_rt.cpp)
+extern emu_dim3 threadIdx;
+extern emu_dim3 blockIdx;
+extern emu_dim3 blockDim;
+extern emu_dim3 gridDim;
+extern unsigned char* emu_smem_base;
+void __syncthreads();
+#define MLV_SMEM_BASE() (emu_smem_base)
+static inline double __ldg(const double* p) { return *p; }
+static inline double2 __ldg(const double2* p) { return *p; }
+#else
+// ----------------------------------------------------------------------- CUDA
+#include <cuda_runtime.h>
+#define MLV_UNROLL _Pragma("unroll")
+extern __shared__ __align__(16) unsigned char mlv_dyn_smem[];
+#define MLV_SMEM_BASE() (mlv_dyn_smem)
+#endif
+
+#define MLV_DEV __device__ __forceinline__
+#define MLV_HD __host__ __device__ __forceinline__
+
+namespace mlv {
+
+typedef double2 cplx;
+
+MLV_HD cplx mk(double x, double y) { cplx r; r.x = x; r.y = y; return r; }
+MLV_HD cplx cadd(cplx a, cplx b) { return mk(a.x + b.x, a.y + b.y); }
+MLV_HD cplx csub(cplx a, cplx b) { return mk(a.x - b.x, a.y - b.y); }
+MLV_HD cplx cneg(cplx a) { return mk(-a.x, -a.y); }
+MLV_HD cplx cconj(cplx a) { return mk(a.x, -a.y); }
+MLV_HD cplx cscale(cplx a, double s) { return mk(a.x * s, a.y * s); }
+MLV_HD cplx cmul(cplx a, cplx b) {
+    return mk(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+// a * conj(b)
+MLV_HD cplx cmulc(cplx a, cplx b) {
+    return mk(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+// multiply by +i
+MLV_HD cplx cmuli(cplx a) { return mk(-a.y, a.x); }
+// multiply by -i
+MLV_HD cplx cmulni(cplx a) { return mk(a.y, -a.x); }
+
+}  // namespace mlv

@@ -1,0 +1,250 @@
+// melvin-b200: register-resident fp64 Stockham FFT building block.
+//
+// One transform line of N = 2^LOG2N complex128 points is owned by T = N/16
+// threads; every thread keeps 16 points in registers for the whole transform:
+// thread tau holds x[tau + T*j], j = 0..15 on entry and X[tau + T*j] on exit
+// (natural order both ways, so global loads/stores are unit-stride across
+// lanes).  The transform is  [radix R0] -> 16 -> 16 ...  with
+// R0 = 2^(LOG2N mod 4) (or 16): between passes the 16 points are exchanged
+// through shared memory (the only shared-memory traffic of the transform),
+// every butterfly runs in registers.
+//
+// Derivation (self-sorting Cooley-Tukey, decimation in time over the top
+// digit):  N = R*N3, n = N3*d + n'',  X[k1 + R*k'] needs
+//   Y[k1][n''] = W_N^{n'' k1} * sum_d x[N3 d + n''] W_R^{d k1}
+// followed by R independent length-N3 transforms over n''.  With "butterfly
+// beta = n'' + N3*K" (K = already produced low output digits) assigned to
+// thread tau = beta (beta = tau + T*u when R < 16), the results of every pass
+// land at linear slot  beta + (N/R)*d' = tau + T*j : the scatter side of every
+// exchange is the identity layout, only the gather side is strided.  The last
+// gather (stride 16) is made bank-conflict free by padding one slot per 16.
+#pragma once
+
+#include "mlv_common.cuh"
+
+namespace mlv {
+
+#define MLV_MAX_PASS 4
+
+// Per-pass twiddle tables (device pointers).  Table p has (R_p-1)*N3_p entries
+//   tw[(d-1)*N3 + n] = exp(-2 pi i n d / (R_p N3_p));   unused when N3_p == 1.
+struct FftTw {
+    const cplx* p[MLV_MAX_PASS];
+};
+
+template <int LOG2N>
+struct FftCfg {
+    static_assert(LOG2N >= 4 && LOG2N <= 16, "line length 16 .. 65536");
+    static constexpr int N = 1 << LOG2N;
+    static constexpr int T = N / 16;                     // threads per line
+    static constexpr int Q = LOG2N & 3;
+    static constexpr int R0 = Q ? (1 << Q) : 16;         // first-pass radix
+    static constexpr int NPASS = (LOG2N >> 2) + (Q ? 1 : 0);
+    static constexpr int XSLOTS = N + N / 16;            // exchange slots per line
+    // sub-problem length left after pass p
+    __host__ __device__ static constexpr int n3(int p) {
+        int n = N / R0;
+        for (int i = 0; i < p; ++i) n /= 16;
+        return n;
+    }
+    __host__ __device__ static constexpr int radix(int p) { return p == 0 ? R0 : 16; }
+};
+
+// ------------------------------------------------------------- butterflies
+// Forward sign: exp(-2 pi i jk/R).  INV conjugates every twiddle.
+template <bool INV>
+MLV_HD cplx rot_w4(cplx a) { return INV ? cmuli(a) : cmulni(a); }        // * W4^1
+
+template <bool INV>
+MLV_HD cplx mul_w8_1(cplx a) {                                          // * W8^1
+    const double c = 0.70710678118654752440;
+    return INV ? mk(c * (a.x - a.y), c * (a.x + a.y))
+               : mk(c * (a.x + a.y), c * (a.y - a.x));
+}
+template <bool INV>
+MLV_HD cplx mul_w8_3(cplx a) {                                          // * W8^3
+    const double c = 0.70710678118654752440;
+    return INV ? mk(-c * (a.x + a.y), c * (a.x - a.y))
+               : mk(c * (a.y - a.x), -c * (a.x + a.y));
+}
+// * (wr + i wi) forward, * conj for inverse
+template <bool INV>
+MLV_HD cplx mul_w(cplx a, double wr, double wi) {
+    return INV ? cmulc(a, mk(wr, wi)) : cmul(a, mk(wr, wi));
+}
+
+MLV_HD void bfly2(cplx& a, cplx& b) {
+    cplx t = a;
+    a = cadd(t, b);
+    b = csub(t, b);
+}
+
+// natural order in, natural order out
+template <bool INV>
+MLV_HD void bfly4(cplx& a0, cplx& a1, cplx& a2, cplx& a3) {
+    cplx t0 = cadd(a0, a2), t1 = csub(a0, a2);
+    cplx t2 = cadd(a1, a3), t3 = rot_w4<INV>(csub(a1, a3));
+    a0 = cadd(t0, t2);
+    a1 = cadd(t1, t3);
+    a2 = csub(t0, t2);
+    a3 = csub(t1, t3);
+}
+
+template <bool INV>
+MLV_HD void bfly8(cplx (&a)[8]) {
+    bfly2(a[0], a[4]);
+    bfly2(a[1], a[5]);
+    bfly2(a[2], a[6]);
+    bfly2(a[3], a[7]);
+    a[5] = mul_w8_1<INV>(a[5]);
+    a[6] = rot_w4<INV>(a[6]);
+    a[7] = mul_w8_3<INV>(a[7]);
+    bfly4<INV>(a[0], a[1], a[2], a[3]);      // X0 X2 X4 X6
+    bfly4<INV>(a[4], a[5], a[6], a[7]);      // X1 X3 X5 X7
+    cplx x1 = a[4], x2 = a[1], x3 = a[5], x4 = a[2], x5 = a[6], x6 = a[3];
+    a[1] = x1; a[2] = x2; a[3] = x3; a[4] = x4; a[5] = x5; a[6] = x6;
+}
+
+template <bool INV>
+MLV_HD void bfly16(cplx (&a)[16]) {
+    const double c1 = 0.92387953251128675613;   // cos(pi/8)
+    const double s1 = 0.38268343236508977173;   // sin(pi/8)
+    // n = 4 n1 + n2 : four radix-4 over n1 (stride 4) -> a[n2 + 4 k1]
+    MLV_UNROLL
+    for (int n2 = 0; n2 < 4; ++n2) bfly4<INV>(a[n2], a[n2 + 4], a[n2 + 8], a[n2 + 12]);
+    // twiddle a[n2 + 4 k1] *= W16^(n2 k1)
+    a[5] = mul_w<INV>(a[5], c1, -s1);           // e = 1
+    a[6] = mul_w8_1<INV>(a[6]);                 // e = 2
+    a[7] = mul_w<INV>(a[7], s1, -c1);           // e = 3
+    a[9] = mul_w8_1<INV>(a[9]);                 // e = 2
+    a[10] = rot_w4<INV>(a[10]);                 // e = 4
+    a[11] = mul_w8_3<INV>(a[11]);               // e = 6
+    a[13] = mul_w<INV>(a[13], s1, -c1);         // e = 3
+    a[14] = mul_w8_3<INV>(a[14]);               // e = 6
+    a[15] = mul_w<INV>(a[15], -c1, s1);         // e = 9
+    // four radix-4 over n2 -> X[k1 + 4 k2] at a[4 k1 + k2]
+    MLV_UNROLL
+    for (int k1 = 0; k1 < 4; ++k1)
+        bfly4<INV>(a[4 * k1], a[4 * k1 + 1], a[4 * k1 + 2], a[4 * k1 + 3]);
+    // transpose 4x4 to natural order
+    cplx t;
+    t = a[1];  a[1] = a[4];   a[4] = t;
+    t = a[2];  a[2] = a[8];   a[8] = t;
+    t = a[3];  a[3] = a[12];  a[12] = t;
+    t = a[6];  a[6] = a[9];   a[9] = t;
+    t = a[7];  a[7] = a[13];  a[13] = t;
+    t = a[11]; a[11] = a[14]; a[14] = t;
+}
+
+// radix-R butterflies over the 16 registers: U = 16/R interleaved butterflies,
+// butterfly u uses registers u + U*d.
+template <int R, bool INV>
+MLV_HD void pass_butterflies(cplx (&v)[16]) {
+    if constexpr (R == 16) {
+        bfly16<INV>(v);
+    } else if constexpr (R == 8) {
+        MLV_UNROLL
+        for (int u = 0; u < 2; ++u) {
+            cplx a[8];
+            MLV_UNROLL
+            for (int d = 0; d < 8; ++d) a[d] = v[u + 2 * d];
+            bfly8<INV>(a);
+            MLV_UNROLL
+            for (int d = 0; d < 8; ++d) v[u + 2 * d] = a[d];
+        }
+    } else if constexpr (R == 4) {
+        MLV_UNROLL
+        for (int u = 0; u < 4; ++u) bfly4<INV>(v[u], v[u + 4], v[u + 8], v[u + 12]);
+    } else {
+        MLV_UNROLL
+        for (int u = 0; u < 8; ++u) bfly2(v[u], v[u + 8]);
+    }
+}
+
+// v[u + U d] *= W_{R N3}^{n'' d},  n'' = (tau + T u) mod N3
+template <int R, int N3, int T, bool INV>
+MLV_DEV void pass_twiddle(cplx (&v)[16], int tau, const cplx* __restrict__ tw) {
+    constexpr int U = 16 / R;
+    MLV_UNROLL
+    for (int u = 0; u < U; ++u) {
+        const int n = (tau + T * u) & (N3 - 1);
+        MLV_UNROLL
+        for (int d = 1; d < R; ++d) {
+            const cplx w = __ldg(&tw[(d - 1) * N3 + n]);
+            v[u + U * d] = INV ? cmulc(v[u + U * d], w) : cmul(v[u + U * d], w);
+        }
+    }
+}
+
+// ------------------------------------------------------ exchange policies
+// Full complex128 exchange buffer shared by C interleaved lines (x passes):
+// slot L of line c lives at buf[L*C + c].  Two barriers per exchange.
+template <int C>
+struct XchgFull {
+    cplx* buf;
+    int c;
+    template <class WI, class RI>
+    MLV_DEV void exchange(cplx (&v)[16], WI wi, RI ri) {
+        __syncthreads();
+        MLV_UNROLL
+        for (int j = 0; j < 16; ++j) buf[wi(j) * C + c] = v[j];
+        __syncthreads();
+        MLV_UNROLL
+        for (int j = 0; j < 16; ++j) v[j] = buf[ri(j) * C + c];
+    }
+};
+
+// Half-size exchange buffer (N+N/16 doubles per line): real parts, then
+// imaginary parts.  Four barriers per exchange, half the shared memory.
+struct XchgSplit {
+    double* buf;
+    template <class WI, class RI>
+    MLV_DEV void exchange(cplx (&v)[16], WI wi, RI ri) {
+        __syncthreads();
+        MLV_UNROLL
+        for (int j = 0; j < 16; ++j) buf[wi(j)] = v[j].x;
+        __syncthreads();
+        MLV_UNROLL
+        for (int j = 0; j < 16; ++j) v[j].x = buf[ri(j)];
+        __syncthreads();
+        MLV_UNROLL
+        for (int j = 0; j < 16; ++j) buf[wi(j)] = v[j].y;
+        __syncthreads();
+        MLV_UNROLL
+        for (int j = 0; j < 16; ++j) v[j].y = buf[ri(j)];
+    }
+};
+
+// ------------------------------------------------------------ the transform
+template <int LOG2N, int P, bool INV, class X>
+MLV_DEV void fft_later_passes(cplx (&v)[16], const int tau, const FftTw& tw, X& xc) {
+    typedef FftCfg<LOG2N> C;
+    constexpr int N3 = C::n3(P);            // length left after this pass
+    constexpr bool PAD = (N3 == 1);         // stride-16 gather: pad 1 per 16
+    const int lo = tau & (N3 - 1);
+    const int hi = tau / N3;
+    xc.exchange(
+        v,
+        [&](int j) { const int L = tau + C::T * j; return PAD ? L + (L >> 4) : L; },
+        [&](int j) { const int L = lo + N3 * j + 16 * N3 * hi; return PAD ? L + (L >> 4) : L; });
+    bfly16<INV>(v);
+    if constexpr (N3 > 1) {
+        pass_twiddle<16, N3, C::T, INV>(v, tau, tw.p[P]);
+        fft_later_passes<LOG2N, P + 1, INV, X>(v, tau, tw, xc);
+    }
+}
+
+// In-register transform of one line.  All T threads of the line (and all
+// other lines sharing the CTA) must call this together (it contains CTA
+// barriers).  INV = unnormalised inverse (sum with exp(+...)).
+template <int LOG2N, bool INV, class X>
+MLV_DEV void fft_line(cplx (&v)[16], const int tau, const FftTw& tw, X& xc) {
+    typedef FftCfg<LOG2N> C;
+    pass_butterflies<C::R0, INV>(v);
+    if constexpr (C::NPASS > 1) {
+        pass_twiddle<C::R0, C::n3(0), C::T, INV>(v, tau, tw.p[0]);
+        fft_later_passes<LOG2N, 1, INV, X>(v, tau, tw, xc);
+    }
+}
+
+}  // namespace mlv

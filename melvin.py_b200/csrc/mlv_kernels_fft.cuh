@@ -1,0 +1,562 @@
+// melvin-b200: FFT-based kernels of the pseudo-spectral step.
+//
+// Data layouts (all row-major, last index contiguous):
+//   S  spectral   (2nn+1, nm) complex128, rows n = 0..nn,-nn..-1   [API layout,
+//                  reference melvin/ArrayFactory.py:8-45]
+//   P  physical   (nx, nz) float64                                  [API layout]
+//   I  x-transformed intermediate (nx, ipitch>=nm) complex128       [private]
+//   FDM-z mode:  S_f (nn, nz) complex128 <-> P, one 1-D transform along x.
+//
+// A 2-D transform is an x pass (complex, strided columns, C adjacent columns per
+// CTA so that every global access is a C*16-byte segment) and a z pass (two real
+// rows packed into one complex line; contiguous).  Pruning (2/3 rule) and all
+// scaling happen in the load/store of the passes; no padded array ever exists.
+#pragma once
+
+#include "mlv_fft.cuh"
+
+namespace mlv {
+
+// ---------------------------------------------------------------- op codes
+// Diagonal spectral operators: value = g(n, m) * src[n][m].
+enum {
+    XOP_IDENT = 0,
+    XOP_PSI = 1,   // psi = (-w)/lap, lap(0,0) := 1   (LaplacianSolver.py:58-68, utility.py:65)
+    XOP_UX = 2,    // ux  = -(i kz m) psi             (utility.py:71, SpatialDifferentiator.py:55)
+    XOP_UZ = 3,    // uz  =  (i kx n) psi             (utility.py:78, SpatialDifferentiator.py:50)
+    XOP_DDX = 4,   // (i kx n) src                    (SpatialDifferentiator.py:50)
+    XOP_DDZ = 5,   // (i kz m) src                    (SpatialDifferentiator.py:55)
+    XOP_D2DX2 = 6, // d2x n^2 src                     (SpatialDifferentiator.py:60)
+    XOP_D2DZ2 = 7, // d2z m^2 src                     (SpatialDifferentiator.py:65)
+    XOP_LAP = 8,   // (d2x n^2 + d2z m^2) src         (Variable.py:111-113)
+    XOP_INVLAP = 9 // src / lap, lap(0,0) := 1        (LaplacianSolver.py:58-68)
+};
+// Multiplier symbols of the forward x pass epilogue.
+enum {
+    XSYM_ONE = 0,
+    XSYM_FDX = 1,  // Fourier symbol of the central x stencil (order 2/4), table symx[k]
+    XSYM_FDZ = 2,  // Fourier symbol of the central z stencil, table symz[m]
+};
+
+struct SpecConsts {
+    double kx0, kz0;   // 2 pi / lx, 2 pi / lz
+    double d2x, d2z;   // -(2 pi)^2/lx^2, -(2 pi)^2/lz^2
+};
+
+MLV_DEV double lap_symbol(int n, int m, const SpecConsts& k) {
+    return k.d2x * ((double)n * (double)n) + k.d2z * ((double)m * (double)m);
+}
+
+MLV_DEV cplx spectral_op(int op, cplx s, int n, int m, const SpecConsts& k) {
+    switch (op) {
+        case XOP_IDENT: return s;
+        case XOP_DDX: { const double b = k.kx0 * n; return mk(-b * s.y, b * s.x); }
+        case XOP_DDZ: { const double b = k.kz0 * m; return mk(-b * s.y, b * s.x); }
+        case XOP_D2DX2: { const double b = k.d2x * ((double)n * (double)n); return mk(b * s.x, b * s.y); }
+        case XOP_D2DZ2: { const double b = k.d2z * ((double)m * (double)m); return mk(b * s.x, b * s.y); }
+        case XOP_LAP: { const double b = lap_symbol(n, m, k); return mk(b * s.x, b * s.y); }
+        default: break;
+    }
+    double lap = lap_symbol(n, m, k);
+    if (n == 0 && m == 0) lap = 1.0;
+    if (op == XOP_INVLAP) return mk(s.x / lap, s.y / lap);
+    const cplx psi = mk(-s.x / lap, -s.y / lap);
+    if (op == XOP_PSI) return psi;
+    if (op == XOP_UX) { const double b = k.kz0 * m; return mk(b * psi.y, -b * psi.x); }
+    /* XOP_UZ */ { const double b = k.kx0 * n; return mk(-b * psi.y, b * psi.x); }
+}
+
+// FFT index k (0..N-1) -> spectral row r and signed mode n; false if truncated.
+MLV_DEV bool xrow_of(int k, int N, int nn, int& r, int& n) {
+    if (k <= nn) { r = k; n = k; return true; }
+    if (k >= N - nn) { n = k - N; r = n + 2 * nn + 1; return true; }
+    return false;
+}
+
+// ------------------------------------------------------ time integration
+// One spectral coefficient of Integrator.py:5-18 (AB2/AB4 predictor) and
+// :53-63 (explicit / theta-scheme update).  History levels are passed oldest
+// last; unused levels are ignored.
+struct IntegArgs {
+    int ab_order;      // 2 or 4
+    int scheme;        // 0: semi-implicit, L = lcoef*lap symbol; 1: semi-implicit, L from array
+                       // 2: explicit (q += AB)
+    double dt, alpha, lcoef;
+    const double* larr;        // scheme 1: real (spectral-shaped) linear operator
+    const cplx* q_in;
+    cplx* q_out;
+    cplx* f0;                  // current history level (written by the caller, read here)
+    const cplx* fm1;
+    const cplx* fm2;
+    const cplx* fm3;
+};
+
+MLV_DEV cplx ab_predict(const IntegArgs& g, cplx f0, size_t idx) {
+    if (g.ab_order == 2) {
+        const cplx f1 = g.fm1[idx];
+        const double h = g.dt / 2;
+        return mk(h * (3 * f0.x - f1.x), h * (3 * f0.y - f1.y));
+    }
+    const cplx f1 = g.fm1[idx], f2 = g.fm2[idx], f3 = g.fm3[idx];
+    const double h = g.dt / 24;
+    return mk(h * (55 * f0.x - 59 * f1.x + 37 * f2.x - 9 * f3.x),
+              h * (55 * f0.y - 59 * f1.y + 37 * f2.y - 9 * f3.y));
+}
+
+MLV_DEV void integrate_point(const IntegArgs& g, cplx f0, size_t idx, int n, int m,
+                             const SpecConsts& k) {
+    const cplx inc = ab_predict(g, f0, idx);
+    const cplx q = g.q_in[idx];
+    if (g.scheme == 2) {
+        g.q_out[idx] = cadd(q, inc);
+        return;
+    }
+    const double L = (g.scheme == 0) ? g.lcoef * lap_symbol(n, m, k) : g.larr[idx];
+    const double a = 1 + ((1 - g.alpha) * g.dt) * L;
+    const double b = 1 - (g.alpha * g.dt) * L;
+    g.q_out[idx] = mk((a * q.x + inc.x) / b, (a * q.y + inc.y) / b);
+}
+
+// Extra linear right-hand-side terms  sum_i coef_i * op_i(src_i)
+#define MLV_MAXLIN 4
+struct LinTerms {
+    int n;
+    const cplx* src[MLV_MAXLIN];
+    int op[MLV_MAXLIN];
+    double cre[MLV_MAXLIN], cim[MLV_MAXLIN];   // complex coefficient
+};
+
+MLV_DEV cplx lin_terms_at(const LinTerms& lt, size_t idx, int n, int m, const SpecConsts& k) {
+    cplx acc = mk(0.0, 0.0);
+    for (int i = 0; i < lt.n; ++i) {
+        const cplx t = spectral_op(lt.op[i], lt.src[i][idx], n, m, k);
+        acc = cadd(acc, cmul(mk(lt.cre[i], lt.cim[i]), t));
+    }
+    return acc;
+}
+
+// ===================================================================== x inverse
+#define MLV_XMAXF 4
+struct XInvArgs {
+    int nn, nm, spitch, ipitch, nf;
+    const cplx* src[MLV_XMAXF];
+    int op[MLV_XMAXF];
+    cplx* dst[MLV_XMAXF];
+    SpecConsts k;
+    FftTw tw;
+};
+
+// spectral (2nn+1, nm) -> I (nx, ipitch); nf fields, each with its own prologue
+template <int LOG2N, int C>
+__global__ void __launch_bounds__(C * FftCfg<LOG2N>::T, 1)
+k_xinv(const XInvArgs a) {
+    typedef FftCfg<LOG2N> F;
+    const int c = threadIdx.x % C, tau = threadIdx.x / C;
+    const int m = blockIdx.x * C + c;
+    const bool valid = m < a.nm;
+    XchgFull<C> xc;
+    xc.buf = reinterpret_cast<cplx*>(MLV_SMEM_BASE());
+    xc.c = c;
+    for (int f = 0; f < a.nf; ++f) {
+        cplx v[16];
+        const cplx* __restrict__ src = a.src[f];
+        const int op = a.op[f];
+        MLV_UNROLL
+        for (int j = 0; j < 16; ++j) {
+            const int kk = tau + F::T * j;
+            int r, n;
+            v[j] = mk(0.0, 0.0);
+            if (valid && xrow_of(kk, F::N, a.nn, r, n))
+                v[j] = spectral_op(op, src[(size_t)r * a.spitch + m], n, m, a.k);
+        }
+        fft_line<LOG2N, true>(v, tau, a.tw, xc);
+        if (valid) {
+            cplx* __restrict__ dst = a.dst[f];
+            MLV_UNROLL
+            for (int j = 0; j < 16; ++j) dst[(size_t)(tau + F::T * j) * a.ipitch + m] = v[j];
+        }
+    }
+}
+
+// ===================================================================== x forward
+struct XFwdArgs {
+    int nn, nm, spitch, ipitch, nf;
+    const cplx* src[MLV_XMAXF];
+    int sym[MLV_XMAXF];
+    double coef[MLV_XMAXF];      // real coefficient per field
+    const double* symx;          // [N]  imaginary part of the x stencil symbol per FFT index
+    const double* symz;          // [nm] imaginary part of the z stencil symbol
+    double scale;                // 1/(nx nz)
+    int mode;                    // 0: dst = value; 1: f0 = value + lin terms, then integrate
+    cplx* dst;                   // mode 0: spectral (2nn+1, nm)
+    LinTerms lin;                // mode 1
+    IntegArgs integ;             // mode 1
+    SpecConsts k;
+    FftTw tw;
+};
+
+// I (nx, ipitch) x nf -> spectral: value = scale * sum_f coef_f * sym_f * FFT_x(src_f),
+// rows truncated to |n| <= nn.  With nf > 1 partial sums are kept in a
+// thread-private shared-memory stash indexed by spectral row.
+template <int LOG2N, int C>
+__global__ void __launch_bounds__(C * FftCfg<LOG2N>::T, 1)
+k_xfwd(const XFwdArgs a) {
+    typedef FftCfg<LOG2N> F;
+    const int c = threadIdx.x % C, tau = threadIdx.x / C;
+    const int m = blockIdx.x * C + c;
+    const bool valid = m < a.nm;
+    XchgFull<C> xc;
+    xc.buf = reinterpret_cast<cplx*>(MLV_SMEM_BASE());
+    xc.c = c;
+    cplx* stash = xc.buf + (size_t)F::XSLOTS * C;     // (2nn+1)*C entries, used when nf > 1
+    const double sz = valid ? a.symz[m] : 0.0;
+    for (int f = 0; f < a.nf; ++f) {
+        cplx v[16];
+        const cplx* __restrict__ src = a.src[f];
+        MLV_UNROLL
+        for (int j = 0; j < 16; ++j) {
+            v[j] = mk(0.0, 0.0);
+            if (valid) v[j] = src[(size_t)(tau + F::T * j) * a.ipitch + m];
+        }
+        fft_line<LOG2N, false>(v, tau, a.tw, xc);
+        if (!valid) continue;
+        const int sym = a.sym[f];
+        const double cf = a.coef[f] * a.scale;
+        const bool last = (f + 1 == a.nf);
+        MLV_UNROLL
+        for (int j = 0; j < 16; ++j) {
+            const int kk = tau + F::T * j;
+            int r, n;
+            if (!xrow_of(kk, F::N, a.nn, r, n)) continue;
+            cplx t;
+            if (sym == XSYM_ONE) {
+                t = cscale(v[j], cf);
+            } else {
+                const double s = (sym == XSYM_FDX ? a.symx[kk] : sz) * cf;
+                t = mk(-s * v[j].y, s * v[j].x);          // * (i s)
+            }
+            if (f > 0) t = cadd(stash[(size_t)r * C + c], t);
+            if (!last) {
+                stash[(size_t)r * C + c] = t;
+                continue;
+            }
+            const size_t idx = (size_t)r * a.spitch + m;
+            if (a.mode == 0) {
+                a.dst[idx] = t;
+            } else {
+                const cplx f0 = cadd(t, lin_terms_at(a.lin, idx, n, m, a.k));
+                a.integ.f0[idx] = f0;
+                integrate_point(a.integ, f0, idx, n, m, a.k);
+            }
+        }
+    }
+}
+
+// ===================================================================== z passes
+// Packed-pair element idx of the Hermitian-extended spectrum of two real rows
+// whose one-sided spectra are rowA, rowB (F4: Im of the m=0 bin is dropped).
+MLV_DEV cplx zpair_load(const cplx* __restrict__ rowA, const cplx* __restrict__ rowB,
+                        int idx, int N, int nm) {
+    if (idx < nm) {
+        const cplx A = rowA[idx], B = rowB[idx];
+        if (idx == 0) return mk(A.x, B.x);
+        return mk(A.x - B.y, A.y + B.x);                 // A + iB
+    }
+    if (idx > N - nm) {
+        const cplx A = rowA[N - idx], B = rowB[N - idx];
+        return mk(A.x + B.y, B.x - A.y);                 // conj(A) + i conj(B)
+    }
+    return mk(0.0, 0.0);
+}
+
+// After a forward transform of z = a + ib every thread holds Zf[tau + T j].
+// Publishes the upper part (index > N-nm) to `pbuf` so that the owner of
+// output k can read Zf[N-k] from pbuf[k].  Caller must __syncthreads() between
+// publish and unpack (and before pbuf is reused).
+template <int LOG2N>
+MLV_DEV void zpair_publish(const cplx (&v)[16], int tau, int nm, cplx* pbuf) {
+    typedef FftCfg<LOG2N> F;
+    MLV_UNROLL
+    for (int j = 0; j < 16; ++j) {
+        const int kk = tau + F::T * j;
+        if (kk > F::N - nm) pbuf[F::N - kk] = v[j];
+    }
+}
+// One-sided spectra of the two rows at index k (k < nm), given Zk and P = Zf[N-k]
+MLV_DEV void zpair_unpack(cplx Zk, cplx P, cplx& A, cplx& B) {
+    A = mk(0.5 * (Zk.x + P.x), 0.5 * (Zk.y - P.y));
+    B = mk(0.5 * (Zk.y + P.y), -0.5 * (Zk.x - P.x));
+}
+
+struct ZArgs {
+    int nx, nm, ipitch;
+    const cplx* I;     // c2r input / unused
+    cplx* Iout;        // r2c output
+    const double* Pin; // r2c input
+    double* P;         // c2r output (nx, nz)
+    FftTw tw;
+};
+
+// I (nx, ipitch) -> P (nx, nz): inverse z pass, two rows per line
+template <int LOG2N, int LPC>
+__global__ void __launch_bounds__(LPC * FftCfg<LOG2N>::T, (LPC * FftCfg<LOG2N>::T <= 256) ? 2 : 1)
+k_z_c2r(const ZArgs a) {
+    typedef FftCfg<LOG2N> F;
+    const int l = threadIdx.x / F::T, tau = threadIdx.x % F::T;
+    const int rp = blockIdx.x * LPC + l;
+    const bool valid = 2 * rp < a.nx;
+    XchgSplit xc;
+    xc.buf = reinterpret_cast<double*>(MLV_SMEM_BASE()) + (size_t)l * F::XSLOTS;
+    const cplx* rowA = a.I + (size_t)(2 * rp) * a.ipitch;
+    const cplx* rowB = rowA + a.ipitch;
+    cplx v[16];
+    MLV_UNROLL
+    for (int j = 0; j < 16; ++j)
+        v[j] = valid ? zpair_load(rowA, rowB, tau + F::T * j, F::N, a.nm) : mk(0.0, 0.0);
+    fft_line<LOG2N, true>(v, tau, a.tw, xc);
+    if (valid) {
+        double* pa = a.P + (size_t)(2 * rp) * F::N;
+        double* pb = pa + F::N;
+        MLV_UNROLL
+        for (int j = 0; j < 16; ++j) {
+            pa[tau + F::T * j] = v[j].x;
+            pb[tau + F::T * j] = v[j].y;
+        }
+    }
+}
+
+// P (nx, nz) -> I (nx, ipitch): forward z pass (unnormalised), truncated to m < nm
+template <int LOG2N, int LPC>
+__global__ void __launch_bounds__(LPC * FftCfg<LOG2N>::T, (LPC * FftCfg<LOG2N>::T <= 256) ? 2 : 1)
+k_z_r2c(const ZArgs a) {
+    typedef FftCfg<LOG2N> F;
+    const int l = threadIdx.x / F::T, tau = threadIdx.x % F::T;
+    const int rp = blockIdx.x * LPC + l;
+    const bool valid = 2 * rp < a.nx;
+    XchgSplit xc;
+    xc.buf = reinterpret_cast<double*>(MLV_SMEM_BASE()) + (size_t)l * F::XSLOTS;
+    cplx v[16];
+    {
+        const double* pa = a.Pin + (size_t)(2 * rp) * F::N;
+        const double* pb = pa + F::N;
+        MLV_UNROLL
+        for (int j = 0; j < 16; ++j)
+            v[j] = valid ? mk(pa[tau + F::T * j], pb[tau + F::T * j]) : mk(0.0, 0.0);
+    }
+    fft_line<LOG2N, false>(v, tau, a.tw, xc);
+    cplx* pbuf = reinterpret_cast<cplx*>(xc.buf);
+    __syncthreads();
+    zpair_publish<LOG2N>(v, tau, a.nm, pbuf);
+    __syncthreads();
+    if (valid) {
+        cplx* oa = a.Iout + (size_t)(2 * rp) * a.ipitch;
+        cplx* ob = oa + a.ipitch;
+        MLV_UNROLL
+        for (int j = 0; j < 16; ++j) {
+            const int kk = tau + F::T * j;
+            if (kk < a.nm) {
+                const cplx P = (kk == 0) ? v[j] : pbuf[kk];
+                cplx A, B;
+                zpair_unpack(v[j], P, A, B);
+                oa[kk] = A;
+                ob[kk] = B;
+            }
+        }
+    }
+}
+
+// ============================================================ 1-D x transforms
+// Fourier-x / finite-difference-z mode (SpectralTransformer.py:33-88): spectral
+// arrays are (nn, nz) with modes n = 0..nn-1, the transform runs along x only and
+// is real-to-complex.  Two adjacent z columns are packed into one complex line.
+struct X1dArgs {
+    int nn, nz;
+    const cplx* S;       // c2r input  (nn, nz)
+    double* P;           // c2r output (nx, nz)
+    const double* Pin;   // r2c input
+    cplx* Sout;          // r2c output
+    double scale;        // r2c: 1/nx
+    FftTw tw;
+};
+
+template <int LOG2N, int C>
+__global__ void __launch_bounds__(C * FftCfg<LOG2N>::T, 1)
+k_x1d_c2r(const X1dArgs a) {
+    typedef FftCfg<LOG2N> F;
+    const int c = threadIdx.x % C, tau = threadIdx.x / C;
+    const int z0 = 2 * (blockIdx.x * C + c);
+    const bool valid = z0 < a.nz, has2 = z0 + 1 < a.nz;
+    XchgFull<C> xc;
+    xc.buf = reinterpret_cast<cplx*>(MLV_SMEM_BASE());
+    xc.c = c;
+    cplx v[16];
+    MLV_UNROLL
+    for (int j = 0; j < 16; ++j) {
+        const int kk = tau + F::T * j;
+        v[j] = mk(0.0, 0.0);
+        if (!valid) continue;
+        if (kk < a.nn) {
+            const cplx A = a.S[(size_t)kk * a.nz + z0];
+            const cplx B = has2 ? a.S[(size_t)kk * a.nz + z0 + 1] : mk(0.0, 0.0);
+            v[j] = (kk == 0) ? mk(A.x, B.x) : mk(A.x - B.y, A.y + B.x);
+        } else if (kk > F::N - a.nn) {
+            const int mm = F::N - kk;
+            const cplx A = a.S[(size_t)mm * a.nz + z0];
+            const cplx B = has2 ? a.S[(size_t)mm * a.nz + z0 + 1] : mk(0.0, 0.0);
+            v[j] = mk(A.x + B.y, B.x - A.y);
+        }
+    }
+    fft_line<LOG2N, true>(v, tau, a.tw, xc);
+    if (valid) {
+        MLV_UNROLL
+        for (int j = 0; j < 16; ++j) {
+            double* o = a.P + (size_t)(tau + F::T * j) * a.nz + z0;
+            o[0] = v[j].x;
+            if (has2) o[1] = v[j].y;
+        }
+    }
+}
+
+template <int LOG2N, int C>
+__global__ void __launch_bounds__(C * FftCfg<LOG2N>::T, 1)
+k_x1d_r2c(const X1dArgs a) {
+    typedef FftCfg<LOG2N> F;
+    const int c = threadIdx.x % C, tau = threadIdx.x / C;
+    const int z0 = 2 * (blockIdx.x * C + c);
+    const bool valid = z0 < a.nz, has2 = z0 + 1 < a.nz;
+    XchgFull<C> xc;
+    xc.buf = reinterpret_cast<cplx*>(MLV_SMEM_BASE());
+    xc.c = c;
+    cplx v[16];
+    MLV_UNROLL
+    for (int j = 0; j < 16; ++j) {
+        v[j] = mk(0.0, 0.0);
+        if (valid) {
+            const double* in = a.Pin + (size_t)(tau + F::T * j) * a.nz + z0;
+            v[j] = mk(in[0], has2 ? in[1] : 0.0);
+        }
+    }
+    fft_line<LOG2N, false>(v, tau, a.tw, xc);
+    __syncthreads();
+    MLV_UNROLL
+    for (int j = 0; j < 16; ++j) {
+        const int kk = tau + F::T * j;
+        if (kk > F::N - a.nn) xc.buf[(size_t)(F::N - kk) * C + c] = v[j];
+    }
+    __syncthreads();
+    if (valid) {
+        MLV_UNROLL
+        for (int j = 0; j < 16; ++j) {
+            const int kk = tau + F::T * j;
+            if (kk < a.nn) {
+                const cplx P = (kk == 0) ? v[j] : xc.buf[(size_t)kk * C + c];
+                cplx A, B;
+                zpair_unpack(v[j], P, A, B);
+                cplx* o = a.Sout + (size_t)kk * a.nz + z0;
+                o[0] = cscale(A, a.scale);
+                if (has2) o[1] = cscale(B, a.scale);
+            }
+        }
+    }
+}
+
+// ============================================================ fused z stage
+// The physical-space stage of Variable.vec_dot_nabla (Variable.py:119-128):
+//   inverse z pass of ux, uz, q  ->  A = ux*q, B = uz*q  ->  forward z pass of
+//   A and B (truncated to m < nm).
+// The two derivatives d/dx(A) + d/dz(B) of the conservative form are applied
+// later as the exact Fourier symbols of the reference's central stencils
+// (SpatialDifferentiator.py:76-185) in the forward x pass.
+// Also produces the reductions the tickers need (Integrator.py:35-44 signed max
+// of ux, uz; utility.py:42-59 sum ux^2, uz^2) as per-CTA partials.
+struct ZAdvArgs {
+    int nx, nm, ipitch;
+    const cplx* Iux;
+    const cplx* Iuz;
+    const cplx* Iq;
+    cplx* IA;                      // out: z-spectrum of ux q   (nx, ipitch)
+    cplx* IB;                      // out: z-spectrum of uz q
+    double* red;                   // [gridDim.x][4] partials: max ux, max uz, sum ux^2, sum uz^2
+    FftTw tw;
+};
+
+template <int LOG2N, int LPC>
+__global__ void __launch_bounds__(LPC * FftCfg<LOG2N>::T, (LPC * FftCfg<LOG2N>::T <= 256) ? 2 : 1)
+k_z_advect(const ZAdvArgs a) {
+    typedef FftCfg<LOG2N> F;
+    const int l = threadIdx.x / F::T, tau = threadIdx.x % F::T;
+    const int rp = blockIdx.x * LPC + l;
+    const bool valid = 2 * rp < a.nx;
+    // shared memory: [ LPC * XSLOTS doubles exchange | LPC * N cplx thread-private stash ]
+    unsigned char* base = MLV_SMEM_BASE();
+    XchgSplit xc;
+    xc.buf = reinterpret_cast<double*>(base) + (size_t)l * F::XSLOTS;
+    cplx* stash = reinterpret_cast<cplx*>(base + (size_t)LPC * F::XSLOTS * sizeof(double)) +
+                  (size_t)l * F::N;
+    cplx* pbuf = reinterpret_cast<cplx*>(xc.buf);
+    const size_t rowoff = (size_t)(2 * rp) * a.ipitch;
+
+    double red[4] = {-INFINITY, -INFINITY, 0.0, 0.0};
+    cplx v[16];
+    {   // q -> physical, parked in the thread-private stash
+        const cplx* rowA = a.Iq + rowoff;
+        MLV_UNROLL
+        for (int j = 0; j < 16; ++j)
+            v[j] = valid ? zpair_load(rowA, rowA + a.ipitch, tau + F::T * j, F::N, a.nm) : mk(0.0, 0.0);
+        fft_line<LOG2N, true>(v, tau, a.tw, xc);
+        MLV_UNROLL
+        for (int j = 0; j < 16; ++j) stash[j * F::T + tau] = v[j];
+    }
+    for (int pass = 0; pass < 2; ++pass) {        // pass 0: A = ux q, pass 1: B = uz q
+        const cplx* src = (pass == 0 ? a.Iux : a.Iuz) + rowoff;
+        MLV_UNROLL
+        for (int j = 0; j < 16; ++j)
+            v[j] = valid ? zpair_load(src, src + a.ipitch, tau + F::T * j, F::N, a.nm) : mk(0.0, 0.0);
+        fft_line<LOG2N, true>(v, tau, a.tw, xc);
+        double mx = -INFINITY, ss = 0.0;
+        MLV_UNROLL
+        for (int j = 0; j < 16; ++j) {
+            mx = fmax(mx, fmax(v[j].x, v[j].y));
+            ss += v[j].x * v[j].x + v[j].y * v[j].y;
+            const cplx q = stash[j * F::T + tau];
+            v[j] = mk(v[j].x * q.x, v[j].y * q.y);
+        }
+        red[pass] = mx;
+        red[2 + pass] = ss;
+        fft_line<LOG2N, false>(v, tau, a.tw, xc);
+        __syncthreads();
+        zpair_publish<LOG2N>(v, tau, a.nm, pbuf);
+        __syncthreads();
+        if (valid) {
+            cplx* oa = (pass == 0 ? a.IA : a.IB) + rowoff;
+            cplx* ob = oa + a.ipitch;
+            MLV_UNROLL
+            for (int j = 0; j < 16; ++j) {
+                const int kk = tau + F::T * j;
+                if (kk < a.nm) {
+                    const cplx P = (kk == 0) ? v[j] : pbuf[kk];
+                    cplx A, B;
+                    zpair_unpack(v[j], P, A, B);
+                    oa[kk] = A;
+                    ob[kk] = B;
+                }
+            }
+        }
+    }
+    // ---- reductions: per-CTA partials (deterministic two-stage reduction)
+    __syncthreads();
+    double* rbuf = reinterpret_cast<double*>(base);      // reuse exchange area: 4*blockDim doubles
+    const int nt = blockDim.x;
+    if (!valid) { red[0] = red[1] = -INFINITY; red[2] = red[3] = 0.0; }
+    MLV_UNROLL
+    for (int w = 0; w < 4; ++w) rbuf[w * nt + threadIdx.x] = red[w];
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        const int w = threadIdx.x;
+        double r = rbuf[w * nt];
+        for (int i = 1; i < nt; ++i) r = (w < 2) ? fmax(r, rbuf[w * nt + i]) : r + rbuf[w * nt + i];
+        a.red[(size_t)blockIdx.x * 4 + w] = r;
+    }
+}
+
+}  // namespace mlv

@@ -1,0 +1,204 @@
+"""Process-wide binding to libmelvin_b200.so and to the device allocator.
+
+torch is used for exactly three things: device memory (tensors own every field
+buffer), the CUDA stream handle and host<->device copies.  All arithmetic on
+those buffers goes through the C ABI in ``include/melvin_b200.h``.
+
+There is NO CPU path: if the shared library or a CUDA device is missing the
+first operation raises.  (``_install`` lets the test-suite point the binding at
+the host *emulation* build of the kernels; product code never does that.)
+"""
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+from . import _capi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libmelvin_b200.so")
+
+_state = {"lib": None, "device": None, "launches": 0, "calls": {}}
+
+
+class BackendUnavailable(RuntimeError):
+    pass
+
+
+def _install(lib, device):
+    """Bind an already loaded library handle and a torch device (tests only)."""
+    _state["lib"] = _capi.declare(lib)
+    _state["device"] = torch.device(device)
+
+
+def _load_default():
+    if not os.path.exists(LIB_PATH):
+        raise BackendUnavailable(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). melvin-b200 has no CPU fallback.")
+    if not torch.cuda.is_available():
+        raise BackendUnavailable("melvin-b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    _install(ctypes.CDLL(LIB_PATH), "cuda")
+
+
+def lib():
+    if _state["lib"] is None:
+        _load_default()
+    return _state["lib"]
+
+
+def device():
+    if _state["device"] is None:
+        _load_default()
+    return _state["device"]
+
+
+def is_cuda():
+    return device().type == "cuda"
+
+
+def count_launch(n=1):
+    _state["launches"] += n
+
+
+def launches():
+    """Number of library calls that enqueued kernels since process start."""
+    return _state["launches"]
+
+
+def call_counts():
+    """Per-entry-point call counts (copy)."""
+    return dict(_state["calls"])
+
+
+def current_stream_handle():
+    if is_cuda():
+        return torch.cuda.current_stream().cuda_stream
+    return 0
+
+
+# --------------------------------------------------------------- allocation
+_TORCH_DTYPE = {np.dtype(np.float64): torch.float64, np.dtype(np.complex128): torch.complex128,
+                np.dtype(np.int64): torch.int64}
+
+
+def torch_dtype(dtype):
+    dt = np.dtype(dtype)
+    if dt not in _TORCH_DTYPE:
+        raise TypeError(f"melvin-b200 arrays are float64 / complex128 (got {dt}); "
+                        "single precision is not implemented")
+    return _TORCH_DTYPE[dt]
+
+
+def empty(shape, dtype):
+    return torch.empty(tuple(shape), dtype=torch_dtype(dtype), device=device())
+
+
+def zeros(shape, dtype):
+    return torch.zeros(tuple(shape), dtype=torch_dtype(dtype), device=device())
+
+
+def from_host(arr, dtype=None):
+    a = np.ascontiguousarray(arr, dtype=dtype)
+    if a.dtype not in _TORCH_DTYPE:
+        a = a.astype(np.complex128 if np.iscomplexobj(a) else np.float64)
+    t = torch.from_numpy(a)
+    if is_cuda():
+        return t.to(device(), non_blocking=False)
+    return t.clone()
+
+
+def to_host(t):
+    return t.detach().cpu().numpy() if t.device.type != "cpu" else t.detach().numpy().copy()
+
+
+def synchronize():
+    if is_cuda():
+        torch.cuda.synchronize()
+
+
+# ------------------------------------------------------------------ context
+class Context:
+    """One mlv_ctx per Parameters object (plans for one grid)."""
+
+    def __init__(self, nx, nz, lx, lz, fdm_z, fd_order):
+        self.lib = lib()
+        p = _capi.Params()
+        p.nx, p.nz, p.fdm_z, p.fd_order = int(nx), int(nz), int(bool(fdm_z)), int(fd_order)
+        p.lx, p.lz = float(lx), float(lz)
+        # reference: melvin/BasisFunctions.py:26-59 (COMPLEX_EXP factors)
+        p.kx0 = float(np.abs(1j * 2 * np.pi / lx))
+        p.kz0 = float(np.abs(1j * 2 * np.pi / lz))
+        p.d2x = float(-np.abs(1j * 2 * np.pi) ** 2 / lx ** 2)
+        p.d2z = float(-np.abs(1j * 2 * np.pi) ** 2 / lz ** 2)
+        h = ctypes.c_void_p()
+        _capi.check(self.lib, self.lib.mlv_create(ctypes.byref(p), ctypes.byref(h)))
+        self.handle = h
+        info = _capi.Info()
+        _capi.check(self.lib, self.lib.mlv_get_info(h, ctypes.byref(info)))
+        self.nn, self.nm = info.nn, info.nm
+        self.spec_shape = (info.spec_rows, info.spec_cols)
+        self.ipitch = info.ipitch
+        self.nx, self.nz = int(nx), int(nz)
+        self.fdm_z = bool(fdm_z)
+        self.fd_order = int(fd_order)
+        self.dx, self.dz = lx / nx, lz / nz
+        self._ipool = []
+        self._scratch_i = None
+        self._red4 = None
+        self.set_stream(current_stream_handle())
+
+    def set_stream(self, handle):
+        self.call("mlv_set_stream", ctypes.c_void_p(handle), count=False)
+
+    def call(self, name, *args, count=True):
+        _capi.check(self.lib, getattr(self.lib, name)(self.handle, *args))
+        if count:
+            _state["launches"] += 1
+            calls = _state["calls"]
+            calls[name] = calls.get(name, 0) + 1
+
+    # pool of x-transformed intermediates (nx, ipitch) complex128
+    def take_i(self):
+        if self._ipool:
+            return self._ipool.pop()
+        return empty((self.nx, self.ipitch), np.complex128)
+
+    def give_i(self, t):
+        if t is not None and len(self._ipool) < 8:
+            self._ipool.append(t)
+
+    def scratch_i(self):
+        if self._scratch_i is None:
+            self._scratch_i = empty((self.nx, max(self.ipitch, 1)), np.complex128)
+        return self._scratch_i
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.lib.mlv_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+_contexts = {}
+
+
+def context_for(params):
+    """Shared context for a Parameters-like object (nx, nz, lx, lz, discretisation, order)."""
+    fdm_z = params.discretisation[1] == "fdm"
+    if params.discretisation[0] == "fdm":
+        raise NotImplementedError("Finite difference not implemented in x direction")
+    if getattr(params, "precision", "double") != "double":
+        raise NotImplementedError(
+            "melvin-b200 computes in float64/complex128 only (precision='double')")
+    key = (int(params.nx), int(params.nz), float(params.lx), float(params.lz), fdm_z,
+           int(params.spatial_derivative_order), str(device()))
+    ctx = _contexts.get(key)
+    if ctx is None:
+        ctx = Context(params.nx, params.nz, params.lx, params.lz, fdm_z,
+                      params.spatial_derivative_order)
+        _contexts[key] = ctx
+    return ctx

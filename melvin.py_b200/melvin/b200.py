@@ -1,0 +1,585 @@
+"""``xp`` array namespace of the B200 backend.
+
+The reference injects an array module (``numpy`` or ``cupy``) into every class
+(e.g. reference ``melvin/Simulation.py:19-21``).  This module is the
+drop-in for that slot: the subset of the NumPy surface the reference and its
+example scripts touch, implemented on device buffers through the C ABI
+(``mlv_elementwise``, ``mlv_reduce``, ``mlv_spec_lincomb`` ...).
+
+Three array-like types live here:
+
+``DeviceArray``  eager float64 / complex128 array on the GPU (views, slicing,
+                 arithmetic, reductions).
+``SpecExpr``     a *deferred* linear combination of spectral arrays and
+                 nonlinear-term handles, ``sum_i c_i op_i(a_i) + sum_k c_k N_k``.
+                 The example scripts build their right-hand sides with ``-``,
+                 ``+``, ``c *`` and ``/ c``; keeping them symbolic lets
+                 ``Integrator.integrate`` evaluate the whole RHS, the history
+                 write and the update in one kernel (the forward-x epilogue).
+``LazyLap``      ``coef * lap`` (``Variable.lap()``) kept symbolic for the same
+                 reason; materialises to a real DeviceArray on any other use.
+"""
+import ctypes
+import numbers
+
+import numpy as np
+
+from . import _backend, _capi
+
+float64 = np.float64
+complex128 = np.complex128
+int64 = np.int64
+pi = np.pi
+
+_util_ctx = None
+
+
+def _ctx():
+    """Context used for shape-agnostic array kernels (stream + reduction scratch)."""
+    global _util_ctx
+    if _util_ctx is None:
+        _util_ctx = _backend.Context(16, 16, 1.0, 1.0, False, 2)
+    return _util_ctx
+
+
+def _is_scalar(x):
+    return isinstance(x, (numbers.Number, np.generic))
+
+
+def _is_complex_scalar(x):
+    return isinstance(x, (complex, np.complexfloating))
+
+
+# ============================================================= DeviceArray
+class DeviceArray:
+    __array_priority__ = 1000
+    __array_ufunc__ = None          # make NumPy scalars defer to our reflected operators
+
+    def __init__(self, tensor):
+        self._t = tensor
+
+    # -- hooks for lazily materialised subclasses
+    def _touch(self):
+        """Called before the data is read or written in place."""
+        return self
+
+    def _pre_write(self):
+        """Called before the data is modified in place."""
+
+    # -- metadata
+    @property
+    def shape(self):
+        return tuple(self._t.shape)
+
+    @property
+    def ndim(self):
+        return self._t.dim()
+
+    @property
+    def size(self):
+        return self._t.numel()
+
+    @property
+    def dtype(self):
+        return np.dtype(np.complex128) if self._t.is_complex() else (
+            np.dtype(np.float64) if self._t.is_floating_point() else np.dtype(np.int64))
+
+    @property
+    def is_complex(self):
+        return self._t.is_complex()
+
+    def __len__(self):
+        return self.shape[0]
+
+    # -- host interop
+    def get(self):
+        self._touch()
+        return _backend.to_host(self._t)
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.get()
+        return a.astype(dtype) if dtype is not None else a
+
+    def item(self):
+        return self.get().reshape(-1)[0].item()
+
+    def __float__(self):
+        return float(self.item())
+
+    def __complex__(self):
+        return complex(self.item())
+
+    def __repr__(self):
+        return f"DeviceArray({self.get()!r})"
+
+    def copy(self):
+        out = DeviceArray(_backend.empty(self.shape, self.dtype))
+        out[...] = self
+        return out
+
+    # -- views
+    def __getitem__(self, idx):
+        self._touch()
+        return DeviceArray(self._t[idx])
+
+    def __setitem__(self, idx, value):
+        self._touch()
+        self._pre_write()
+        target = self._t[idx]
+        if isinstance(value, (SpecExpr, LazyLap)):
+            value = value.materialize()
+        if isinstance(value, np.ndarray):
+            value = DeviceArray(_backend.from_host(value))
+        _elementwise(_capi.EW_COPY, value, None, out=target)
+
+    def reshape(self, *shape):
+        self._touch()
+        return DeviceArray(self._t.reshape(*shape))
+
+    # -- arithmetic (eager)
+    def _bin(self, op, other, reflected=False):
+        if isinstance(other, (SpecExpr, LazyLap)):
+            return NotImplemented
+        self._touch()
+        if isinstance(other, np.ndarray):
+            other = DeviceArray(_backend.from_host(other))
+        if not (isinstance(other, DeviceArray) or _is_scalar(other)):
+            return NotImplemented
+        a, b = (other, self) if reflected else (self, other)
+        return DeviceArray(_elementwise(op, a, b))
+
+    def __add__(self, o): return self._bin(_capi.EW_ADD, o)
+    def __radd__(self, o): return self._bin(_capi.EW_ADD, o, True)
+    def __sub__(self, o): return self._bin(_capi.EW_SUB, o)
+    def __rsub__(self, o): return self._bin(_capi.EW_SUB, o, True)
+    def __mul__(self, o): return self._bin(_capi.EW_MUL, o)
+    def __rmul__(self, o): return self._bin(_capi.EW_MUL, o, True)
+    def __truediv__(self, o): return self._bin(_capi.EW_DIV, o)
+    def __rtruediv__(self, o): return self._bin(_capi.EW_DIV, o, True)
+    def __neg__(self): return self._bin(_capi.EW_MUL, -1.0)
+    def __pos__(self): return self
+
+    def __pow__(self, e):
+        if self.is_complex or not _is_scalar(e) or int(e) != e or e < 0 or e > 16:
+            raise NotImplementedError("only real ** small non-negative integer is implemented")
+        return self._bin(_capi.EW_POW, float(e))
+
+    def __iadd__(self, o):
+        self[...] = self + o
+        return self
+
+    def __isub__(self, o):
+        self[...] = self - o
+        return self
+
+    def __imul__(self, o):
+        self[...] = self * o
+        return self
+
+    def __itruediv__(self, o):
+        self[...] = self / o
+        return self
+
+    # -- reductions (host scalars: every reduction is a sync, as in the reference
+    #    where Python min()/if consume device scalars, Integrator.py:37-44)
+    def max(self): return max(self)
+    def min(self): return min(self)
+    def sum(self): return sum(self)
+    def mean(self): return mean(self)
+
+
+def _view2(t):
+    """(ptr, rows, cols, row_stride, col_stride) of a <=2-D (or contiguous n-D) tensor."""
+    if t.dim() > 2:
+        if not t.is_contiguous():
+            raise NotImplementedError("only contiguous arrays with more than 2 dimensions")
+        t = t.reshape(-1, t.shape[-1])
+    if t.dim() == 0:
+        return t.data_ptr(), 1, 1, 0, 0
+    if t.dim() == 1:
+        return t.data_ptr(), 1, t.shape[0], 0, t.stride(0)
+    return t.data_ptr(), t.shape[0], t.shape[1], t.stride(0), t.stride(1)
+
+
+def _operand(x, shape):
+    """-> (kind, View, re, im, keepalive) broadcast to `shape` (<= 2-D)."""
+    if isinstance(x, DeviceArray):
+        t = x._touch()._t
+        if not (t.is_complex() or t.is_floating_point()):
+            raise TypeError("integer device arrays do not support arithmetic")
+        if tuple(t.shape) != tuple(shape):
+            t = t.expand(tuple(shape))
+        ptr, _, _, rs, cs = _view2(t)
+        kind = _capi.KIND_CPLX if t.is_complex() else _capi.KIND_REAL
+        return kind, _capi.View(ptr, rs, cs), 0.0, 0.0, t
+    z = complex(x)
+    return _capi.KIND_SCALAR, _capi.View(None, 0, 0), z.real, z.imag, None
+
+
+def _result_shape(a, b):
+    sa = a.shape if isinstance(a, DeviceArray) else ()
+    sb = b.shape if isinstance(b, DeviceArray) else ()
+    return tuple(np.broadcast_shapes(sa, sb))
+
+
+def _elementwise(op, a, b, out=None):
+    """out = a (op) b ; returns the torch tensor holding the result."""
+    if out is None:
+        shape = _result_shape(a, b)
+        cplx = any((isinstance(x, DeviceArray) and x.is_complex) or _is_complex_scalar(x)
+                   for x in (a, b) if x is not None)
+        out = _backend.empty(shape, np.complex128 if cplx else np.float64)
+    result = out
+    if out.numel() == 0:
+        return result
+    if out.dim() > 2:
+        shape = tuple(out.shape)
+        flat = out.reshape(-1, shape[-1])
+        if flat.data_ptr() != out.data_ptr() or not out.is_contiguous():
+            raise NotImplementedError("only contiguous targets with more than 2 dimensions")
+
+        def prep(x):
+            if isinstance(x, DeviceArray):
+                return DeviceArray(x._touch()._t.expand(shape).reshape(flat.shape))
+            return x
+        a, b, out = prep(a), (prep(b) if b is not None else None), flat
+    shape = tuple(out.shape)
+    d = _capi.Ew()
+    d.op = op
+    optr, rows, cols, ors, ocs = _view2(out)
+    d.rows, d.cols = rows, cols
+    d.out = _capi.View(optr, ors, ocs)
+    d.out_kind = _capi.KIND_CPLX if out.is_complex() else _capi.KIND_REAL
+    ka = _operand(a, shape)
+    d.a_kind, d.a, d.a_re, d.a_im = ka[0], ka[1], ka[2], ka[3]
+    kb = None
+    if b is not None:
+        kb = _operand(b, shape)
+        d.b_kind, d.b, d.b_re, d.b_im = kb[0], kb[1], kb[2], kb[3]
+    else:
+        d.b_kind = _capi.KIND_SCALAR
+    _ctx().call("mlv_elementwise", ctypes.byref(d))
+    del ka, kb
+    return result
+
+
+def _reduce(op, a, b=None):
+    a._touch()
+    if a.is_complex:
+        raise NotImplementedError("reductions are implemented for real arrays")
+    t = a._t if a._t.dim() <= 2 else a._t.contiguous()
+    ptr, rows, cols, rs, cs = _view2(t)
+    if rows * cols == 0:
+        raise ValueError("zero-size array to reduction operation")
+    va = _capi.View(ptr, rs, cs)
+    vb = None
+    if b is not None:
+        b._touch()
+        bp, _, _, brs, bcs = _view2(b._t.expand(tuple(a.shape)))
+        vb = _capi.View(bp, brs, bcs)
+    out = _backend.empty((1,), np.float64)
+    _ctx().call("mlv_reduce", op, rows, cols, ctypes.byref(va),
+                ctypes.byref(vb) if vb is not None else None, ctypes.c_void_p(out.data_ptr()))
+    return float(_backend.to_host(out)[0])
+
+
+# ------------------------------------------------------ namespace functions
+def _as_dev(x):
+    if isinstance(x, DeviceArray):
+        return x
+    if isinstance(x, (SpecExpr, LazyLap)):
+        return x.materialize()
+    return DeviceArray(_backend.from_host(np.asarray(x)))
+
+
+def zeros(shape, dtype=np.float64):
+    if isinstance(shape, (int, np.integer)):
+        shape = (int(shape),)
+    return DeviceArray(_backend.zeros(shape, dtype))
+
+
+def empty(shape, dtype=np.float64):
+    if isinstance(shape, (int, np.integer)):
+        shape = (int(shape),)
+    return DeviceArray(_backend.empty(shape, dtype))
+
+
+def ones(shape, dtype=np.float64):
+    out = empty(shape, dtype)
+    out[...] = 1.0
+    return out
+
+
+def zeros_like(a, dtype=None):
+    return zeros(a.shape, dtype or a.dtype)
+
+
+def empty_like(a, dtype=None):
+    return empty(a.shape, dtype or a.dtype)
+
+
+def array(obj, dtype=None):
+    if isinstance(obj, DeviceArray):
+        return obj.copy()
+    return DeviceArray(_backend.from_host(np.array(obj, dtype=dtype)))
+
+
+asarray = array
+
+
+def asnumpy(a):
+    return a.get() if isinstance(a, (DeviceArray, SpecExpr, LazyLap)) else np.asarray(a)
+
+
+def arange(*args, **kw):
+    return DeviceArray(_backend.from_host(np.arange(*args, **kw)))
+
+
+def max(a):   # noqa: A001  (NumPy name)
+    return _reduce(_capi.RED_MAX, _as_dev(a))
+
+
+def min(a):   # noqa: A001
+    return _reduce(_capi.RED_MIN, _as_dev(a))
+
+
+def sum(a):   # noqa: A001
+    return _reduce(_capi.RED_SUM, _as_dev(a))
+
+
+def mean(a):
+    a = _as_dev(a)
+    return _reduce(_capi.RED_SUM, a) / a.size
+
+
+def sum_of_squares(a):
+    return _reduce(_capi.RED_SUMSQ, _as_dev(a))
+
+
+def sum_of_product(a, b):
+    return _reduce(_capi.RED_SUMPROD, _as_dev(a), _as_dev(b))
+
+
+def save(fname, a):
+    np.save(fname, asnumpy(a))
+
+
+def savez(fname, **arrays):
+    np.savez(fname, **{k: asnumpy(v) for k, v in arrays.items()})
+
+
+def load(fname, **kw):
+    return np.load(fname, **kw)
+
+
+def synchronize():
+    _backend.synchronize()
+
+
+class _FFT:
+    """The reference library calls xp.fft.* itself; this backend performs the
+    transforms inside SpectralTransformer, so the namespace has nothing to offer."""
+
+    def __getattr__(self, name):
+        raise NotImplementedError(
+            f"xp.fft.{name}: transforms are provided by melvin.SpectralTransformer on this backend")
+
+
+fft = _FFT()
+
+
+# ================================================================ SpecExpr
+class NLTerm:
+    """Handle on the z-spectra (IA, IB) of the products ux*q, uz*q produced by the
+    fused physical-space stage; consumed by the forward x pass."""
+
+    def __init__(self, ctx, ia, ib):
+        self.ctx, self.ia, self.ib = ctx, ia, ib
+
+    def __del__(self):
+        try:
+            self.ctx.give_i(self.ia)
+            self.ctx.give_i(self.ib)
+        except Exception:
+            pass
+
+
+class SpecExpr:
+    """sum_i c_i * op_i(a_i)  +  sum_k c_k * NL_k   (spectral-shaped, complex128)."""
+    __array_priority__ = 2000
+    __array_ufunc__ = None
+
+    def __init__(self, ctx, terms=(), nls=()):
+        self.ctx = ctx
+        self.terms = list(terms)      # (complex coef, op code, DeviceArray)
+        self.nls = list(nls)          # (float coef, NLTerm)
+
+    # -- metadata
+    @property
+    def shape(self):
+        return self.ctx.spec_shape
+
+    @property
+    def dtype(self):
+        return np.dtype(np.complex128)
+
+    # -- algebra
+    def _scaled(self, c):
+        c = complex(c)
+        if self.nls and c.imag != 0.0:
+            return SpecExpr(self.ctx, [(c, _capi.OP_IDENT, self.materialize())])
+        return SpecExpr(self.ctx, [(k * c, op, a) for k, op, a in self.terms],
+                        [(k * c.real, n) for k, n in self.nls])
+
+    @staticmethod
+    def _lift(ctx, x):
+        if isinstance(x, SpecExpr):
+            return x
+        if isinstance(x, DeviceArray) and x.is_complex and x.shape == ctx.spec_shape \
+                and x._touch()._t.is_contiguous():
+            return SpecExpr(ctx, [(1.0 + 0j, _capi.OP_IDENT, x)])
+        return None
+
+    def __neg__(self): return self._scaled(-1.0)
+    def __pos__(self): return self
+
+    def __mul__(self, o):
+        if _is_scalar(o):
+            return self._scaled(o)
+        return self.materialize() * o
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, o):
+        if _is_scalar(o):
+            return self._scaled(1.0 / complex(o) if isinstance(o, (complex, np.complexfloating))
+                                else 1.0 / float(o))
+        return self.materialize() / o
+
+    def __rtruediv__(self, o):
+        return o / self.materialize()
+
+    def _add(self, o, sign):
+        other = self._lift(self.ctx, o)
+        if other is None:
+            m = self.materialize()
+            return m + o if sign > 0 else m - o
+        if sign < 0:
+            other = other._scaled(-1.0)
+        return SpecExpr(self.ctx, self.terms + other.terms, self.nls + other.nls)
+
+    def __add__(self, o): return self._add(o, +1)
+    def __radd__(self, o): return self._add(o, +1)
+    def __sub__(self, o): return self._add(o, -1)
+
+    def __rsub__(self, o):
+        return self._scaled(-1.0)._add(o, +1)
+
+    # -- evaluation
+    def materialize(self, out=None):
+        """Evaluate into a (new) spectral DeviceArray."""
+        ctx = self.ctx
+        if out is None:
+            out = DeviceArray(_backend.empty(ctx.spec_shape, np.complex128))
+        out_t = out._t
+        terms = list(self.terms)
+        first = True
+        nls = list(self.nls)
+        while nls:
+            chunk, nls = nls[:2], nls[2:]
+            d = _capi.XFwd()
+            d.nf, d.mode = 2 * len(chunk), 0
+            for i, (coef, nl) in enumerate(chunk):
+                d.src[2 * i], d.src[2 * i + 1] = nl.ia.data_ptr(), nl.ib.data_ptr()
+                d.sym[2 * i], d.sym[2 * i + 1] = _capi.SYM_FDX, _capi.SYM_FDZ
+                d.coef[2 * i] = d.coef[2 * i + 1] = coef
+            if first:
+                d.dst = out_t.data_ptr()
+                ctx.call("mlv_x_forward", ctypes.byref(d))
+                first = False
+            else:
+                tmp = _backend.empty(ctx.spec_shape, np.complex128)
+                d.dst = tmp.data_ptr()
+                ctx.call("mlv_x_forward", ctypes.byref(d))
+                terms.append((1.0 + 0j, _capi.OP_IDENT, DeviceArray(tmp)))
+        if not terms and first:
+            out_t.zero_()
+            return out
+        while terms:
+            room = 4 if first else 3
+            chunk, terms = terms[:room], terms[room:]
+            packed = [(c, op, a._touch()._t.data_ptr()) for c, op, a in chunk]
+            if not first:
+                packed.append((1.0, _capi.OP_IDENT, out_t.data_ptr()))
+            lt = _capi.make_lin_terms(packed)
+            ctx.call("mlv_spec_lincomb", ctypes.byref(lt), ctypes.c_void_p(out_t.data_ptr()))
+            first = False
+        return out
+
+    # -- array-like fallbacks
+    def __getitem__(self, idx):
+        return self.materialize()[idx]
+
+    def __array__(self, dtype=None, copy=None):
+        return self.materialize().__array__(dtype)
+
+    def get(self):
+        return self.materialize().get()
+
+
+# ================================================================= LazyLap
+class LazyLap:
+    """``coef * (d2x n^2 + d2z m^2)`` -- Variable.lap() / SpatialDifferentiator.calc_lap
+    (reference melvin/SpatialDifferentiator.py:70-74) kept symbolic."""
+    __array_priority__ = 2000
+    __array_ufunc__ = None
+
+    def __init__(self, ctx, coef=1.0):
+        self.ctx, self.coef = ctx, float(coef)
+        self._mat = None
+
+    @property
+    def shape(self):
+        return self.ctx.spec_shape
+
+    @property
+    def dtype(self):
+        return np.dtype(np.float64)
+
+    def __mul__(self, o):
+        if _is_scalar(o) and complex(o).imag == 0.0:
+            return LazyLap(self.ctx, self.coef * float(np.real(o)))
+        return self.materialize() * o
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, o):
+        if _is_scalar(o) and complex(o).imag == 0.0:
+            return LazyLap(self.ctx, self.coef / float(np.real(o)))
+        return self.materialize() / o
+
+    def __neg__(self):
+        return LazyLap(self.ctx, -self.coef)
+
+    def materialize(self):
+        if self._mat is None:
+            out = _backend.empty(self.ctx.spec_shape, np.float64)
+            self.ctx.call("mlv_lap_array", ctypes.c_double(self.coef), ctypes.c_void_p(out.data_ptr()))
+            self._mat = DeviceArray(out)
+        return self._mat
+
+    def __add__(self, o): return self.materialize() + o
+    def __radd__(self, o): return o + self.materialize()
+    def __sub__(self, o): return self.materialize() - o
+    def __rsub__(self, o): return o - self.materialize()
+    def __rtruediv__(self, o): return o / self.materialize()
+    def __getitem__(self, idx): return self.materialize()[idx]
+
+    def __setitem__(self, idx, v):
+        self.materialize()[idx] = v
+
+    def __array__(self, dtype=None, copy=None):
+        return self.materialize().__array__(dtype)
+
+    def get(self):
+        return self.materialize().get()

@@ -1,0 +1,466 @@
+"""Field objects: ``Variable`` (spectral + physical pair) and ``TimeDerivative``
+(ring buffer of right-hand-side history).
+
+API mirror of the reference's ``melvin/Variable.py`` and
+``melvin/TimeDerivative.py``; the storage is device memory and the operators are
+the C-ABI kernels.  On top of the reference semantics a Variable keeps a
+*private* x-transformed intermediate (``_i``) so that the physical field never
+has to be written to HBM inside the time step:
+
+    spectral  --x pass-->  I (nx, nm)  --z pass-->  physical
+
+``to_physical()`` only records the request; the x pass is issued when the
+intermediate is first needed (batched with the other fields of the same
+``vec_dot_nabla``), the z pass only when somebody really reads ``getp()``.
+Whatever is read is always what the reference would have returned: pending
+work captures the buffer it was defined on, in-place writes flush dependants
+first, and ``Integrator`` double-buffers a state that still has dependants.
+"""
+import ctypes
+import weakref
+
+import numpy as np
+
+from . import _backend, _capi
+from .b200 import DeviceArray, LazyLap, NLTerm, SpecExpr
+from .basis import BasisFunctions
+
+_I_NONE, _I_PENDING, _I_VALID = 0, 1, 2
+
+
+class _SpecHandle(DeviceArray):
+    """Spectral buffer of a Variable: reads materialise a deferred definition,
+    in-place writes first flush everything that still depends on the old data."""
+
+    def __init__(self, tensor, owner):
+        super().__init__(tensor)
+        self._owner = weakref.ref(owner)
+
+    def _touch(self):
+        o = self._owner()
+        if o is not None and o._s is self:
+            o._materialize_s()
+        return self
+
+    def _pre_write(self):
+        o = self._owner()
+        if o is not None:
+            o._flush_dependants(self)
+
+
+class _PhysHandle(DeviceArray):
+    """Physical buffer of a Variable: the z pass runs on first touch."""
+
+    def __init__(self, tensor, owner):
+        super().__init__(tensor)
+        self._owner = weakref.ref(owner)
+
+    def _touch(self):
+        o = self._owner()
+        if o is not None:
+            o._ensure_p()
+        return self
+
+    def _pre_write(self):
+        o = self._owner()
+        if o is not None:
+            o._p_written()
+
+
+class Variable:
+    """Encapsulates the physical and spectral representations of a variable
+    (reference melvin/Variable.py:6-37)."""
+
+    def __init__(self, params, xp, sd=None, st=None, dt=None, array_factory=None,
+                 dump_name=None, basis_functions=None):
+        self._params = params
+        self._xp = xp
+        self._st = st
+        self._sd = sd
+        self._dt = dt
+        self._array_factory = array_factory
+        self._dump_name = dump_name
+        if basis_functions is None:
+            raise Exception("Basis functions must be specified.")
+        self._basis_functions = basis_functions
+        self._ctx = _backend.context_for(params)
+        self._fused = (not self._ctx.fdm_z
+                       and basis_functions[0] is BasisFunctions.COMPLEX_EXP
+                       and basis_functions[1] is BasisFunctions.COMPLEX_EXP)
+        self._s = _SpecHandle(_backend.zeros(params.spectral_shape, np.complex128), self)
+        self._s_spare = None                 # second state buffer (double buffering)
+        self._p = _PhysHandle(_backend.zeros(params.physical_shape, np.float64), self)
+        self._virt = None                    # (op, DeviceArray): deferred spectral definition
+        self._i = None                       # torch tensor (nx, ipitch) complex128
+        self._i_state = _I_NONE
+        self._i_def = None                   # (op, DeviceArray) the pending x pass reads
+        self._p_valid = True
+        self._red = None                     # (red4 tensor, max index, sumsq index)
+        self._ctx_vars().add(self)
+
+    # ------------------------------------------------------------ registry
+    def _ctx_vars(self):
+        reg = getattr(self._ctx, "_lazy_vars", None)
+        if reg is None:
+            reg = weakref.WeakSet()
+            self._ctx._lazy_vars = reg
+        return reg
+
+    def _depends_on(self, handle):
+        return ((self._virt is not None and self._virt[1] is handle)
+                or (self._i_state == _I_PENDING and self._i_def[1] is handle))
+
+    def _flush_dependants(self, handle):
+        """`handle`'s buffer is about to change in place."""
+        for v in list(self._ctx_vars()):
+            if v._i_state == _I_PENDING and v._i_def[1] is handle:
+                v._ensure_i()
+            if v._virt is not None and v._virt[1] is handle:
+                v._materialize_s()
+
+    def _has_dependants(self, handle):
+        return any(v._depends_on(handle) for v in self._ctx_vars())
+
+    # ---------------------------------------------------- spectral storage
+    @property
+    def _sdata(self):
+        self._materialize_s()
+        return self._s
+
+    @_sdata.setter
+    def _sdata(self, value):
+        self.sets(value)
+
+    @property
+    def _pdata(self):
+        return self._p
+
+    def _materialize_s(self):
+        if self._virt is None:
+            return
+        op, src = self._virt
+        self._virt = None
+        lt = _capi.make_lin_terms([(1.0, op, src._touch()._t.data_ptr())])
+        self._ctx.call("mlv_spec_lincomb", ctypes.byref(lt), ctypes.c_void_p(self._s._t.data_ptr()))
+
+    def _set_virtual(self, op, src):
+        """Spectral data := op(src) without writing it (fully spectral mode)."""
+        self._flush_dependants(self._s)
+        self._virt = (op, src)
+
+    def _spec_def(self):
+        return self._virt if self._virt is not None else (_capi.OP_IDENT, self._s)
+
+    def __setitem__(self, index, value):
+        self._materialize_s()
+        self._s[index] = value
+
+    def __getitem__(self, index):
+        full = index == slice(None) if isinstance(index, slice) else index is Ellipsis
+        if full and self._virt is not None:
+            op, src = self._virt
+            return SpecExpr(self._ctx, [(1.0 + 0j, op, src)])
+        return self._sdata[index]
+
+    def sets(self, data):
+        """Setter for spectral data"""
+        if isinstance(data, SpecExpr):
+            self._flush_dependants(self._s)
+            self._virt = None
+            data.materialize(out=DeviceArray(self._s._t))
+            return
+        self._flush_dependants(self._s)
+        self._virt = None
+        self._s[:, :] = data[:, :]
+
+    def gets(self):
+        return self._sdata
+
+    # ---------------------------------------------------- physical storage
+    def setp(self, data):
+        """Setter for physical data"""
+        if isinstance(data, np.ndarray):
+            data = DeviceArray(_backend.from_host(data))
+        self._p_written()
+        DeviceArray(self._p._t)[:, :] = data[:, :]
+
+    def getp(self):
+        return self._p
+
+    def _p_written(self):
+        self._i_state = _I_NONE
+        self._i_def = None
+        self._p_valid = True
+        self._red = None
+
+    def _ensure_i(self):
+        """Make the x-transformed intermediate valid (runs the pending x pass)."""
+        if self._i_state == _I_PENDING:
+            _run_x_inverse(self._ctx, [self])
+        return self._i_state == _I_VALID
+
+    def _ensure_p(self):
+        if self._p_valid:
+            return
+        if self._ctx.fdm_z:
+            raise RuntimeError("internal: FDM-z transforms are eager")
+        self._ensure_i()
+        self._ctx.call("mlv_z_inverse", ctypes.c_void_p(self._i.data_ptr()),
+                       ctypes.c_void_p(self._p._t.data_ptr()))
+        self._p_valid = True
+
+    def _request_physical(self):
+        """Record `pdata = T(sdata)` for the current spectral definition."""
+        self._i_def = self._spec_def()
+        self._i_state = _I_PENDING
+        self._p_valid = False
+        self._red = None
+
+    # ------------------------------------------------------- transforms
+    def to_physical(self):
+        """Convert spectral data to physical"""
+        if self._fused:
+            self._request_physical()
+        else:
+            self._st.to_physical(self._sdata, DeviceArray(self._p._t), self._basis_functions)
+            self._p_written()
+
+    def to_spectral(self):
+        """Convert physical data to spectral"""
+        self._flush_dependants(self._s)
+        self._virt = None
+        self._st.to_spectral(self._p, DeviceArray(self._s._t), self._basis_functions)
+
+    def load(self, data, is_physical=False):
+        if isinstance(data, str):
+            raise NotImplementedError
+        data = self._dt.from_host(data)
+        if is_physical:
+            self.setp(data)
+            self.to_spectral()
+        else:
+            nn, nm = self._params.nn, self._params.nm
+            if tuple(data.shape) != (nn, nm):
+                data = scale_variable(data, (nn, nm), self._xp)
+            self.sets(data)
+
+    # ------------------------------------------------------ derivatives
+    def pddx(self):
+        """Calculate spatial derivative of physical data"""
+        return self._sd.pddx(self.getp())
+
+    def pddz(self):
+        """Calculate spatial derivative of physical data"""
+        return self._sd.pddz(self.getp())
+
+    def _sterm(self, op):
+        cop, src = self._spec_def()
+        if cop == _capi.OP_IDENT:
+            return SpecExpr(self._ctx, [(1.0 + 0j, op, src)])
+        return SpecExpr(self._ctx, [(1.0 + 0j, op, self._sdata)])
+
+    def sddx(self):
+        """Calculate first derivative of spectral data"""
+        return self._sd.sddx(self._spec_operand(), self._basis_functions[0])
+
+    def sddz(self):
+        """Calculate first derivative of spectral data"""
+        return self._sd.sddz(self._spec_operand(), self._basis_functions[1])
+
+    def sd2dx2(self):
+        """Calculate second derivative of spectral data"""
+        return self._sd.sd2dx2(self._spec_operand(), self._basis_functions[0])
+
+    def sd2dz2(self):
+        """Calculate second derivative of spectral data"""
+        return self._sd.sd2dz2(self._spec_operand(), self._basis_functions[1])
+
+    def _spec_operand(self):
+        return self._sdata
+
+    def snabla2(self):
+        """Calculate nabla^2 in spectral form"""
+        if self._fused:
+            return SpecExpr(self._ctx, [(1.0 + 0j, _capi.OP_LAP, self._sdata)])
+        return self.sd2dx2() + self.sd2dz2()
+
+    def lap(self):
+        """Returns linear operator representing laplacian"""
+        return self._sd.calc_lap(self._basis_functions)
+
+    # --------------------------------------------------- nonlinear term
+    def vec_dot_nabla(self, ux, uz, out=None, convert_to_physical=True):
+        """d/dx(ux q) + d/dz(uz q) -> spectral (reference melvin/Variable.py:119-128)."""
+        uxo = ux._owner() if isinstance(ux, _PhysHandle) else None
+        uzo = uz._owner() if isinstance(uz, _PhysHandle) else None
+        fused = (self._fused and out is None and uxo is not None and uzo is not None
+                 and uxo._fused and uzo._fused
+                 and uxo._i_state != _I_NONE and uzo._i_state != _I_NONE)
+        if fused:
+            if convert_to_physical:
+                self._request_physical()
+            fused = self._i_state != _I_NONE
+        if not fused:
+            return self._vec_dot_nabla_eager(ux, uz, out, convert_to_physical)
+        ctx = self._ctx
+        _run_x_inverse(ctx, [v for v in (uxo, uzo, self) if v._i_state == _I_PENDING])
+        ia, ib = ctx.take_i(), ctx.take_i()
+        red4 = _backend.empty((4,), np.float64)
+        ctx.call("mlv_advect_z", ctypes.c_void_p(uxo._i.data_ptr()), ctypes.c_void_p(uzo._i.data_ptr()),
+                 ctypes.c_void_p(self._i.data_ptr()), ctypes.c_void_p(ia.data_ptr()),
+                 ctypes.c_void_p(ib.data_ptr()), ctypes.c_void_p(red4.data_ptr()))
+        uxo._red = (red4, 0, 2)
+        uzo._red = (red4, 1, 3)
+        return SpecExpr(ctx, [], [(1.0, NLTerm(ctx, ia, ib))])
+
+    def _vec_dot_nabla_eager(self, ux, uz, out, convert_to_physical):
+        if convert_to_physical:
+            self.to_physical()
+        if isinstance(ux, np.ndarray):
+            ux = DeviceArray(_backend.from_host(ux))
+        if isinstance(uz, np.ndarray):
+            uz = DeviceArray(_backend.from_host(uz))
+        q = self.getp()
+        if out is None:
+            out = self._xp.zeros_like(self._p)
+        args = []
+        for a in (ux, uz, q, out):
+            t = a._touch()._t
+            if not t.is_contiguous() or t.is_complex():
+                raise NotImplementedError("vec_dot_nabla needs contiguous real (nx, nz) operands")
+            args.append(ctypes.c_void_p(t.data_ptr()))
+        self._ctx.call("mlv_advect_phys", *args)
+        return self._st.to_spectral(out, basis_functions=self._basis_functions)
+
+    # ------------------------------------------------------ reductions
+    def _cached_reduction(self, which):
+        """max (which=1) or sum of squares (which=2) of the physical field if the fused
+        z stage already produced it for the current intermediate."""
+        if self._red is None or self._i_state == _I_NONE:
+            return None
+        return float(_backend.to_host(self._red[0])[self._red[which]])
+
+    # ------------------------------------------------------------- I/O
+    def save(self, dump_counter):
+        fname = self._dump_name + f"{dump_counter:04d}.npy"
+        self._xp.save(fname, self._p)
+
+    def on_host(self):
+        return self._dt.to_host(self.gets())
+
+    def get_name(self):
+        return self._dump_name
+
+
+def _run_x_inverse(ctx, variables):
+    """One inverse x pass for every listed Variable with a pending request."""
+    variables = [v for i, v in enumerate(variables) if v not in variables[:i]]
+    while variables:
+        chunk, variables = variables[:4], variables[4:]
+        n = len(chunk)
+        srcs = (ctypes.c_void_p * n)()
+        ops = (ctypes.c_int32 * n)()
+        dsts = (ctypes.c_void_p * n)()
+        for k, v in enumerate(chunk):
+            op, src = v._i_def
+            if v._i is None:
+                v._i = _backend.empty((ctx.nx, ctx.ipitch), np.complex128)
+            srcs[k] = src._touch()._t.data_ptr()
+            ops[k] = op
+            dsts[k] = v._i.data_ptr()
+        ctx.call("mlv_x_inverse", n, srcs, ops, dsts)
+        for v in chunk:
+            v._i_state = _I_VALID
+            v._i_def = None
+
+
+def scale_variable(var, outsize, xp):
+    """Scale an array in spectral space from its size to `outsize` (nn, nm)
+    (reference melvin/Variable.py:142-151, but complex-preserving: the reference
+    allocates a real buffer here)."""
+    insize = var.shape
+    outvar = xp.zeros((2 * outsize[0] + 1, outsize[1]), dtype=np.complex128)
+    nx_min = min(insize[0], outsize[0])
+    nz_min = min(insize[1], outsize[1])
+    outvar[: nx_min + 1, :nz_min] = var[: nx_min + 1, :nz_min]
+    outvar[-nx_min:, :nz_min] = var[-nx_min:, :nz_min]
+    return outvar
+
+
+class TimeDerivative:
+    """Represents a sequence of derivatives in time
+    (reference melvin/TimeDerivative.py:4-65).  Assigning a deferred expression
+    to the current level (``dvar[:] = expr``) is recorded and evaluated by
+    ``Integrator.integrate`` (or on first read)."""
+
+    def __init__(self, params, xp, dump_name="", array_factory=None):
+        self._params = params
+        self._xp = xp
+        self._curr_idx = 0
+        self._store = DeviceArray(_backend.zeros(
+            (params.integrator_order,) + tuple(params.spectral_shape), np.complex128))
+        self._dump_name = dump_name
+        self._pending = None
+
+    # -- deferred assignment
+    def _flush(self):
+        if self._pending is not None:
+            expr, self._pending = self._pending, None
+            expr.materialize(out=self._level(0))
+
+    def _level(self, back):
+        """History level curr_idx+back with Python negative wrap (:38-39)."""
+        return self._store[self._curr_idx + back]
+
+    @property
+    def _data(self):
+        self._flush()
+        return self._store
+
+    def __setitem__(self, index, value):
+        full = (isinstance(index, slice) and index == slice(None)) or index is Ellipsis
+        if full and isinstance(value, SpecExpr):
+            self._pending = value
+            return
+        self._flush()
+        self._level(0)[index] = value
+
+    def __getitem__(self, index):
+        self._flush()
+        return self._level(0)[index]
+
+    def get_curr_idx(self):
+        return self._curr_idx
+
+    def set_curr_idx(self, curr_idx):
+        self._flush()
+        self._curr_idx = int(curr_idx)
+
+    def advance(self):
+        self._flush()
+        self._curr_idx = (self._curr_idx + 1) % self._params.integrator_order
+
+    def get(self, idx=0):
+        self._flush()
+        return self._level(idx)
+
+    def get_all(self):
+        return self._data
+
+    def set(self, data, idx=0):
+        self._flush()
+        self._level(idx)[...] = data
+
+    def load(self, data):
+        if isinstance(data, str):
+            raise NotImplementedError
+        self._flush()
+        nn, nm = self._params.nn, self._params.nm
+        for i in range(self._params.integrator_order):
+            level = data[i]
+            if tuple(level.shape) != (2 * nn + 1, nm):
+                level = scale_variable(level, (nn, nm), self._xp)
+            self._store[i][...] = level
+
+    def get_name(self):
+        return self._dump_name

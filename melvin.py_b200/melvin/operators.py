@@ -1,0 +1,460 @@
+"""Numerical operators: ArrayFactory, SpectralTransformer, SpatialDifferentiator,
+LaplacianSolver, Integrator.
+
+API mirrors of the reference classes of the same names (constructor signatures,
+slot names, argument meaning and error behaviour); every operation is a call into
+libmelvin_b200.so.  Reference locations are cited per method.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _backend, _capi
+from .b200 import DeviceArray, LazyLap, SpecExpr
+from .basis import BasisFunctions
+
+_CE = BasisFunctions.COMPLEX_EXP
+_FDM = BasisFunctions.FDM
+
+
+def _require_device_namespace(xp):
+    if getattr(xp, "__name__", "") == "numpy":
+        raise _backend.BackendUnavailable(
+            "melvin-b200 has no CPU path: pass the device namespace (`from melvin import b200 as xp`, "
+            "or the `cupy` shim) instead of numpy")
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _dev(x, dtype=None):
+    """Host arrays are uploaded; device arrays pass through (materialised)."""
+    if isinstance(x, (SpecExpr, LazyLap)):
+        return x.materialize()
+    if isinstance(x, DeviceArray):
+        return x
+    return DeviceArray(_backend.from_host(np.asarray(x), dtype))
+
+
+def _contig(a):
+    t = a._touch()._t
+    return t if t.is_contiguous() else t.contiguous()
+
+
+class ArrayFactory:
+    """Creates arrays of the correct size and shape (reference melvin/ArrayFactory.py)."""
+
+    def __init__(self, params, xp):
+        _require_device_namespace(xp)
+        self._p = params
+        self._xp = xp
+
+    def make_mode_number_matrices(self):
+        """Integer mode numbers n, m (ArrayFactory.py:8-26).  Host metadata: the
+        kernels derive n and m from the element index and never read these."""
+        p = self._p
+        if p.is_fully_spectral():
+            n = np.concatenate((np.arange(0, p.nn + 1), np.arange(-p.nn, 0)))
+            m = np.arange(0, p.nm)
+        elif p.discretisation[0] == "fdm":
+            n, m = np.arange(0, p.nx), np.arange(0, p.nm)
+        else:
+            n, m = np.arange(0, p.nn), np.arange(0, p.nz)
+        return np.meshgrid(n, m, indexing="ij")
+
+    def make_spectral(self, ni=None, nj=None):
+        ni = self._p.spectral_shape[0] if ni is None else ni
+        nj = self._p.spectral_shape[1] if nj is None else nj
+        return self._xp.zeros((ni, nj), dtype=self._p.complex)
+
+    def make_physical(self, nx=None, nz=None):
+        nx = self._p.nx if nx is None else nx
+        nz = self._p.nz if nz is None else nz
+        return self._xp.zeros((nx, nz), dtype=self._p.float)
+
+
+class SpectralTransformer:
+    """Physical <-> spectral transforms with 2/3-rule truncation
+    (reference melvin/SpectralTransformer.py)."""
+
+    def __init__(self, params, xp, array_factory):
+        _require_device_namespace(xp)
+        self._p = params
+        self._xp = xp
+        self._array_factory = array_factory
+        self._ctx = _backend.context_for(params)
+        if params.is_fully_spectral():
+            self.to_physical = self.__to_physical_2d
+            self.to_spectral = self.__to_spectral_2d
+        else:
+            self.to_physical = self.__to_physical_1d
+            self.to_spectral = self.__to_spectral_1d
+
+    _DEFAULT = [_CE, _CE]
+
+    @staticmethod
+    def _only_fourier(basis_functions):
+        if not (basis_functions[0] is _CE and basis_functions[1] is _CE):
+            raise NotImplementedError(
+                "COSINE/SINE bases are not implemented on the B200 backend yet (SURVEY 8f-2)")
+
+    @staticmethod
+    def _fdm_axis(basis_functions):
+        if basis_functions[0] is _FDM:
+            raise NotImplementedError("Finite difference not implemented in x direction")
+        if basis_functions[1] is not _FDM:
+            raise Exception("One basis function must be FDM")
+
+    def __to_physical_2d(self, in_arr, out=None, basis_functions=_DEFAULT):
+        """SpectralTransformer.py:90-150"""
+        self._only_fourier(basis_functions)
+        if out is None:
+            out = self._array_factory.make_physical()
+        src = _contig(_dev(in_arr, np.complex128))
+        dst = out._t if isinstance(out, DeviceArray) else None
+        if dst is None or not dst.is_contiguous():
+            raise TypeError("out must be a contiguous device array")
+        out._pre_write()
+        self._ctx.call("mlv_to_physical", _ptr(src), _ptr(self._ctx.scratch_i()), _ptr(dst))
+        return out
+
+    def __to_spectral_2d(self, in_arr, out=None, basis_functions=_DEFAULT):
+        """SpectralTransformer.py:152-199"""
+        self._only_fourier(basis_functions)
+        if out is None:
+            out = self._array_factory.make_spectral()
+        src = _contig(_dev(in_arr, np.float64))
+        if src.is_complex():
+            raise TypeError("to_spectral expects a real physical array")
+        out._touch()
+        out._pre_write()
+        self._ctx.call("mlv_to_spectral", _ptr(src), _ptr(self._ctx.scratch_i()), _ptr(out._t))
+        return out
+
+    def __to_physical_1d(self, in_arr, out=None, basis_functions=_DEFAULT):
+        """SpectralTransformer.py:33-61"""
+        self._fdm_axis(basis_functions)
+        if out is None:
+            out = self._array_factory.make_physical()
+        src = _contig(_dev(in_arr, np.complex128))
+        out._pre_write()
+        self._ctx.call("mlv_to_physical", _ptr(src), None, _ptr(out._t))
+        return out
+
+    def __to_spectral_1d(self, in_arr, out=None, basis_functions=_DEFAULT):
+        """SpectralTransformer.py:63-88"""
+        self._fdm_axis(basis_functions)
+        if out is None:
+            out = self._array_factory.make_spectral()
+        src = _contig(_dev(in_arr, np.float64))
+        out._touch()
+        out._pre_write()
+        self._ctx.call("mlv_to_spectral", _ptr(src), None, _ptr(out._t))
+        return out
+
+
+class SpatialDifferentiator:
+    """Spectral derivative symbols and physical-space central differences
+    (reference melvin/SpatialDifferentiator.py)."""
+
+    def __init__(self, params, xp, array_factory=None):
+        _require_device_namespace(xp)
+        self._xp = xp
+        self._params = params
+        self._ctx = _backend.context_for(params)
+        self._x_periodic = params.discretisation[0] == "spectral"
+        self._z_periodic = params.discretisation[1] == "spectral"
+        if params.spatial_derivative_order not in (2, 4):
+            raise NotImplementedError("spatial_derivative_order must be 2 or 4")
+        self._order = params.spatial_derivative_order
+        self._n, self._m = array_factory.make_mode_number_matrices()
+        if params.discretisation[0] == "fdm":
+            raise NotImplementedError("Finite difference not implemented in x direction")
+        self.sddx = self.__s_ddx
+        self.sd2dx2 = self.__s_d2dx2
+        if params.discretisation[1] == "fdm":
+            self.sddz = lambda var, bs: self.pddz(var)
+            self.sd2dz2 = lambda var, bs: self.pd2dz2(var)
+        else:
+            self.sddz = self.__s_ddz
+            self.sd2dz2 = self.__s_d2dz2
+
+    # -- spectral symbols (SpatialDifferentiator.py:50-74): deferred terms
+    def _term(self, var, basis_fn, op):
+        if basis_fn is _FDM:
+            return 0.0 * _dev(var)          # diff factor of FDM is 0 (BasisFunctions.py:26-36)
+        if basis_fn is not _CE:
+            raise NotImplementedError("COSINE/SINE bases are not implemented on the B200 backend yet")
+        if isinstance(var, SpecExpr) and not var.nls and len(var.terms) == 1 \
+                and var.terms[0][1] == _capi.OP_IDENT:
+            c, _, a = var.terms[0]
+            return SpecExpr(self._ctx, [(c, op, a)])
+        a = _dev(var, np.complex128)
+        lifted = SpecExpr._lift(self._ctx, a)
+        if lifted is None:
+            raise TypeError("spectral derivative expects a contiguous complex spectral-shaped array")
+        return SpecExpr(self._ctx, [(1.0 + 0j, op, a)])
+
+    def __s_ddx(self, var, basis_fn):
+        return self._term(var, basis_fn, _capi.OP_DDX)
+
+    def __s_ddz(self, var, basis_fn):
+        return self._term(var, basis_fn, _capi.OP_DDZ)
+
+    def __s_d2dx2(self, var, basis_fn):
+        return self._term(var, basis_fn, _capi.OP_D2DX2)
+
+    def __s_d2dz2(self, var, basis_fn):
+        return self._term(var, basis_fn, _capi.OP_D2DZ2)
+
+    def calc_lap(self, basis_fns):
+        """SpatialDifferentiator.py:70-74"""
+        if basis_fns[0] is _CE and basis_fns[1] is _CE and self._z_periodic:
+            return LazyLap(self._ctx, 1.0)
+        from .basis import gen_diff2_factors
+        fx = gen_diff2_factors(self._params.lx)[basis_fns[0]]
+        fz = gen_diff2_factors(self._params.lz)[basis_fns[1]]
+        return DeviceArray(_backend.from_host(np.asarray(fx * self._n ** 2 + fz * self._m ** 2,
+                                                         dtype=np.float64)))
+
+    # -- physical stencils (SpatialDifferentiator.py:76-185)
+    def _stencil(self, var, out, axis, periodic, second, h):
+        a = _dev(var)
+        src = _contig(a)
+        if src.dim() != 2:
+            raise ValueError("stencils operate on 2-D arrays")
+        ncomp = 2 if src.is_complex() else 1
+        if out is None:
+            if not second:
+                # the reference allocates a real (nx, nz) buffer here; a complex or
+                # differently shaped operand fails on assignment
+                if ncomp == 2 or tuple(src.shape) != (self._params.nx, self._params.nz):
+                    raise ValueError("could not broadcast input array into a real (nx, nz) output")
+                out = self._xp.zeros((self._params.nx, self._params.nz), dtype=np.float64)
+            else:
+                out = self._xp.zeros_like(a)
+        dst = out._touch()._t
+        out._pre_write()
+        if not dst.is_contiguous() or tuple(dst.shape) != tuple(src.shape) \
+                or dst.is_complex() != src.is_complex():
+            raise ValueError("out must be contiguous and match the operand")
+        self._ctx.call("mlv_stencil", _ptr(src), _ptr(dst), int(src.shape[0]), int(src.shape[1]),
+                       ncomp, axis, self._order, int(periodic), int(second), ctypes.c_double(h))
+        return out
+
+    def pddx(self, var, out=None):
+        return self._stencil(var, out, 0, self._x_periodic, 0, self._params.dx)
+
+    def pddz(self, var, out=None):
+        return self._stencil(var, out, 1, self._z_periodic, 0, self._params.dz)
+
+    def pd2dz2(self, var, out=None):
+        return self._stencil(var, out, 1, False, 1, self._params.dz)
+
+
+class LaplacianSolver:
+    """Solves lap(psi) = rhs (reference melvin/LaplacianSolver.py)."""
+
+    def __init__(self, params, xp, basis_fns, spatial_diff=None, array_factory=None):
+        _require_device_namespace(xp)
+        self._params = params
+        self._xp = xp
+        self._array_factory = array_factory
+        self._ctx = _backend.context_for(params)
+        if params.is_fully_spectral():
+            self._lap = spatial_diff.calc_lap(basis_fns)
+            self.solve = self._solve_fully_spectral
+        else:
+            print("WARNING: Laplacian solver only implemented for boundary conditions "
+                  "where soln matches value of rhs")
+            self.solve = self._solve_fdm
+
+    @property
+    def lap(self):
+        return self._lap.materialize() if isinstance(self._lap, LazyLap) else self._lap
+
+    @property
+    def laps(self):
+        """Host copies of the nn tridiagonal matrices (LaplacianSolver.py:25-49);
+        the device solve uses their Thomas factors held by the context."""
+        import scipy.sparse as sp
+        p = self._params
+        kx0 = abs(1j * 2 * np.pi / p.lx)
+        mats = []
+        for n in range(p.nn):
+            diag = np.full(p.nz, -((n * kx0) ** 2 + 2.0 / p.dz ** 2))
+            off = np.full(p.nz, 1.0 / p.dz ** 2)
+            m = sp.dia_matrix((np.array([off, diag, off]), np.array([-1, 0, 1])),
+                              shape=(p.nz, p.nz), dtype=np.complex128).tolil()
+            m[0, 0], m[0, 1], m[-1, -1], m[-1, -2] = 1.0, 0.0, 1.0, 0.0
+            mats.append(m.tocsr())
+        return mats
+
+    def _solve_fully_spectral(self, rhs, out=None):
+        """rhs / lap with lap[0,0] := 1 (LaplacianSolver.py:58-68)"""
+        if out is None:
+            out = self._array_factory.make_spectral()
+        src = _contig(_dev(rhs, np.complex128))
+        out._touch()
+        out._pre_write()
+        lt = _capi.make_lin_terms([(1.0, _capi.OP_INVLAP, src.data_ptr())])
+        self._ctx.call("mlv_spec_lincomb", ctypes.byref(lt), _ptr(out._t))
+        return out
+
+    def _solve_fdm(self, rhs, out=None):
+        """nn tridiagonal Dirichlet systems (LaplacianSolver.py:70-79)"""
+        if out is None:
+            out = self._array_factory.make_spectral()
+        src = _contig(_dev(rhs, np.complex128))
+        out._touch()
+        out._pre_write()
+        self._ctx.call("mlv_solve_fdm", _ptr(src), _ptr(out._t))
+        return out
+
+
+class Integrator:
+    """Adams-Bashforth predictor with explicit or semi-implicit (theta-scheme)
+    treatment of the linear term (reference melvin/Integrator.py)."""
+
+    def __init__(self, params, xp):
+        _require_device_namespace(xp)
+        self._dt = params.initial_dt
+        self._dx = params.dx
+        self._dz = params.dz
+        self._cfl_cutoff = params.cfl_cutoff
+        self._xp = xp
+        self._order = params.integrator_order
+        self._ctx = _backend.context_for(params)
+        if params.integrator_order == 2:
+            self.predictor = self._adams_bashforth_2
+            self.corrector = self._adams_moulton_2
+        elif params.integrator_order == 4:
+            self.predictor = self._adams_bashforth_4
+            self.corrector = self._adams_moulton_4
+        if params.integrator == "semi-implicit":
+            if params.is_fully_spectral():
+                self.integrate = self._semi_implicit_spectral
+                self._alpha = params.alpha
+        elif params.integrator == "explicit":
+            self.integrate = self._explicit
+            self._alpha = params.alpha
+
+    # -- stand-alone predictor / corrector formulas (Integrator.py:5-33); the fused
+    #    kernels evaluate the predictor themselves, these exist for API parity
+    def _adams_bashforth_2(self, dvar):
+        return self._dt / 2 * (3 * dvar.get() - dvar.get(-1))
+
+    def _adams_bashforth_4(self, dvar):
+        return self._dt / 24 * (55 * dvar.get() - 59 * dvar.get(-1)
+                                + 37 * dvar.get(-2) - 9 * dvar.get(-3))
+
+    def _adams_moulton_2(self, dvar):
+        return self._dt / 2 * (dvar.get() + dvar.get(-1))
+
+    def _adams_moulton_4(self, dvar):
+        return self._dt / 24 * (9 * dvar.get() + 19 * dvar.get(-1)
+                                - 5 * dvar.get(-2) + dvar.get(-3))
+
+    def set_dt(self, ux, uz):
+        """Sets dt based on CFL limit (Integrator.py:35-44; signed max)."""
+        mx = ux._cached_reduction(1) if hasattr(ux, "_cached_reduction") else None
+        mz = uz._cached_reduction(1) if hasattr(uz, "_cached_reduction") else None
+        if mx is None:
+            mx = self._xp.max(ux.getp())
+        if mz is None:
+            mz = self._xp.max(uz.getp())
+        with np.errstate(divide="ignore", invalid="ignore"):
+            cfl_dt = min(np.float64(self._dx) / np.float64(mx), np.float64(self._dz) / np.float64(mz))
+        if self._dt > cfl_dt or np.isnan(cfl_dt):
+            raise Exception("CFL condition breached")
+        while self._dt > self._cfl_cutoff * cfl_dt:
+            self._dt = self._dt * 0.9
+
+    def override_dt(self, dt):
+        """Manually set dt"""
+        self._dt = dt
+
+    def get_dt(self):
+        return self._dt
+
+    # -- the update
+    def _launch(self, var, dvar, scheme, lcoef, larr, extra):
+        """f0 = pending RHS (+ extra terms); var <- update; dvar.advance()."""
+        from .fields import Variable
+        ctx = self._ctx
+        order = self._order
+        pending, dvar._pending = dvar._pending, None
+        f0 = dvar._level(0)._t
+        older = [dvar._level(-k)._t for k in range(1, order)]
+        is_var = isinstance(var, Variable)
+        if is_var:
+            var._materialize_s()
+            q_in = var._s
+            double = var._has_dependants(q_in)
+            if double:
+                if var._s_spare is None:
+                    from .fields import _SpecHandle
+                    var._s_spare = _SpecHandle(_backend.empty(q_in.shape, np.complex128), var)
+                q_out = var._s_spare
+                var._flush_dependants(q_out)
+            else:
+                q_out = q_in
+        else:
+            q_in = q_out = var._touch()
+            double = False
+            var._pre_write()
+        g = _capi.Integ()
+        g.ab_order, g.scheme = order, scheme
+        g.dt, g.alpha, g.lcoef = float(self._dt), float(getattr(self, "_alpha", 0.0)), float(lcoef)
+        g.larr = larr._t.data_ptr() if larr is not None else None
+        g.q_in, g.q_out = q_in._t.data_ptr(), q_out._t.data_ptr()
+        g.f0, g.fm1 = f0.data_ptr(), older[0].data_ptr()
+        if order == 4:
+            g.fm2, g.fm3 = older[1].data_ptr(), older[2].data_ptr()
+        keep = [larr]
+        lin = list(extra)
+        fused = (pending is not None and 1 <= len(pending.nls) <= 2
+                 and len(pending.terms) + len(lin) <= 4)
+        if fused:
+            d = _capi.XFwd()
+            d.nf, d.mode = 2 * len(pending.nls), 1
+            for i, (coef, nl) in enumerate(pending.nls):
+                d.src[2 * i], d.src[2 * i + 1] = nl.ia.data_ptr(), nl.ib.data_ptr()
+                d.sym[2 * i], d.sym[2 * i + 1] = _capi.SYM_FDX, _capi.SYM_FDZ
+                d.coef[2 * i] = d.coef[2 * i + 1] = coef
+            lin = list(pending.terms) + lin
+            d.lin = _capi.make_lin_terms([(c, op, a._touch()._t.data_ptr()) for c, op, a in lin])
+            d.integ = g
+            ctx.call("mlv_x_forward", ctypes.byref(d))
+        else:
+            if pending is not None:
+                pending.materialize(out=dvar._level(0))
+            lt = _capi.make_lin_terms([(c, op, a._touch()._t.data_ptr()) for c, op, a in lin])
+            ctx.call("mlv_integrate", ctypes.byref(lt) if lin else None, ctypes.byref(g))
+        del keep
+        if double:
+            var._s, var._s_spare = q_out, q_in
+        dvar.advance()
+
+    def _explicit(self, var, dvar, diffusion_term):
+        """dvar += diffusion; var += AB(dvar); advance (Integrator.py:53-56)"""
+        if isinstance(diffusion_term, SpecExpr) and not diffusion_term.nls \
+                and len(diffusion_term.terms) <= 4:
+            extra = diffusion_term.terms
+        else:
+            extra = [(1.0 + 0j, _capi.OP_IDENT, _dev(diffusion_term, np.complex128))]
+        pend = dvar._pending
+        if pend is not None and (len(pend.terms) + len(extra) > 4 or not pend.nls):
+            dvar._flush()
+        self._launch(var, dvar, _capi.SCHEME_EXPLICIT, 0.0, None, extra)
+
+    def _semi_implicit_spectral(self, var, dvar, lin_op):
+        """theta-scheme with the AB predictor (Integrator.py:58-63)"""
+        if isinstance(lin_op, LazyLap):
+            self._launch(var, dvar, _capi.SCHEME_SI_LAP, lin_op.coef, None, [])
+        else:
+            larr = _dev(lin_op, np.float64)
+            if larr.is_complex or not larr._t.is_contiguous():
+                raise TypeError("lin_op must be a real contiguous spectral-shaped array")
+            self._launch(var, dvar, _capi.SCHEME_SI_ARR, 0.0, larr, [])
