@@ -147,6 +147,7 @@ int mlv_set_stream(mlv_ctx* ctx, void* cuda_stream);
 int mlv_get_info(const mlv_ctx* ctx, mlv_info* out);
 const char* mlv_last_error(void);
 int mlv_abi_version(void);
+long long mlv_launch_count(void);   /* kernels launched by the library so far (process-wide) */
 
 /* ---- transforms: SpectralTransformer.to_physical / to_spectral ------------
  * (melvin/SpectralTransformer.py:33-88 1-D, :90-199 2-D, COMPLEX_EXP bases) */

@@ -11,6 +11,7 @@
 namespace mlv {
 
 static thread_local char g_err[512] = "";
+unsigned long long g_launches = 0;     // kernels launched by this library (process-wide)
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -304,6 +305,8 @@ extern "C" {
 
 int mlv_abi_version(void) { return 1; }
 
+long long mlv_launch_count(void) { return (long long)g_launches; }
+
 const char* mlv_last_error(void) { return g_err; }
 
 int mlv_create(const mlv_params* p, mlv_ctx** out) {
@@ -547,9 +550,8 @@ int mlv_advect_z(mlv_ctx* c, const void* iux, const void* iuz, const void* iq, v
 #undef MLV_GO
     if (rc) return rc;
     if (red4) {
-        for (int w = 0; w < 4; ++w)
-            if ((rc = reduce_final(c, c->red, (int)grid, 4, w, w < 2 ? RED_MAX : RED_SUM, red4 + w)))
-                return rc;
+        auto kfn = k_reduce_final4;
+        MLV_LAUNCH(kfn, 4u, 256u, 256 * sizeof(double), c->stream, (const double*)c->red, (int)grid, red4);
     }
     return MLV_OK;
 }

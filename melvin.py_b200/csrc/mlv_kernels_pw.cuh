@@ -288,6 +288,31 @@ k_reduce_final(const double* partial, int n, int stride, int off, int op, double
     if (threadIdx.x == 0) out[0] = sm[0];
 }
 
+// final stage of the fused z stage's reductions: block w combines column w of the
+// [n][4] partials (w < 2: max, else sum) into out[w]
+__global__ void __launch_bounds__(256) k_reduce_final4(const double* partial, int n, double* out) {
+    double* sm = reinterpret_cast<double*>(MLV_SMEM_BASE());
+    const int w = blockIdx.x;
+    const int op = w < 2 ? RED_MAX : RED_SUM;
+    double acc = red_identity(op);
+    bool nan = false;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double x = partial[(size_t)i * 4 + w];
+        nan = nan || (x != x);
+        acc = red_combine(op, acc, x);
+    }
+    sm[threadIdx.x] = nan ? NAN : acc;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) {
+            const double x = sm[threadIdx.x], y = sm[threadIdx.x + s];
+            sm[threadIdx.x] = (x != x || y != y) ? NAN : red_combine(op, x, y);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[w] = sm[0];
+}
+
 // ------------------------------------------------------- tridiagonal solve
 // nn independent systems (LaplacianSolver.py:22-56):  rows 1..nz-2:
 //   x[i-1]/dz^2 - (kx_n^2 + 2/dz^2) x[i] + x[i+1]/dz^2 = rhs[i],  x[0]=rhs[0], x[nz-1]=rhs[nz-1].

@@ -12,6 +12,7 @@
 namespace mlv {
 
 void set_error(const char* fmt, ...);
+extern unsigned long long g_launches;
 
 #ifdef MLV_EMU
 typedef void* stream_t;
@@ -27,6 +28,7 @@ inline size_t rt_max_smem() { return 232448; }
             return MLV_ERR_UNSUPPORTED;                                                   \
         }                                                                                 \
         mlv::emu_launch((grid), (block), (smem), [=]() { kfn(__VA_ARGS__); });            \
+        ++mlv::g_launches;                                                                \
     } while (0)
 #else
 typedef cudaStream_t stream_t;
@@ -59,6 +61,7 @@ inline size_t rt_max_smem() { return 232448; }   // 227 KB opt-in per CTA on sm_
         kfn<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                          \
         cudaError_t e2_ = cudaGetLastError();                                             \
         if (e2_ != cudaSuccess) return mlv::rt_check(e2_, #kfn);                          \
+        ++mlv::g_launches;                                                                \
     } while (0)
 #endif
 

@@ -63,8 +63,9 @@ def count_launch(n=1):
 
 
 def launches():
-    """Number of library calls that enqueued kernels since process start."""
-    return _state["launches"]
+    """Number of kernels the library has launched since process start
+    (counted inside libmelvin_b200.so at every launch site)."""
+    return int(lib().mlv_launch_count())
 
 
 def call_counts():

@@ -19,7 +19,7 @@ RED_SUM, RED_MAX, RED_MIN, RED_SUMSQ, RED_SUMPROD = range(5)
 
 EXPORTS = [
     "mlv_create", "mlv_destroy", "mlv_set_stream", "mlv_get_info", "mlv_last_error",
-    "mlv_abi_version", "mlv_to_physical", "mlv_to_spectral", "mlv_x_inverse",
+    "mlv_abi_version", "mlv_launch_count", "mlv_to_physical", "mlv_to_spectral", "mlv_x_inverse",
     "mlv_z_inverse", "mlv_z_forward", "mlv_x_forward", "mlv_advect_z", "mlv_advect_phys",
     "mlv_spec_lincomb", "mlv_lap_array", "mlv_stencil", "mlv_solve_fdm", "mlv_integrate",
     "mlv_elementwise", "mlv_reduce",
@@ -120,6 +120,8 @@ def declare(lib):
         fn.restype = C.c_int
     lib.mlv_last_error.argtypes = []
     lib.mlv_last_error.restype = C.c_char_p
+    lib.mlv_launch_count.argtypes = []
+    lib.mlv_launch_count.restype = C.c_longlong
     if lib.mlv_abi_version() != ABI_VERSION:
         raise MlvError("libmelvin_b200 ABI version mismatch")
     return lib

@@ -1,0 +1,227 @@
+"""Kernel-level cases driven straight through the C ABI (include/melvin_b200.h).
+
+Each case takes a harness ``H`` providing ``H.Ctx(nx, nz, lx, lz, fdm_z=, fd_order=)``
+(with ``.call(name, *args)``, ``.ibuf()``, ``.close()``) and ``H.ptr(numpy_array)``:
+  * tests/gpu_harness.py  -- the real library on a CUDA device (``-m gpu`` tests);
+  * tests/emu/emu_harness.py -- the host emulation build (development, CPU box).
+Expected values always come from the oracle.
+"""
+import ctypes
+
+import numpy as np
+
+from melvin import _capi
+from oracle import melvin_oracle as mo
+
+SIZES_2D = [(16, 16), (32, 64), (64, 32), (128, 16), (256, 128), (512, 32), (16, 1024),
+            (2048, 16), (16, 2048), (4096, 16), (16, 4096), (8192, 16), (16, 8192)]
+SIZES_1D = [(16, 16), (64, 13), (64, 32), (256, 24), (1024, 6)]
+SIZES_FUSED = [(32, 64), (64, 32), (256, 64)]
+
+
+def rel(a, b):
+    return np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-300)
+
+
+SIZES_2D = [(16, 16), (32, 64), (64, 32), (128, 16), (256, 128), (512, 32), (16, 1024),
+            (2048, 16), (16, 2048), (4096, 16), (16, 4096), (8192, 16), (16, 8192)]
+
+
+def case_transforms_2d(H, nx, nz, tol=1e-14):
+    g = mo.Grid(nx, nz, 1.5, 1.0)
+    ctx = H.Ctx(nx, nz, 1.5, 1.0)
+    rng = np.random.default_rng(nx * 1000 + nz)
+    phys = rng.standard_normal((nx, nz))
+    spec = np.zeros(g.spectral_shape, complex)
+    I = ctx.ibuf()
+    ctx.call("mlv_to_spectral", H.ptr(phys), H.ptr(I), H.ptr(spec))
+    assert rel(spec, mo.to_spectral(g, phys)) < tol
+    srand = rng.standard_normal(g.spectral_shape) + 1j * rng.standard_normal(g.spectral_shape)
+    out = np.zeros((nx, nz))
+    ctx.call("mlv_to_physical", H.ptr(srand), H.ptr(I), H.ptr(out))
+    assert rel(out, mo.to_physical(g, srand)) < tol
+    ctx.close()
+
+
+def case_transforms_1d_fdm(H, nx, nz, tol=1e-14):
+    g = mo.Grid(nx, nz, 2.44, 1.0, fdm_z=True)
+    ctx = H.Ctx(nx, nz, 2.44, 1.0, fdm_z=True)
+    rng = np.random.default_rng(7)
+    phys = rng.standard_normal((nx, nz))
+    spec = np.zeros(g.spectral_shape, complex)
+    ctx.call("mlv_to_spectral", H.ptr(phys), None, H.ptr(spec))
+    assert rel(spec, mo.to_spectral(g, phys)) < tol
+    srand = rng.standard_normal(g.spectral_shape) + 1j * rng.standard_normal(g.spectral_shape)
+    out = np.zeros((nx, nz))
+    ctx.call("mlv_to_physical", H.ptr(srand), None, H.ptr(out))
+    assert rel(out, mo.to_physical(g, srand)) < tol
+    ctx.close()
+
+
+def case_fused_advection_step(H, nx, nz, order, tol=1e-13):
+    """x-inverse (velocity prologue) -> fused z stage -> x-forward with stencil
+    symbols == oracle vec_dot_nabla on oracle velocities."""
+    g = mo.Grid(nx, nz, 1.5, 1.0, fd_order=order)
+    ctx = H.Ctx(nx, nz, 1.5, 1.0, fd_order=order)
+    rng = np.random.default_rng(3)
+    w = mo.to_spectral(g, rng.standard_normal((nx, nz)))
+    q = mo.to_spectral(g, rng.standard_normal((nx, nz)))
+    vel = mo.velocity_from_vorticity(g, w)
+    want, _ = mo.vec_dot_nabla(g, q, vel["ux_p"], vel["uz_p"])
+
+    Iux, Iuz, Iq, IA, IB = (ctx.ibuf() for _ in range(5))
+    srcs = (ctypes.c_void_p * 3)(H.ptr(w), H.ptr(w), H.ptr(q))
+    ops = (ctypes.c_int32 * 3)(_capi.OP_UX, _capi.OP_UZ, _capi.OP_IDENT)
+    dsts = (ctypes.c_void_p * 3)(H.ptr(Iux), H.ptr(Iuz), H.ptr(Iq))
+    ctx.call("mlv_x_inverse", 3, srcs, ops, dsts)
+    red = np.zeros(4)
+    ctx.call("mlv_advect_z", H.ptr(Iux), H.ptr(Iuz), H.ptr(Iq), H.ptr(IA), H.ptr(IB), H.ptr(red))
+    np.testing.assert_allclose(red[0], vel["ux_p"].max(), rtol=1e-13)
+    np.testing.assert_allclose(red[1], vel["uz_p"].max(), rtol=1e-13)
+    np.testing.assert_allclose(red[2], (vel["ux_p"] ** 2).sum(), rtol=1e-13)
+    np.testing.assert_allclose(red[3], (vel["uz_p"] ** 2).sum(), rtol=1e-13)
+
+    got = np.zeros(g.spectral_shape, complex)
+    d = _capi.XFwd()
+    d.nf, d.mode = 2, 0
+    d.src[0], d.src[1] = H.ptr(IA), H.ptr(IB)
+    d.sym[0], d.sym[1] = _capi.SYM_FDX, _capi.SYM_FDZ
+    d.coef[0] = d.coef[1] = 1.0
+    d.dst = H.ptr(got)
+    ctx.call("mlv_x_forward", ctypes.byref(d))
+    assert rel(got, want) < tol
+
+    # fused epilogue: f0 = -N + 0.3*ddx(q); theta-scheme AB2 update of w
+    hist = mo.History(g)
+    hist.data[1] = rng.standard_normal(g.spectral_shape) + 0j
+    hist.curr = 0
+    f0_want = -want + 0.3 * mo.sddx(g, q)
+    hist.set_current(f0_want)
+    w_want = mo.integrate_semi_implicit(g, w.copy(), hist, 0.02 * mo.lap_symbol(g), 1e-3)
+    f0 = np.zeros(g.spectral_shape, complex)
+    fm1 = hist.data[1].copy()
+    w_new = np.zeros(g.spectral_shape, complex)
+    d.mode = 1
+    d.coef[0] = d.coef[1] = -1.0
+    d.lin = _capi.make_lin_terms([(0.3, _capi.OP_DDX, H.ptr(q))])
+    d.integ.ab_order, d.integ.scheme = 2, _capi.SCHEME_SI_LAP
+    d.integ.dt, d.integ.alpha, d.integ.lcoef = 1e-3, g.alpha, 0.02
+    d.integ.q_in, d.integ.q_out = H.ptr(w), H.ptr(w_new)
+    d.integ.f0, d.integ.fm1 = H.ptr(f0), H.ptr(fm1)
+    ctx.call("mlv_x_forward", ctypes.byref(d))
+    assert rel(f0, f0_want) < tol
+    assert rel(w_new, w_want) < tol
+    ctx.close()
+
+
+def case_pointwise_and_stencils(H):
+    nx, nz = 32, 64
+    g = mo.Grid(nx, nz, 1.5, 1.0)
+    ctx = H.Ctx(nx, nz, 1.5, 1.0)
+    rng = np.random.default_rng(5)
+    s = rng.standard_normal(g.spectral_shape) + 1j * rng.standard_normal(g.spectral_shape)
+    out = np.zeros_like(s)
+    for op, fn in ((_capi.OP_DDX, mo.sddx), (_capi.OP_DDZ, mo.sddz), (_capi.OP_D2DX2, mo.sd2dx2),
+                   (_capi.OP_D2DZ2, mo.sd2dz2), (_capi.OP_LAP, mo.snabla2),
+                   (_capi.OP_INVLAP, mo.solve_spectral)):
+        lt = _capi.make_lin_terms([(1.0, op, H.ptr(s))])
+        ctx.call("mlv_spec_lincomb", ctypes.byref(lt), H.ptr(out))
+        assert rel(out, fn(g, s)) < 1e-15, op
+    vel = mo.velocity_from_vorticity(g, s)
+    for op, key in ((_capi.OP_PSI, "psi_s"), (_capi.OP_UX, "ux_s"), (_capi.OP_UZ, "uz_s")):
+        lt = _capi.make_lin_terms([(1.0, op, H.ptr(s))])
+        ctx.call("mlv_spec_lincomb", ctypes.byref(lt), H.ptr(out))
+        assert rel(out, vel[key]) < 1e-15, key
+    lap = np.zeros(g.spectral_shape)
+    ctx.call("mlv_lap_array", 0.5, H.ptr(lap))
+    assert rel(lap, 0.5 * mo.lap_symbol(g)) < 1e-15
+    f = rng.standard_normal((nx, nz))
+    o = np.zeros_like(f)
+    for order in (2, 4):
+        go = mo.Grid(nx, nz, 1.5, 1.0, fd_order=order)
+        ctx.call("mlv_stencil", H.ptr(f), H.ptr(o), nx, nz, 1, 0, order, 1, 0, go.dx)
+        assert rel(o, mo.pddx(go, f)) < 1e-14
+        ctx.call("mlv_stencil", H.ptr(f), H.ptr(o), nx, nz, 1, 1, order, 1, 0, go.dz)
+        assert rel(o, mo.pddz(go, f)) < 1e-14
+    ctx.close()
+
+
+def case_fdm_solver_and_stencils(H):
+    nx, nz = 64, 40
+    for order in (2, 4):
+        g = mo.Grid(nx, nz, 2.44, 1.0, fdm_z=True, fd_order=order)
+        ctx = H.Ctx(nx, nz, 2.44, 1.0, fdm_z=True, fd_order=order)
+        rng = np.random.default_rng(11)
+        s = rng.standard_normal(g.spectral_shape) + 1j * rng.standard_normal(g.spectral_shape)
+        out = np.zeros_like(s)
+        ctx.call("mlv_solve_fdm", H.ptr(s), H.ptr(out))
+        assert rel(out, mo.solve_fdm(g, s)) < 1e-13
+        ctx.call("mlv_stencil", H.ptr(s), H.ptr(out), g.nn, nz, 2, 1, order, 0, 1, g.dz)
+        assert rel(out, mo.pd2dz2(g, s)) < 1e-14
+        f = rng.standard_normal((nx, nz))
+        o = np.zeros_like(f)
+        ctx.call("mlv_stencil", H.ptr(f), H.ptr(o), nx, nz, 1, 1, order, 0, 0, g.dz)
+        assert rel(o, mo.pddz(g, f)) < 1e-14
+        ux, uz = rng.standard_normal((nx, nz)), rng.standard_normal((nx, nz))
+        ctx.call("mlv_advect_phys", H.ptr(ux), H.ptr(uz), H.ptr(f), H.ptr(o))
+        assert rel(o, mo.pddx(g, ux * f) + mo.pddz(g, uz * f)) < 1e-14
+        ctx.close()
+
+
+def case_integrate_and_array_ops(H):
+    nx, nz = 32, 32
+    ctx = H.Ctx(nx, nz, 1.0, 1.0)
+    rng = np.random.default_rng(2)
+    for order in (2, 4):
+        g = mo.Grid(nx, nz, 1.0, 1.0, int_order=order)
+        shape = g.spectral_shape
+        q = rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+        hist = mo.History(g)
+        hist.data[:] = rng.standard_normal(hist.data.shape) + 1j * rng.standard_normal(hist.data.shape)
+        hist.curr = 1
+        diff = rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+        levels = [hist.data[(hist.curr - k) % order].copy() for k in range(order)]
+        h2 = mo.History(g)
+        h2.data[:] = hist.data
+        h2.curr = hist.curr
+        want = mo.integrate_explicit(g, q.copy(), h2, diff, 1e-2)
+        out = np.zeros_like(q)
+        ig = _capi.Integ()
+        ig.ab_order, ig.scheme, ig.dt, ig.alpha = order, _capi.SCHEME_EXPLICIT, 1e-2, 0.51
+        ig.q_in, ig.q_out, ig.f0 = H.ptr(q), H.ptr(out), H.ptr(levels[0])
+        ig.fm1 = H.ptr(levels[1])
+        if order == 4:
+            ig.fm2, ig.fm3 = H.ptr(levels[2]), H.ptr(levels[3])
+        lt = _capi.make_lin_terms([(1.0, _capi.OP_IDENT, H.ptr(diff))])
+        ctx.call("mlv_integrate", ctypes.byref(lt), ctypes.byref(ig))
+        assert rel(out, want) < 1e-15
+        assert rel(levels[0], h2.data[hist.curr]) < 1e-15
+        L = rng.standard_normal(shape)
+        h3 = mo.History(g)
+        h3.data[:] = hist.data
+        h3.curr = hist.curr
+        want = mo.integrate_semi_implicit(g, q.copy(), h3, L, 1e-2)
+        levels[0] = hist.data[hist.curr].copy()
+        ig.scheme, ig.larr, ig.f0 = _capi.SCHEME_SI_ARR, H.ptr(L), H.ptr(levels[0])
+        ctx.call("mlv_integrate", None, ctypes.byref(ig))
+        assert rel(out, want) < 1e-15
+    # elementwise on strided views + reductions
+    a = rng.standard_normal((20, 30))
+    b = rng.standard_normal((20, 30))
+    o = np.zeros((10, 15))
+    e = _capi.Ew()
+    e.op, e.rows, e.cols = _capi.EW_MUL, 10, 15
+    e.out_kind, e.a_kind, e.b_kind = _capi.KIND_REAL, _capi.KIND_REAL, _capi.KIND_REAL
+    e.out = _capi.View(H.ptr(o), 15, 1)
+    e.a = _capi.View(H.ptr(a), 60, 2)
+    e.b = _capi.View(H.ptr(b[10:]), 30, 1)
+    ctx.call("mlv_elementwise", ctypes.byref(e))
+    np.testing.assert_allclose(o, a[::2, ::2] * b[10:, :15], rtol=1e-15)
+    r = np.zeros(1)
+    va = _capi.View(H.ptr(a), 30, 1)
+    vb = _capi.View(H.ptr(b), 30, 1)
+    for op, want in ((_capi.RED_SUM, a.sum()), (_capi.RED_MAX, a.max()), (_capi.RED_MIN, a.min()),
+                     (_capi.RED_SUMSQ, (a * a).sum()), (_capi.RED_SUMPROD, (a * b).sum())):
+        ctx.call("mlv_reduce", op, 20, 30, ctypes.byref(va), ctypes.byref(vb), H.ptr(r))
+        np.testing.assert_allclose(r[0], want, rtol=1e-13)
+    ctx.close()

@@ -64,3 +64,6 @@ class EmuCtx:
 
     def close(self):
         self.lib.mlv_destroy(self.h)
+
+
+Ctx = EmuCtx

@@ -1,0 +1,78 @@
+"""Parity tests of the CUDA kernels through the C ABI (device run of abi_cases.py),
+plus full-size checks on the BASELINE grid (4096^2) against the oracle and through
+size-independent properties."""
+import ctypes
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import abi_cases as ac  # noqa: E402
+from conftest import rel_l2  # noqa: E402
+from oracle import melvin_oracle as mo  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def H():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("-m gpu tests need a CUDA device")
+    import gpu_harness
+    return gpu_harness
+
+
+@pytest.mark.parametrize("nx,nz", ac.SIZES_2D + [(1024, 1024)])
+def test_transforms_2d(H, nx, nz):
+    ac.case_transforms_2d(H, nx, nz)
+
+
+@pytest.mark.parametrize("nx,nz", ac.SIZES_1D + [(2048, 512)])
+def test_transforms_1d_fdm(H, nx, nz):
+    ac.case_transforms_1d_fdm(H, nx, nz)
+
+
+@pytest.mark.parametrize("order", [2, 4])
+@pytest.mark.parametrize("nx,nz", ac.SIZES_FUSED + [(1024, 512)])
+def test_fused_advection_step(H, nx, nz, order):
+    ac.case_fused_advection_step(H, nx, nz, order)
+
+
+def test_pointwise_and_stencils(H):
+    ac.case_pointwise_and_stencils(H)
+
+
+def test_fdm_solver_and_stencils(H):
+    ac.case_fdm_solver_and_stencils(H)
+
+
+def test_integrate_and_array_ops(H):
+    ac.case_integrate_and_array_ops(H)
+
+
+def test_full_size_4096_transforms_and_properties(H):
+    """BASELINE config-2 grid: transform parity vs the oracle (pocketfft), round trip
+    (idempotence on the retained band) and linearity."""
+    nx = nz = 4096
+    g = mo.Grid(nx, nz, 16.0 / 9.0, 1.0)
+    ctx = H.Ctx(nx, nz, g.lx, g.lz)
+    rng = np.random.default_rng(42)
+    phys = rng.standard_normal((nx, nz))
+    spec = np.zeros(g.spectral_shape, complex)
+    I = ctx.ibuf()
+    ctx.call("mlv_to_spectral", H.ptr(phys), H.ptr(I), H.ptr(spec))
+    assert rel_l2(spec, mo.to_spectral(g, phys)) < 1e-13
+    back = np.zeros((nx, nz))
+    ctx.call("mlv_to_physical", H.ptr(spec), H.ptr(I), H.ptr(back))
+    assert rel_l2(back, mo.to_physical(g, spec)) < 1e-13
+    spec2 = np.zeros_like(spec)
+    ctx.call("mlv_to_spectral", H.ptr(back), H.ptr(I), H.ptr(spec2))
+    assert rel_l2(spec2, spec) < 1e-13                       # band-limited round trip
+    other = rng.standard_normal((nx, nz))
+    so = np.zeros_like(spec)
+    ctx.call("mlv_to_spectral", H.ptr(other), H.ptr(I), H.ptr(so))
+    comb = np.zeros_like(spec)
+    mix = 0.3 * phys - 1.7 * other
+    ctx.call("mlv_to_spectral", H.ptr(mix), H.ptr(I), H.ptr(comb))
+    assert rel_l2(comb, 0.3 * spec - 1.7 * so) < 1e-13       # linearity
+    ctx.close()
