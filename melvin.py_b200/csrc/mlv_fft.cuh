@@ -40,7 +40,8 @@ struct FftCfg {
     static constexpr int Q = LOG2N & 3;
     static constexpr int R0 = Q ? (1 << Q) : 16;         // first-pass radix
     static constexpr int NPASS = (LOG2N >> 2) + (Q ? 1 : 0);
-    static constexpr int XSLOTS = N + N / 16;            // exchange slots per line
+    static constexpr int XSLOTS = (N + N / 16 + 1) & ~1; // exchange slots per line (even: keeps
+                                                         // per-line buffers 16-byte aligned)
     // sub-problem length left after pass p
     __host__ __device__ static constexpr int n3(int p) {
         int n = N / R0;
