@@ -78,26 +78,37 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                 "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            t0 = time.time()
+            while not self.lines and time.time() - t0 < 5.0:     # wait for the first sample
+                time.sleep(0.02)
         except OSError:
             self.proc = None
         return self
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def mark(self):
+        return time.time()
 
     def __exit__(self, *exc):
         if self.proc is not None:
+            time.sleep(0.06)
             self.proc.terminate()
             self.thread.join(timeout=2)
 
-    def summary(self):
+    def summary(self, t_begin=None, t_end=None):
         sm, smmax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
+        window = [ln for ts, ln in self.lines
+                  if (t_begin is None or ts >= t_begin) and (t_end is None or ts <= t_end + 0.06)]
+        if len(window) < 2:          # very short timed region: use every sample taken under load
+            window = [ln for _, ln in self.lines]
+        for line in window:
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 7:
                 continue
@@ -215,21 +226,21 @@ def gpu_arm(args, rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
-
     # ---- device-resident throughput (state in HBM, CUDA events, max over ranks)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n_before = _backend.launches()
     with ClockSampler(local) as clk:
+        for _ in range(max(args.warmup, 3)):
+            step()
         barrier()
+        n_before = _backend.launches()
+        t_begin = clk.mark()
         e0.record()
         for _ in range(args.steps):
             step()
         e1.record()
         barrier()
-    launches = _backend.launches() - n_before
+        t_end = clk.mark()
+        launches = _backend.launches() - n_before
     ms = e0.elapsed_time(e1)
     if world > 1:
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
@@ -348,7 +359,7 @@ def gpu_arm(args, rank, world):
                 "l2": "working set ~1 GB per step and >= 0.4 GB per kernel launch, larger than the "
                       "126 MB L2; no flush between iterations",
             },
-            "clocks": clk.summary(),
+            "clocks": clk.summary(t_begin, t_end),
             "roofline": roofline,
             "cpu_baseline": cpu,
             "e2e": e2e,
@@ -362,8 +373,8 @@ def gpu_arm(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nx", type=int, default=4096)
     ap.add_argument("--nz", type=int, default=4096)

@@ -62,10 +62,12 @@ static void build_tables(std::vector<cplx>& host, size_t (&offs)[MLV_MAX_PASS]) 
         if (n3 <= 1) continue;
         offs[p] = host.size();
         const long double ncur = (long double)r * n3;
-        for (int d = 1; d < r; ++d)
-            for (int n = 0; n < n3; ++n) {
-                // exp(-2 pi i n d / ncur), argument reduced exactly in integers
-                const long long e = ((long long)n * d) % (long long)ncur;
+        int lr = 0;
+        while ((1 << lr) < r) ++lr;
+        for (int n = 0; n < n3; ++n)
+            for (int b = 0; b < lr; ++b) {
+                // exp(-2 pi i n 2^b / ncur), argument reduced exactly in integers
+                const long long e = ((long long)n << b) % (long long)ncur;
                 const long double ang = -2.0L * 3.14159265358979323846264338327950288L * (long double)e / ncur;
                 host.push_back(mk((double)cosl(ang), (double)sinl(ang)));
             }
@@ -218,7 +220,7 @@ static int launch_xinv(mlv_ctx* c, XInvArgs& a) {
     constexpr int C = xcols(L);
     typedef FftCfg<L> F;
     auto kfn = k_xinv<L, C>;
-    const size_t smem = (size_t)F::XSLOTS * C * sizeof(cplx);
+    const size_t smem = ((size_t)F::XSLOTS + (size_t)(2 * a.nn + 1)) * C * sizeof(cplx);
     const unsigned grid = (unsigned)((a.nm + C - 1) / C);
     MLV_LAUNCH(kfn, grid, (unsigned)(C * F::T), smem, c->stream, a);
     return 0;
@@ -229,8 +231,7 @@ static int launch_xfwd(mlv_ctx* c, XFwdArgs& a) {
     constexpr int C = xcols(L);
     typedef FftCfg<L> F;
     auto kfn = k_xfwd<L, C>;
-    size_t smem = (size_t)F::XSLOTS * C * sizeof(cplx);
-    if (a.nf > 1) smem += (size_t)(2 * a.nn + 1) * C * sizeof(cplx);
+    const size_t smem = ((size_t)F::XSLOTS + (size_t)(2 * a.nn + 1)) * C * sizeof(cplx);
     const unsigned grid = (unsigned)((a.nm + C - 1) / C);
     MLV_LAUNCH(kfn, grid, (unsigned)(C * F::T), smem, c->stream, a);
     return 0;
@@ -263,7 +264,8 @@ static int launch_zadv(mlv_ctx* c, ZAdvArgs& a, unsigned& grid_out) {
     constexpr int LPC = zlines(L);
     typedef FftCfg<L> F;
     auto kfn = k_z_advect<L, LPC>;
-    const size_t smem = (size_t)LPC * (F::XSLOTS * sizeof(double) + (size_t)F::N * sizeof(cplx));
+    const size_t smem = (size_t)LPC * (F::XSLOTS * sizeof(double) + (size_t)F::N * sizeof(cplx)) +
+                        (size_t)4 * LPC * F::T * sizeof(double);
     const unsigned grid = (unsigned)((a.nx / 2 + LPC - 1) / LPC);
     grid_out = grid;
     int rc = ensure_red(c, (size_t)grid * 4);

@@ -46,7 +46,25 @@ extern __shared__ __align__(16) unsigned char mlv_dyn_smem[];
 #define MLV_SMEM_BASE() (mlv_dyn_smem)
 #endif
 
+// compiler-only fence: keeps memory operations (and the registers they need) of one
+// kernel phase from being hoisted into the previous one
+#ifdef MLV_EMU
+#define MLV_SCHED_FENCE() do {} while (0)
+#else
+#define MLV_SCHED_FENCE() asm volatile("" ::: "memory")
+#endif
+
 #define MLV_DEV __device__ __forceinline__
+
+// Returns x, but hides the value from common-subexpression elimination: index and
+// address arithmetic derived from it is recomputed per kernel phase instead of being
+// kept live (and spilled) across whole transforms.
+__device__ __forceinline__ int opaque_int(int x) {
+#ifndef MLV_EMU
+    asm volatile("" : "+r"(x));
+#endif
+    return x;
+}
 #define MLV_HD __host__ __device__ __forceinline__
 
 namespace mlv {
@@ -70,5 +88,21 @@ MLV_HD cplx cmulc(cplx a, cplx b) {
 MLV_HD cplx cmuli(cplx a) { return mk(-a.y, a.x); }
 // multiply by -i
 MLV_HD cplx cmulni(cplx a) { return mk(a.y, -a.x); }
+
+// Reciprocal to ~1 ulp without the branchy IEEE division sequence: 20-bit hardware
+// seed + two Newton steps (operands here are O(1)..O(1e9), never denormal or zero).
+MLV_DEV double fast_rcp(double x) {
+#if defined(MLV_EMU)
+    return 1.0 / x;
+#else
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+#endif
+}
 
 }  // namespace mlv

@@ -26,8 +26,8 @@ namespace mlv {
 
 #define MLV_MAX_PASS 4
 
-// Per-pass twiddle tables (device pointers).  Table p has (R_p-1)*N3_p entries
-//   tw[(d-1)*N3 + n] = exp(-2 pi i n d / (R_p N3_p));   unused when N3_p == 1.
+// Per-pass twiddle tables (device pointers).  Table p has N3_p rows of log2(R_p) entries
+//   tw[n*log2(R) + b] = exp(-2 pi i n 2^b / (R_p N3_p));   unused when N3_p == 1.
 struct FftTw {
     const cplx* p[MLV_MAX_PASS];
 };
@@ -162,17 +162,80 @@ MLV_HD void pass_butterflies(cplx (&v)[16]) {
     }
 }
 
-// v[u + U d] *= W_{R N3}^{n'' d},  n'' = (tau + T u) mod N3
-template <int R, int N3, int T, bool INV>
-MLV_DEV void pass_twiddle(cplx (&v)[16], int tau, const cplx* __restrict__ tw) {
-    constexpr int U = 16 / R;
+// ---------------------------------------------------------------- twiddles
+// After a radix-R pass:  v[u + U d] *= W_{R N3}^{n'' d},  n'' = (tau + T u) mod N3.
+// The kernels leave almost no L1 (shared memory takes ~all of the 228 KB), so a
+// table lookup per factor costs an L2 round trip each.  Only the log2(R) "binary"
+// powers  w^1, w^2, w^4, w^8  are tabulated (table row n'' = log2(R) entries); the
+// other powers are products of those (depth <= 3, error a few ulp).  The loads are
+// issued before the butterfly of the pass so that their latency hides behind it.
+template <int R> struct Log2R { static constexpr int v = R == 16 ? 4 : R == 8 ? 3 : R == 4 ? 2 : 1; };
+
+template <int R, int N3, int T>
+MLV_DEV void tw_fetch(cplx (&wb)[4], int tau, int u, const cplx* tw) {
+    constexpr int LR = Log2R<R>::v;
+    const int n = (tau + T * u) & (N3 - 1);
     MLV_UNROLL
-    for (int u = 0; u < U; ++u) {
-        const int n = (tau + T * u) & (N3 - 1);
+    for (int b = 0; b < LR; ++b) wb[b] = tw[n * LR + b];
+}
+
+template <bool INV>
+MLV_HD cplx tw_mul(cplx a, cplx w) { return INV ? cmulc(a, w) : cmul(a, w); }
+
+template <int R, bool INV>
+MLV_HD void tw_apply(cplx (&v)[16], int u, const cplx (&wb)[4]) {
+    constexpr int U = 16 / R;
+#define MLV_V(d) v[u + U * (d)]
+    const cplx w1 = wb[0];
+    MLV_V(1) = tw_mul<INV>(MLV_V(1), w1);
+    if constexpr (R >= 4) {
+        const cplx w2 = wb[1];
+        const cplx w3 = cmul(w1, w2);
+        MLV_V(2) = tw_mul<INV>(MLV_V(2), w2);
+        MLV_V(3) = tw_mul<INV>(MLV_V(3), w3);
+        if constexpr (R >= 8) {
+            const cplx w4 = wb[2];
+            const cplx w5 = cmul(w1, w4), w6 = cmul(w2, w4), w7 = cmul(w3, w4);
+            MLV_V(4) = tw_mul<INV>(MLV_V(4), w4);
+            MLV_V(5) = tw_mul<INV>(MLV_V(5), w5);
+            MLV_V(6) = tw_mul<INV>(MLV_V(6), w6);
+            MLV_V(7) = tw_mul<INV>(MLV_V(7), w7);
+            if constexpr (R >= 16) {
+                const cplx w8 = wb[3];
+                MLV_V(8) = tw_mul<INV>(MLV_V(8), w8);
+                MLV_V(9) = tw_mul<INV>(MLV_V(9), cmul(w1, w8));
+                MLV_V(10) = tw_mul<INV>(MLV_V(10), cmul(w2, w8));
+                MLV_V(11) = tw_mul<INV>(MLV_V(11), cmul(w3, w8));
+                MLV_V(12) = tw_mul<INV>(MLV_V(12), cmul(w4, w8));
+                MLV_V(13) = tw_mul<INV>(MLV_V(13), cmul(w5, w8));
+                MLV_V(14) = tw_mul<INV>(MLV_V(14), cmul(w6, w8));
+                MLV_V(15) = tw_mul<INV>(MLV_V(15), cmul(w7, w8));
+            }
+        }
+    }
+#undef MLV_V
+}
+
+// butterflies + twiddles of one pass (R, N3); N3 == 1: no twiddles
+template <int R, int N3, int T, bool INV>
+MLV_DEV void fft_pass(cplx (&v)[16], int tau, const cplx* tw) {
+    constexpr int U = 16 / R;
+    if constexpr (N3 == 1) {
+        pass_butterflies<R, INV>(v);
+    } else if constexpr (U == 1) {
+        cplx wb[4];
+        MLV_SCHED_FENCE();            // keep the table loads inside this pass
+        tw_fetch<R, N3, T>(wb, tau, 0, tw);
+        pass_butterflies<R, INV>(v);
+        tw_apply<R, INV>(v, 0, wb);
+    } else {
+        pass_butterflies<R, INV>(v);
+        MLV_SCHED_FENCE();
         MLV_UNROLL
-        for (int d = 1; d < R; ++d) {
-            const cplx w = __ldg(&tw[(d - 1) * N3 + n]);
-            v[u + U * d] = INV ? cmulc(v[u + U * d], w) : cmul(v[u + U * d], w);
+        for (int u = 0; u < U; ++u) {
+            cplx wb[4];
+            tw_fetch<R, N3, T>(wb, tau, u, tw);
+            tw_apply<R, INV>(v, u, wb);
         }
     }
 }
@@ -228,24 +291,19 @@ MLV_DEV void fft_later_passes(cplx (&v)[16], const int tau, const FftTw& tw, X& 
         v,
         [&](int j) { const int L = tau + C::T * j; return PAD ? L + (L >> 4) : L; },
         [&](int j) { const int L = lo + N3 * j + 16 * N3 * hi; return PAD ? L + (L >> 4) : L; });
-    bfly16<INV>(v);
-    if constexpr (N3 > 1) {
-        pass_twiddle<16, N3, C::T, INV>(v, tau, tw.p[P]);
-        fft_later_passes<LOG2N, P + 1, INV, X>(v, tau, tw, xc);
-    }
+    fft_pass<16, N3, C::T, INV>(v, tau, tw.p[P]);
+    if constexpr (N3 > 1) fft_later_passes<LOG2N, P + 1, INV, X>(v, tau, tw, xc);
 }
 
 // In-register transform of one line.  All T threads of the line (and all
 // other lines sharing the CTA) must call this together (it contains CTA
 // barriers).  INV = unnormalised inverse (sum with exp(+...)).
 template <int LOG2N, bool INV, class X>
-MLV_DEV void fft_line(cplx (&v)[16], const int tau, const FftTw& tw, X& xc) {
+MLV_DEV void fft_line(cplx (&v)[16], const int tau_, const FftTw& tw, X& xc) {
     typedef FftCfg<LOG2N> C;
-    pass_butterflies<C::R0, INV>(v);
-    if constexpr (C::NPASS > 1) {
-        pass_twiddle<C::R0, C::n3(0), C::T, INV>(v, tau, tw.p[0]);
-        fft_later_passes<LOG2N, 1, INV, X>(v, tau, tw, xc);
-    }
+    const int tau = opaque_int(tau_);    // per-transform index arithmetic (see opaque_int)
+    fft_pass<C::R0, C::n3(0), C::T, INV>(v, tau, tw.p[0]);
+    if constexpr (C::NPASS > 1) fft_later_passes<LOG2N, 1, INV, X>(v, tau, tw, xc);
 }
 
 }  // namespace mlv

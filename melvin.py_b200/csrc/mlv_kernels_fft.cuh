@@ -59,11 +59,11 @@ MLV_DEV cplx spectral_op(int op, cplx s, int n, int m, const SpecConsts& k) {
     }
     double lap = lap_symbol(n, m, k);
     if (n == 0 && m == 0) lap = 1.0;
-    if (op == XOP_INVLAP) return mk(s.x / lap, s.y / lap);
-    const cplx psi = mk(-s.x / lap, -s.y / lap);
-    if (op == XOP_PSI) return psi;
-    if (op == XOP_UX) { const double b = k.kz0 * m; return mk(b * psi.y, -b * psi.x); }
-    /* XOP_UZ */ { const double b = k.kx0 * n; return mk(-b * psi.y, b * psi.x); }
+    const double r = fast_rcp(lap);
+    if (op == XOP_INVLAP) return mk(s.x * r, s.y * r);
+    if (op == XOP_PSI) return mk(-s.x * r, -s.y * r);
+    if (op == XOP_UX) { const double c = (k.kz0 * m) * r; return mk(-c * s.y, c * s.x); }
+    /* XOP_UZ */ { const double c = (k.kx0 * n) * r; return mk(c * s.y, -c * s.x); }
 }
 
 // FFT index k (0..N-1) -> spectral row r and signed mode n; false if truncated.
@@ -113,8 +113,8 @@ MLV_DEV void integrate_point(const IntegArgs& g, cplx f0, size_t idx, int n, int
     }
     const double L = (g.scheme == 0) ? g.lcoef * lap_symbol(n, m, k) : g.larr[idx];
     const double a = 1 + ((1 - g.alpha) * g.dt) * L;
-    const double b = 1 - (g.alpha * g.dt) * L;
-    g.q_out[idx] = mk((a * q.x + inc.x) / b, (a * q.y + inc.y) / b);
+    const double rb = fast_rcp(1 - (g.alpha * g.dt) * L);
+    g.q_out[idx] = mk((a * q.x + inc.x) * rb, (a * q.y + inc.y) * rb);
 }
 
 // Extra linear right-hand-side terms  sum_i coef_i * op_i(src_i)
@@ -146,28 +146,53 @@ struct XInvArgs {
     FftTw tw;
 };
 
-// spectral (2nn+1, nm) -> I (nx, ipitch); nf fields, each with its own prologue
+// spectral (2nn+1, nm) -> I (nx, ipitch); nf fields, each with its own prologue.
+// Shared memory: [ exchange XSLOTS*C cplx | raw-column stash (2nn+1)*C cplx ].
+// Consecutive fields that read the same spectral array (ux, uz, w all come from
+// the vorticity) load it from global memory once and re-read it from the
+// thread-private stash.
 template <int LOG2N, int C>
 __global__ void __launch_bounds__(C * FftCfg<LOG2N>::T, 1)
 k_xinv(const XInvArgs a) {
     typedef FftCfg<LOG2N> F;
     const int c = threadIdx.x % C, tau = threadIdx.x / C;
-    const int m = blockIdx.x * C + c;
-    const bool valid = m < a.nm;
+    const int mreal = blockIdx.x * C + c;
+    const bool valid = mreal < a.nm;
+    const int m = valid ? mreal : a.nm - 1;          // clamp: loads stay unpredicated
     XchgFull<C> xc;
     xc.buf = reinterpret_cast<cplx*>(MLV_SMEM_BASE());
     xc.c = c;
+    cplx* stash = xc.buf + (size_t)F::XSLOTS * C;
+    // row / mode of each of this thread's 16 points (same for every field)
     for (int f = 0; f < a.nf; ++f) {
         cplx v[16];
         const cplx* __restrict__ src = a.src[f];
-        const int op = a.op[f];
+        const bool reuse = f > 0 && a.src[f] == a.src[f - 1];
+        const bool keep = f + 1 < a.nf && a.src[f + 1] == a.src[f];
         MLV_UNROLL
         for (int j = 0; j < 16; ++j) {
             const int kk = tau + F::T * j;
             int r, n;
             v[j] = mk(0.0, 0.0);
-            if (valid && xrow_of(kk, F::N, a.nn, r, n))
-                v[j] = spectral_op(op, src[(size_t)r * a.spitch + m], n, m, a.k);
+            if (xrow_of(kk, F::N, a.nn, r, n))
+                v[j] = reuse ? stash[(size_t)r * C + c] : src[(size_t)r * a.spitch + m];
+        }
+        if (keep && !reuse) {
+            MLV_UNROLL
+            for (int j = 0; j < 16; ++j) {
+                const int kk = tau + F::T * j;
+                int r, n;
+                if (xrow_of(kk, F::N, a.nn, r, n)) stash[(size_t)r * C + c] = v[j];
+            }
+        }
+        const int op = a.op[f];
+        if (op != XOP_IDENT) {
+            MLV_UNROLL
+            for (int j = 0; j < 16; ++j) {
+                const int kk = tau + F::T * j;
+                int r, n;
+                if (xrow_of(kk, F::N, a.nn, r, n)) v[j] = spectral_op(op, v[j], n, m, a.k);
+            }
         }
         fft_line<LOG2N, true>(v, tau, a.tw, xc);
         if (valid) {
@@ -196,33 +221,32 @@ struct XFwdArgs {
 };
 
 // I (nx, ipitch) x nf -> spectral: value = scale * sum_f coef_f * sym_f * FFT_x(src_f),
-// rows truncated to |n| <= nn.  With nf > 1 partial sums are kept in a
-// thread-private shared-memory stash indexed by spectral row.
+// rows truncated to |n| <= nn.  The per-field results are accumulated in a
+// shared-memory tile indexed by spectral row (each (row, column) slot is owned
+// by one thread until the barrier), then a compact rolled loop runs the epilogue
+// (right-hand-side assembly + time integration) over the tile with C*16-byte
+// coalesced global accesses.
 template <int LOG2N, int C>
 __global__ void __launch_bounds__(C * FftCfg<LOG2N>::T, 1)
 k_xfwd(const XFwdArgs a) {
     typedef FftCfg<LOG2N> F;
     const int c = threadIdx.x % C, tau = threadIdx.x / C;
-    const int m = blockIdx.x * C + c;
-    const bool valid = m < a.nm;
+    const int mreal = blockIdx.x * C + c;
+    const bool valid = mreal < a.nm;
+    const int m = valid ? mreal : a.nm - 1;
     XchgFull<C> xc;
     xc.buf = reinterpret_cast<cplx*>(MLV_SMEM_BASE());
     xc.c = c;
-    cplx* stash = xc.buf + (size_t)F::XSLOTS * C;     // (2nn+1)*C entries, used when nf > 1
-    const double sz = valid ? a.symz[m] : 0.0;
+    cplx* tile = xc.buf + (size_t)F::XSLOTS * C;      // (2nn+1)*C entries
+    const double sz = a.symz[m];
     for (int f = 0; f < a.nf; ++f) {
         cplx v[16];
         const cplx* __restrict__ src = a.src[f];
         MLV_UNROLL
-        for (int j = 0; j < 16; ++j) {
-            v[j] = mk(0.0, 0.0);
-            if (valid) v[j] = src[(size_t)(tau + F::T * j) * a.ipitch + m];
-        }
+        for (int j = 0; j < 16; ++j) v[j] = src[(size_t)(tau + F::T * j) * a.ipitch + m];
         fft_line<LOG2N, false>(v, tau, a.tw, xc);
-        if (!valid) continue;
         const int sym = a.sym[f];
         const double cf = a.coef[f] * a.scale;
-        const bool last = (f + 1 == a.nf);
         MLV_UNROLL
         for (int j = 0; j < 16; ++j) {
             const int kk = tau + F::T * j;
@@ -235,38 +259,55 @@ k_xfwd(const XFwdArgs a) {
                 const double s = (sym == XSYM_FDX ? a.symx[kk] : sz) * cf;
                 t = mk(-s * v[j].y, s * v[j].x);          // * (i s)
             }
-            if (f > 0) t = cadd(stash[(size_t)r * C + c], t);
-            if (!last) {
-                stash[(size_t)r * C + c] = t;
-                continue;
-            }
-            const size_t idx = (size_t)r * a.spitch + m;
-            if (a.mode == 0) {
-                a.dst[idx] = t;
-            } else {
-                const cplx f0 = cadd(t, lin_terms_at(a.lin, idx, n, m, a.k));
-                a.integ.f0[idx] = f0;
-                integrate_point(a.integ, f0, idx, n, m, a.k);
-            }
+            cplx* slot = &tile[(size_t)r * C + c];
+            if (f > 0) t = cadd(*slot, t);
+            *slot = t;
+        }
+    }
+    __syncthreads();
+    // ---- epilogue over the (2nn+1) x C tile
+    const int rows = 2 * a.nn + 1;
+    const int m0 = blockIdx.x * C;
+    for (int e = threadIdx.x; e < rows * C; e += C * F::T) {
+        const int r = e / C, cc = e % C;
+        const int mm = m0 + cc;
+        if (mm >= a.nm) continue;
+        const cplx t = tile[e];
+        const size_t idx = (size_t)r * a.spitch + mm;
+        if (a.mode == 0) {
+            a.dst[idx] = t;
+        } else {
+            const int n = r <= a.nn ? r : r - rows;
+            const cplx f0 = cadd(t, lin_terms_at(a.lin, idx, n, mm, a.k));
+            a.integ.f0[idx] = f0;
+            integrate_point(a.integ, f0, idx, n, mm, a.k);
         }
     }
 }
 
 // ===================================================================== z passes
 // Packed-pair element idx of the Hermitian-extended spectrum of two real rows
-// whose one-sided spectra are rowA, rowB (F4: Im of the m=0 bin is dropped).
-MLV_DEV cplx zpair_load(const cplx* __restrict__ rowA, const cplx* __restrict__ rowB,
-                        int idx, int N, int nm) {
-    if (idx < nm) {
-        const cplx A = rowA[idx], B = rowB[idx];
-        if (idx == 0) return mk(A.x, B.x);
-        return mk(A.x - B.y, A.y + B.x);                 // A + iB
+// whose one-sided spectra are rowA, rowB (F4: Im of the m=0 bin is dropped):
+//   idx < nm        : A[idx] + i B[idx]            (idx = 0: Re A + i Re B)
+//   idx > N - nm    : conj(A[N-idx]) + i conj(B[N-idx])
+//   otherwise       : 0   (2/3-rule truncation)
+template <int LOG2N>
+MLV_DEV void zpair_load_line(cplx (&v)[16], const cplx* __restrict__ rowA,
+                             const cplx* __restrict__ rowB, int tau_, int nm) {
+    typedef FftCfg<LOG2N> F;
+    const int tau = opaque_int(tau_);
+    MLV_UNROLL
+    for (int j = 0; j < 16; ++j) {
+        const int idx = tau + F::T * j;
+        const bool lo = idx < nm, hi = idx > F::N - nm;
+        v[j] = mk(0.0, 0.0);
+        if (lo || hi) {
+            const int mm = lo ? idx : F::N - idx;
+            const cplx A = rowA[mm], B = rowB[mm];
+            v[j] = lo ? (idx == 0 ? mk(A.x, B.x) : mk(A.x - B.y, A.y + B.x))
+                      : mk(A.x + B.y, B.x - A.y);
+        }
     }
-    if (idx > N - nm) {
-        const cplx A = rowA[N - idx], B = rowB[N - idx];
-        return mk(A.x + B.y, B.x - A.y);                 // conj(A) + i conj(B)
-    }
-    return mk(0.0, 0.0);
 }
 
 // After a forward transform of z = a + ib every thread holds Zf[tau + T j].
@@ -303,16 +344,15 @@ __global__ void __launch_bounds__(LPC * FftCfg<LOG2N>::T, (LPC * FftCfg<LOG2N>::
 k_z_c2r(const ZArgs a) {
     typedef FftCfg<LOG2N> F;
     const int l = threadIdx.x / F::T, tau = threadIdx.x % F::T;
-    const int rp = blockIdx.x * LPC + l;
-    const bool valid = 2 * rp < a.nx;
+    const int rpreal = blockIdx.x * LPC + l;
+    const bool valid = 2 * rpreal < a.nx;
+    const int rp = valid ? rpreal : 0;               // clamp: loads stay unpredicated
     XchgSplit xc;
     xc.buf = reinterpret_cast<double*>(MLV_SMEM_BASE()) + (size_t)l * F::XSLOTS;
     const cplx* rowA = a.I + (size_t)(2 * rp) * a.ipitch;
     const cplx* rowB = rowA + a.ipitch;
     cplx v[16];
-    MLV_UNROLL
-    for (int j = 0; j < 16; ++j)
-        v[j] = valid ? zpair_load(rowA, rowB, tau + F::T * j, F::N, a.nm) : mk(0.0, 0.0);
+    zpair_load_line<LOG2N>(v, rowA, rowB, tau, a.nm);
     fft_line<LOG2N, true>(v, tau, a.tw, xc);
     if (valid) {
         double* pa = a.P + (size_t)(2 * rp) * F::N;
@@ -484,46 +524,51 @@ template <int LOG2N, int LPC>
 __global__ void __launch_bounds__(LPC * FftCfg<LOG2N>::T, (LPC * FftCfg<LOG2N>::T <= 256) ? 2 : 1)
 k_z_advect(const ZAdvArgs a) {
     typedef FftCfg<LOG2N> F;
+    constexpr int NT = LPC * F::T;
     const int l = threadIdx.x / F::T, tau = threadIdx.x % F::T;
-    const int rp = blockIdx.x * LPC + l;
-    const bool valid = 2 * rp < a.nx;
-    // shared memory: [ LPC * XSLOTS doubles exchange | LPC * N cplx thread-private stash ]
+    const int rpreal = blockIdx.x * LPC + l;
+    const bool valid = 2 * rpreal < a.nx;
+    const int rp = valid ? rpreal : 0;               // clamp: loads stay unpredicated
+    // shared memory: [ LPC*XSLOTS doubles exchange | LPC*N cplx thread-private stash | 4*NT doubles ]
     unsigned char* base = MLV_SMEM_BASE();
     XchgSplit xc;
     xc.buf = reinterpret_cast<double*>(base) + (size_t)l * F::XSLOTS;
     cplx* stash = reinterpret_cast<cplx*>(base + (size_t)LPC * F::XSLOTS * sizeof(double)) +
-                  (size_t)l * F::N;
-    cplx* pbuf = reinterpret_cast<cplx*>(xc.buf);
+                  (size_t)l * F::N + tau;
+    double* rbuf = reinterpret_cast<double*>(base + (size_t)LPC * F::XSLOTS * sizeof(double) +
+                                             (size_t)LPC * F::N * sizeof(cplx));
     const size_t rowoff = (size_t)(2 * rp) * a.ipitch;
 
-    double red[4] = {-INFINITY, -INFINITY, 0.0, 0.0};
     cplx v[16];
     {   // q -> physical, parked in the thread-private stash
         const cplx* rowA = a.Iq + rowoff;
-        MLV_UNROLL
-        for (int j = 0; j < 16; ++j)
-            v[j] = valid ? zpair_load(rowA, rowA + a.ipitch, tau + F::T * j, F::N, a.nm) : mk(0.0, 0.0);
+        zpair_load_line<LOG2N>(v, rowA, rowA + a.ipitch, tau, a.nm);
         fft_line<LOG2N, true>(v, tau, a.tw, xc);
         MLV_UNROLL
-        for (int j = 0; j < 16; ++j) stash[j * F::T + tau] = v[j];
+        for (int j = 0; j < 16; ++j) stash[j * F::T] = v[j];
     }
     for (int pass = 0; pass < 2; ++pass) {        // pass 0: A = ux q, pass 1: B = uz q
-        const cplx* src = (pass == 0 ? a.Iux : a.Iuz) + rowoff;
-        MLV_UNROLL
-        for (int j = 0; j < 16; ++j)
-            v[j] = valid ? zpair_load(src, src + a.ipitch, tau + F::T * j, F::N, a.nm) : mk(0.0, 0.0);
-        fft_line<LOG2N, true>(v, tau, a.tw, xc);
-        double mx = -INFINITY, ss = 0.0;
-        MLV_UNROLL
-        for (int j = 0; j < 16; ++j) {
-            mx = fmax(mx, fmax(v[j].x, v[j].y));
-            ss += v[j].x * v[j].x + v[j].y * v[j].y;
-            const cplx q = stash[j * F::T + tau];
-            v[j] = mk(v[j].x * q.x, v[j].y * q.y);
+        MLV_SCHED_FENCE();
+        {
+            const cplx* src = (pass == 0 ? a.Iux : a.Iuz) + rowoff;
+            zpair_load_line<LOG2N>(v, src, src + a.ipitch, tau, a.nm);
         }
-        red[pass] = mx;
-        red[2 + pass] = ss;
+        MLV_SCHED_FENCE();
+        fft_line<LOG2N, true>(v, tau, a.tw, xc);
+        {
+            double mx = -INFINITY, ss = 0.0;
+            MLV_UNROLL
+            for (int j = 0; j < 16; ++j) {
+                mx = fmax(mx, fmax(v[j].x, v[j].y));
+                ss += v[j].x * v[j].x + v[j].y * v[j].y;
+                const cplx q = stash[j * F::T];
+                v[j] = mk(v[j].x * q.x, v[j].y * q.y);
+            }
+            rbuf[pass * NT + threadIdx.x] = valid ? mx : -INFINITY;
+            rbuf[(2 + pass) * NT + threadIdx.x] = valid ? ss : 0.0;
+        }
         fft_line<LOG2N, false>(v, tau, a.tw, xc);
+        cplx* pbuf = reinterpret_cast<cplx*>(xc.buf);
         __syncthreads();
         zpair_publish<LOG2N>(v, tau, a.nm, pbuf);
         __syncthreads();
@@ -545,16 +590,10 @@ k_z_advect(const ZAdvArgs a) {
     }
     // ---- reductions: per-CTA partials (deterministic two-stage reduction)
     __syncthreads();
-    double* rbuf = reinterpret_cast<double*>(base);      // reuse exchange area: 4*blockDim doubles
-    const int nt = blockDim.x;
-    if (!valid) { red[0] = red[1] = -INFINITY; red[2] = red[3] = 0.0; }
-    MLV_UNROLL
-    for (int w = 0; w < 4; ++w) rbuf[w * nt + threadIdx.x] = red[w];
-    __syncthreads();
     if (threadIdx.x < 4) {
         const int w = threadIdx.x;
-        double r = rbuf[w * nt];
-        for (int i = 1; i < nt; ++i) r = (w < 2) ? fmax(r, rbuf[w * nt + i]) : r + rbuf[w * nt + i];
+        double r = rbuf[w * NT];
+        for (int i = 1; i < NT; ++i) r = (w < 2) ? fmax(r, rbuf[w * NT + i]) : r + rbuf[w * NT + i];
         a.red[(size_t)blockIdx.x * 4 + w] = r;
     }
 }
