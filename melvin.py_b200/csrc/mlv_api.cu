@@ -31,7 +31,7 @@ struct Plan {            // twiddle tables of one line length
 
 struct mlv_ctx {
     mlv_params p;
-    int nn, nm, spec_rows, spec_cols, ipitch;
+    int nn, nm, spec_rows, spec_cols, ipitch, ct;
     int log2nx, log2nz;
     double dx, dz;
     mlv::SpecConsts k;
@@ -338,7 +338,11 @@ int mlv_create(const mlv_params* p, mlv_ctx** out) {
     c->nm = p->fdm_z ? -1 : (p->nz - 1) / 3;
     c->spec_rows = p->fdm_z ? c->nn : 2 * c->nn + 1;
     c->spec_cols = p->fdm_z ? p->nz : c->nm;
-    c->ipitch = p->fdm_z ? 0 : ((c->nm + 1) & ~1);  // even pitch: 32-byte aligned column pairs
+    c->ct = xcols(lx);                               // columns per x-pass CTA = tile width
+    {   // pitch: multiple of the tile width (and even: 32-byte aligned column pairs)
+        const int q = c->ct > 2 ? c->ct : 2;
+        c->ipitch = p->fdm_z ? 0 : ((c->nm + q - 1) / q) * q;
+    }
     c->dx = p->lx / p->nx;
     c->dz = p->lz / p->nz;
     c->k.kx0 = p->kx0; c->k.kz0 = p->kz0; c->k.d2x = p->d2x; c->k.d2z = p->d2z;
@@ -441,7 +445,7 @@ int mlv_z_inverse(mlv_ctx* c, const void* isrc, double* phys) {
     if (!c || !isrc || !phys) { set_error("mlv_z_inverse: null argument"); return MLV_ERR_INVALID; }
     if (int rc = need_2d(c, "mlv_z_inverse")) return rc;
     ZArgs a{};
-    a.nx = c->p.nx; a.nm = c->nm; a.ipitch = c->ipitch;
+    a.nx = c->p.nx; a.nm = c->nm; a.ipitch = c->ipitch; a.ct = c->ct;
     a.I = (const cplx*)isrc; a.P = phys; a.tw = c->planz.tw;
 #define MLV_GO(L) return launch_zc2r<L>(c, a)
     MLV_SWITCH_LOG2(c->log2nz, MLV_GO)
@@ -453,7 +457,7 @@ int mlv_z_forward(mlv_ctx* c, const double* phys, void* idst) {
     if (!c || !idst || !phys) { set_error("mlv_z_forward: null argument"); return MLV_ERR_INVALID; }
     if (int rc = need_2d(c, "mlv_z_forward")) return rc;
     ZArgs a{};
-    a.nx = c->p.nx; a.nm = c->nm; a.ipitch = c->ipitch;
+    a.nx = c->p.nx; a.nm = c->nm; a.ipitch = c->ipitch; a.ct = c->ct;
     a.Pin = phys; a.Iout = (cplx*)idst; a.tw = c->planz.tw;
 #define MLV_GO(L) return launch_zr2c<L>(c, a)
     MLV_SWITCH_LOG2(c->log2nz, MLV_GO)
@@ -542,7 +546,7 @@ int mlv_advect_z(mlv_ctx* c, const void* iux, const void* iuz, const void* iq, v
     if (!c || !iux || !iuz || !iq || !ia || !ib) { set_error("mlv_advect_z: null argument"); return MLV_ERR_INVALID; }
     if (int rc = need_2d(c, "mlv_advect_z")) return rc;
     ZAdvArgs a{};
-    a.nx = c->p.nx; a.nm = c->nm; a.ipitch = c->ipitch;
+    a.nx = c->p.nx; a.nm = c->nm; a.ipitch = c->ipitch; a.ct = c->ct;
     a.Iux = (const cplx*)iux; a.Iuz = (const cplx*)iuz; a.Iq = (const cplx*)iq;
     a.IA = (cplx*)ia; a.IB = (cplx*)ib; a.tw = c->planz.tw;
     unsigned grid = 0;

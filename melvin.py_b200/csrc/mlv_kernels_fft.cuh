@@ -4,7 +4,14 @@
 //   S  spectral   (2nn+1, nm) complex128, rows n = 0..nn,-nn..-1   [API layout,
 //                  reference melvin/ArrayFactory.py:8-45]
 //   P  physical   (nx, nz) float64                                  [API layout]
-//   I  x-transformed intermediate (nx, ipitch>=nm) complex128       [private]
+//   I  x-transformed intermediate, private.  Two layouts, chosen so that every
+//      *read* is contiguous and only *writes* scatter (the L2 merges scattered
+//      32-byte writes; scattered reads would cost a DRAM row activation each):
+//        row layout   (nx, ipitch)          written by the inverse x pass (column
+//                      tiles), read row-wise by the z stage;
+//        tile layout  [m/CT][nx][CT]        written by the forward z stage (CT = column
+//                      count of an x-pass CTA), read as one contiguous block per CTA by
+//                      the forward x pass.
 //   FDM-z mode:  S_f (nn, nz) complex128 <-> P, one 1-D transform along x.
 //
 // A 2-D transform is an x pass (complex, strided columns, C adjacent columns per
@@ -71,6 +78,11 @@ MLV_DEV bool xrow_of(int k, int N, int nn, int& r, int& n) {
     if (k <= nn) { r = k; n = k; return true; }
     if (k >= N - nn) { n = k - N; r = n + 2 * nn + 1; return true; }
     return false;
+}
+
+// element (x, m) of a forward intermediate in tile layout [m/CT][nx][CT]
+MLV_DEV size_t tile_off(int x, int m, int nx, int ct) {
+    return ((size_t)(m / ct) * nx + x) * ct + (m % ct);
 }
 
 // ------------------------------------------------------ time integration
@@ -220,7 +232,7 @@ struct XFwdArgs {
     FftTw tw;
 };
 
-// I (nx, ipitch) x nf -> spectral: value = scale * sum_f coef_f * sym_f * FFT_x(src_f),
+// I (tile layout) x nf -> spectral: value = scale * sum_f coef_f * sym_f * FFT_x(src_f),
 // rows truncated to |n| <= nn.  The per-field results are accumulated in a
 // shared-memory tile indexed by spectral row (each (row, column) slot is owned
 // by one thread until the barrier), then a compact rolled loop runs the epilogue
@@ -243,7 +255,8 @@ k_xfwd(const XFwdArgs a) {
         cplx v[16];
         const cplx* __restrict__ src = a.src[f];
         MLV_UNROLL
-        for (int j = 0; j < 16; ++j) v[j] = src[(size_t)(tau + F::T * j) * a.ipitch + m];
+        for (int j = 0; j < 16; ++j)                       // tile layout: one contiguous block
+            v[j] = src[((size_t)blockIdx.x * F::N + (tau + F::T * j)) * C + c];
         fft_line<LOG2N, false>(v, tau, a.tw, xc);
         const int sym = a.sym[f];
         const double cf = a.coef[f] * a.scale;
@@ -330,7 +343,7 @@ MLV_DEV void zpair_unpack(cplx Zk, cplx P, cplx& A, cplx& B) {
 }
 
 struct ZArgs {
-    int nx, nm, ipitch;
+    int nx, nm, ipitch, ct;
     const cplx* I;     // c2r input / unused
     cplx* Iout;        // r2c output
     const double* Pin; // r2c input
@@ -365,7 +378,7 @@ k_z_c2r(const ZArgs a) {
     }
 }
 
-// P (nx, nz) -> I (nx, ipitch): forward z pass (unnormalised), truncated to m < nm
+// P (nx, nz) -> I (tile layout): forward z pass (unnormalised), truncated to m < nm
 template <int LOG2N, int LPC>
 __global__ void __launch_bounds__(LPC * FftCfg<LOG2N>::T, (LPC * FftCfg<LOG2N>::T <= 256) ? 2 : 1)
 k_z_r2c(const ZArgs a) {
@@ -389,8 +402,6 @@ k_z_r2c(const ZArgs a) {
     zpair_publish<LOG2N>(v, tau, a.nm, pbuf);
     __syncthreads();
     if (valid) {
-        cplx* oa = a.Iout + (size_t)(2 * rp) * a.ipitch;
-        cplx* ob = oa + a.ipitch;
         MLV_UNROLL
         for (int j = 0; j < 16; ++j) {
             const int kk = tau + F::T * j;
@@ -398,8 +409,9 @@ k_z_r2c(const ZArgs a) {
                 const cplx P = (kk == 0) ? v[j] : pbuf[kk];
                 cplx A, B;
                 zpair_unpack(v[j], P, A, B);
-                oa[kk] = A;
-                ob[kk] = B;
+                cplx* o = a.Iout + tile_off(2 * rp, kk, a.nx, a.ct);
+                o[0] = A;
+                o[a.ct] = B;                                   // row 2rp+1
             }
         }
     }
@@ -510,11 +522,11 @@ k_x1d_r2c(const X1dArgs a) {
 // Also produces the reductions the tickers need (Integrator.py:35-44 signed max
 // of ux, uz; utility.py:42-59 sum ux^2, uz^2) as per-CTA partials.
 struct ZAdvArgs {
-    int nx, nm, ipitch;
+    int nx, nm, ipitch, ct;
     const cplx* Iux;
     const cplx* Iuz;
     const cplx* Iq;
-    cplx* IA;                      // out: z-spectrum of ux q   (nx, ipitch)
+    cplx* IA;                      // out: z-spectrum of ux q   (tile layout)
     cplx* IB;                      // out: z-spectrum of uz q
     double* red;                   // [gridDim.x][4] partials: max ux, max uz, sum ux^2, sum uz^2
     FftTw tw;
@@ -573,8 +585,7 @@ k_z_advect(const ZAdvArgs a) {
         zpair_publish<LOG2N>(v, tau, a.nm, pbuf);
         __syncthreads();
         if (valid) {
-            cplx* oa = (pass == 0 ? a.IA : a.IB) + rowoff;
-            cplx* ob = oa + a.ipitch;
+            cplx* out = (pass == 0 ? a.IA : a.IB);
             MLV_UNROLL
             for (int j = 0; j < 16; ++j) {
                 const int kk = tau + F::T * j;
@@ -582,8 +593,9 @@ k_z_advect(const ZAdvArgs a) {
                     const cplx P = (kk == 0) ? v[j] : pbuf[kk];
                     cplx A, B;
                     zpair_unpack(v[j], P, A, B);
-                    oa[kk] = A;
-                    ob[kk] = B;
+                    cplx* o = out + tile_off(2 * rp, kk, a.nx, a.ct);
+                    o[0] = A;
+                    o[a.ct] = B;                               // row 2rp+1
                 }
             }
         }
