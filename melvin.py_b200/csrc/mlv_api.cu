@@ -222,6 +222,7 @@ static int launch_xinv(mlv_ctx* c, XInvArgs& a) {
     auto kfn = k_xinv<L, C>;
     const size_t smem = ((size_t)F::XSLOTS + (size_t)(2 * a.nn + 1)) * C * sizeof(cplx);
     const unsigned grid = (unsigned)((a.nm + C - 1) / C);
+    a.wave = 148 * (smem > 113 * 1024 ? 1 : 2);
     MLV_LAUNCH(kfn, grid, (unsigned)(C * F::T), smem, c->stream, a);
     return 0;
 }
@@ -233,6 +234,7 @@ static int launch_xfwd(mlv_ctx* c, XFwdArgs& a) {
     auto kfn = k_xfwd<L, C>;
     const size_t smem = ((size_t)F::XSLOTS + (size_t)(2 * a.nn + 1)) * C * sizeof(cplx);
     const unsigned grid = (unsigned)((a.nm + C - 1) / C);
+    a.wave = 148 * (smem > 113 * 1024 ? 1 : 2);
     MLV_LAUNCH(kfn, grid, (unsigned)(C * F::T), smem, c->stream, a);
     return 0;
 }
@@ -271,6 +273,8 @@ static int launch_zadv(mlv_ctx* c, ZAdvArgs& a, unsigned& grid_out) {
     int rc = ensure_red(c, (size_t)grid * 4);
     if (rc) return rc;
     a.red = c->red;
+    a.wave = 148 * (smem > 113 * 1024 ? 1 : 2);
+
     MLV_LAUNCH(kfn, grid, (unsigned)(LPC * F::T), smem, c->stream, a);
     return 0;
 }
@@ -387,6 +391,7 @@ int mlv_create(const mlv_params* p, mlv_ctx** out) {
         if (!rc) rc = rt_h2d(c->tri_inv, inv.data(), tot * sizeof(double), c->stream);
     }
     if (!rc) rc = ensure_red(c, 148 * 16 * 4);
+
     if (rc) { mlv_destroy(c); return rc; }
     *out = c;
     return MLV_OK;

@@ -89,6 +89,24 @@ MLV_HD cplx cmuli(cplx a) { return mk(-a.y, a.x); }
 // multiply by -i
 MLV_HD cplx cmulni(cplx a) { return mk(a.y, -a.x); }
 
+// L2 prefetch hints (no registers, no shared memory): the kernels keep only two
+// transform lines per SM in flight, so loads that would otherwise expose a DRAM round
+// trip are announced one phase ahead and later hit the L2.
+MLV_DEV void l2_prefetch_bulk(const void* p, unsigned bytes) {   // 16-byte aligned, multiple of 16
+#ifndef MLV_EMU
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+#else
+    (void)p; (void)bytes;
+#endif
+}
+MLV_DEV void l2_prefetch_line(const void* p) {
+#ifndef MLV_EMU
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+
 // Reciprocal to ~1 ulp without the branchy IEEE division sequence: 20-bit hardware
 // seed + two Newton steps (operands here are O(1)..O(1e9), never denormal or zero).
 MLV_DEV double fast_rcp(double x) {

@@ -129,6 +129,25 @@ MLV_DEV void integrate_point(const IntegArgs& g, cplx f0, size_t idx, int n, int
     g.q_out[idx] = mk((a * q.x + inc.x) * rb, (a * q.y + inc.y) * rb);
 }
 
+// same update with the state and history values already in registers
+MLV_DEV cplx integrate_value(const IntegArgs& g, cplx f0, cplx q, cplx f1, cplx f2, cplx f3,
+                             size_t idx, int n, int m, const SpecConsts& k) {
+    cplx inc;
+    if (g.ab_order == 2) {
+        const double h = g.dt / 2;
+        inc = mk(h * (3 * f0.x - f1.x), h * (3 * f0.y - f1.y));
+    } else {
+        const double h = g.dt / 24;
+        inc = mk(h * (55 * f0.x - 59 * f1.x + 37 * f2.x - 9 * f3.x),
+                 h * (55 * f0.y - 59 * f1.y + 37 * f2.y - 9 * f3.y));
+    }
+    if (g.scheme == 2) return cadd(q, inc);
+    const double L = (g.scheme == 0) ? g.lcoef * lap_symbol(n, m, k) : g.larr[idx];
+    const double a = 1 + ((1 - g.alpha) * g.dt) * L;
+    const double rb = fast_rcp(1 - (g.alpha * g.dt) * L);
+    return mk((a * q.x + inc.x) * rb, (a * q.y + inc.y) * rb);
+}
+
 // Extra linear right-hand-side terms  sum_i coef_i * op_i(src_i)
 #define MLV_MAXLIN 4
 struct LinTerms {
@@ -151,6 +170,7 @@ MLV_DEV cplx lin_terms_at(const LinTerms& lt, size_t idx, int n, int m, const Sp
 #define MLV_XMAXF 4
 struct XInvArgs {
     int nn, nm, spitch, ipitch, nf;
+    int wave;                    // CTAs resident at once (prefetch distance)
     const cplx* src[MLV_XMAXF];
     int op[MLV_XMAXF];
     cplx* dst[MLV_XMAXF];
@@ -175,12 +195,24 @@ k_xinv(const XInvArgs a) {
     xc.buf = reinterpret_cast<cplx*>(MLV_SMEM_BASE());
     xc.c = c;
     cplx* stash = xc.buf + (size_t)F::XSLOTS * C;
-    // row / mode of each of this thread's 16 points (same for every field)
+    // announce the columns of the CTA that follows this one on the SM
+    if ((int)(blockIdx.x + a.wave) < (int)gridDim.x) {
+        const int rows = 2 * a.nn + 1;
+        for (int r = threadIdx.x; r < rows; r += C * F::T)
+            l2_prefetch_line(a.src[0] + (size_t)r * a.spitch + (size_t)(blockIdx.x + a.wave) * C);
+    }
+    bool stash_psi = false;     // stash holds psi = -src/lap instead of the raw column
     for (int f = 0; f < a.nf; ++f) {
         cplx v[16];
         const cplx* __restrict__ src = a.src[f];
-        const bool reuse = f > 0 && a.src[f] == a.src[f - 1];
+        const int op = a.op[f];
+        const bool wants_psi = (op == XOP_PSI || op == XOP_UX || op == XOP_UZ);
+        const bool same_prev = f > 0 && a.src[f] == a.src[f - 1];
+        const bool reuse = same_prev && (!stash_psi || wants_psi);
+        if (!reuse) stash_psi = false;
         const bool keep = f + 1 < a.nf && a.src[f + 1] == a.src[f];
+        const int opn = keep ? a.op[f + 1] : -1;
+        const bool next_wants_psi = (opn == XOP_PSI || opn == XOP_UX || opn == XOP_UZ);
         MLV_UNROLL
         for (int j = 0; j < 16; ++j) {
             const int kk = tau + F::T * j;
@@ -189,7 +221,7 @@ k_xinv(const XInvArgs a) {
             if (xrow_of(kk, F::N, a.nn, r, n))
                 v[j] = reuse ? stash[(size_t)r * C + c] : src[(size_t)r * a.spitch + m];
         }
-        if (keep && !reuse) {
+        if (keep && !reuse && !(wants_psi && next_wants_psi)) {      // park the raw column
             MLV_UNROLL
             for (int j = 0; j < 16; ++j) {
                 const int kk = tau + F::T * j;
@@ -197,8 +229,26 @@ k_xinv(const XInvArgs a) {
                 if (xrow_of(kk, F::N, a.nn, r, n)) stash[(size_t)r * C + c] = v[j];
             }
         }
-        const int op = a.op[f];
-        if (op != XOP_IDENT) {
+        if (wants_psi) {
+            const bool have_psi = reuse && stash_psi;
+            const bool park_psi = keep && next_wants_psi && !have_psi;
+            MLV_UNROLL
+            for (int j = 0; j < 16; ++j) {
+                const int kk = tau + F::T * j;
+                int r, n;
+                if (!xrow_of(kk, F::N, a.nn, r, n)) continue;
+                cplx psi = v[j];
+                if (!have_psi) {
+                    psi = spectral_op(XOP_PSI, v[j], n, m, a.k);
+                    if (park_psi) stash[(size_t)r * C + c] = psi;
+                }
+                // ux = -(i kz m) psi, uz = (i kx n) psi   (utility.py:71,78)
+                if (op == XOP_UX) { const double b = a.k.kz0 * m; v[j] = mk(b * psi.y, -b * psi.x); }
+                else if (op == XOP_UZ) { const double b = a.k.kx0 * n; v[j] = mk(-b * psi.y, b * psi.x); }
+                else v[j] = psi;
+            }
+            if (park_psi) stash_psi = true;
+        } else if (op != XOP_IDENT) {
             MLV_UNROLL
             for (int j = 0; j < 16; ++j) {
                 const int kk = tau + F::T * j;
@@ -224,6 +274,7 @@ struct XFwdArgs {
     const double* symx;          // [N]  imaginary part of the x stencil symbol per FFT index
     const double* symz;          // [nm] imaginary part of the z stencil symbol
     double scale;                // 1/(nx nz)
+    int wave;                    // CTAs resident at once (prefetch distance)
     int mode;                    // 0: dst = value; 1: f0 = value + lin terms, then integrate
     cplx* dst;                   // mode 0: spectral (2nn+1, nm)
     LinTerms lin;                // mode 1
@@ -251,6 +302,30 @@ k_xfwd(const XFwdArgs a) {
     xc.c = c;
     cplx* tile = xc.buf + (size_t)F::XSLOTS * C;      // (2nn+1)*C entries
     const double sz = a.symz[m];
+    {   // L2 prefetch: the other fields' blocks, the next CTA's first block, and the
+        // state / history columns the epilogue will read
+        constexpr unsigned CHUNK = 16384;
+        constexpr unsigned BLOCK = (unsigned)F::N * C * (unsigned)sizeof(cplx);
+        constexpr int NCH = (int)(BLOCK / CHUNK) > 0 ? (int)(BLOCK / CHUNK) : 1;
+        const int t = threadIdx.x;
+        if (t < NCH * a.nf) {
+            const int f = t / NCH, ch = t % NCH;
+            const unsigned bytes = BLOCK < CHUNK ? BLOCK : CHUNK;
+            if (f > 0) {
+                l2_prefetch_bulk(reinterpret_cast<const char*>(a.src[f] + (size_t)blockIdx.x * F::N * C) + (size_t)ch * CHUNK, bytes);
+            } else if ((int)(blockIdx.x + a.wave) < (int)gridDim.x) {
+                l2_prefetch_bulk(reinterpret_cast<const char*>(a.src[0] + (size_t)(blockIdx.x + a.wave) * F::N * C) + (size_t)ch * CHUNK, bytes);
+            }
+        }
+        if (a.mode == 1) {
+            const int rows = 2 * a.nn + 1;
+            for (int r = t; r < rows; r += C * F::T) {
+                const size_t idx = (size_t)r * a.spitch + blockIdx.x * C;
+                l2_prefetch_line(a.integ.q_in + idx);
+                l2_prefetch_line(a.integ.fm1 + idx);
+            }
+        }
+    }
     for (int f = 0; f < a.nf; ++f) {
         cplx v[16];
         const cplx* __restrict__ src = a.src[f];
@@ -278,22 +353,46 @@ k_xfwd(const XFwdArgs a) {
         }
     }
     __syncthreads();
-    // ---- epilogue over the (2nn+1) x C tile
+    // ---- epilogue over the (2nn+1) x C tile: 4 elements per thread per trip, all global
+    //      loads of a trip issued before the arithmetic (memory-level parallelism)
     const int rows = 2 * a.nn + 1;
     const int m0 = blockIdx.x * C;
-    for (int e = threadIdx.x; e < rows * C; e += C * F::T) {
-        const int r = e / C, cc = e % C;
-        const int mm = m0 + cc;
-        if (mm >= a.nm) continue;
-        const cplx t = tile[e];
-        const size_t idx = (size_t)r * a.spitch + mm;
-        if (a.mode == 0) {
-            a.dst[idx] = t;
-        } else {
+    constexpr int NT = C * F::T;
+    constexpr int UN = 4;
+    for (int e0 = threadIdx.x; e0 < rows * C; e0 += UN * NT) {
+        cplx t[UN], q[UN], f1[UN], f2[UN], f3[UN];
+        size_t idx[UN];
+        bool ok[UN];
+        MLV_UNROLL
+        for (int u = 0; u < UN; ++u) {
+            const int e = e0 + u * NT;
+            const int r = e / C, mm = m0 + e % C;
+            ok[u] = e < rows * C && mm < a.nm;
+            idx[u] = ok[u] ? (size_t)r * a.spitch + mm : 0;
+        }
+        if (a.mode == 1) {
+            MLV_UNROLL
+            for (int u = 0; u < UN; ++u) {
+                q[u] = a.integ.q_in[idx[u]];
+                f1[u] = a.integ.fm1[idx[u]];
+                if (a.integ.ab_order == 4) { f2[u] = a.integ.fm2[idx[u]]; f3[u] = a.integ.fm3[idx[u]]; }
+            }
+        }
+        MLV_UNROLL
+        for (int u = 0; u < UN; ++u) t[u] = ok[u] ? tile[e0 + u * NT] : mk(0.0, 0.0);
+        MLV_UNROLL
+        for (int u = 0; u < UN; ++u) {
+            if (!ok[u]) continue;
+            if (a.mode == 0) {
+                a.dst[idx[u]] = t[u];
+                continue;
+            }
+            const int e = e0 + u * NT;
+            const int r = e / C, mm = m0 + e % C;
             const int n = r <= a.nn ? r : r - rows;
-            const cplx f0 = cadd(t, lin_terms_at(a.lin, idx, n, mm, a.k));
-            a.integ.f0[idx] = f0;
-            integrate_point(a.integ, f0, idx, n, mm, a.k);
+            const cplx f0 = cadd(t[u], lin_terms_at(a.lin, idx[u], n, mm, a.k));
+            a.integ.f0[idx[u]] = f0;
+            a.integ.q_out[idx[u]] = integrate_value(a.integ, f0, q[u], f1[u], f2[u], f3[u], idx[u], n, mm, a.k);
         }
     }
 }
@@ -523,6 +622,7 @@ k_x1d_r2c(const X1dArgs a) {
 // of ux, uz; utility.py:42-59 sum ux^2, uz^2) as per-CTA partials.
 struct ZAdvArgs {
     int nx, nm, ipitch, ct;
+    int wave;                      // CTAs resident at once (prefetch distance)
     const cplx* Iux;
     const cplx* Iuz;
     const cplx* Iq;
@@ -550,6 +650,19 @@ k_z_advect(const ZAdvArgs a) {
     double* rbuf = reinterpret_cast<double*>(base + (size_t)LPC * F::XSLOTS * sizeof(double) +
                                              (size_t)LPC * F::N * sizeof(cplx));
     const size_t rowoff = (size_t)(2 * rp) * a.ipitch;
+
+    // announce the rows of the two velocity components (needed one and two transforms
+    // from now) and the scalar rows of the CTA that will follow this one on the SM
+    if (tau < 6) {
+        const unsigned rowbytes = (unsigned)a.nm * (unsigned)sizeof(cplx);
+        if (tau < 4) {
+            l2_prefetch_bulk((tau < 2 ? a.Iux : a.Iuz) + rowoff + (size_t)(tau & 1) * a.ipitch, rowbytes);
+        } else {
+            const int rpn = rp + a.wave * LPC;
+            if (2 * rpn < a.nx)
+                l2_prefetch_bulk(a.Iq + (size_t)(2 * rpn + (tau & 1)) * a.ipitch, rowbytes);
+        }
+    }
 
     cplx v[16];
     {   // q -> physical, parked in the thread-private stash
@@ -602,11 +715,23 @@ k_z_advect(const ZAdvArgs a) {
     }
     // ---- reductions: per-CTA partials (deterministic two-stage reduction)
     __syncthreads();
-    if (threadIdx.x < 4) {
-        const int w = threadIdx.x;
-        double r = rbuf[w * NT];
-        for (int i = 1; i < NT; ++i) r = (w < 2) ? fmax(r, rbuf[w * NT + i]) : r + rbuf[w * NT + i];
-        a.red[(size_t)blockIdx.x * 4 + w] = r;
+    // tree over the 4 x NT table: thread t reduces column block of quantity w = t / (NT/4)
+    {
+        constexpr int G = NT / 4 > 0 ? NT / 4 : 1;          // threads per quantity
+        const int w = threadIdx.x / G, g = threadIdx.x % G;
+        if (w < 4) {
+            double r = rbuf[w * NT + g];
+            for (int i = g + G; i < NT; i += G) r = (w < 2) ? fmax(r, rbuf[w * NT + i]) : r + rbuf[w * NT + i];
+            rbuf[w * NT + g] = r;
+        }
+        for (int s2 = G / 2; s2 > 0; s2 >>= 1) {
+            __syncthreads();
+            if (w < 4 && g < s2) {
+                const double x = rbuf[w * NT + g], y = rbuf[w * NT + g + s2];
+                rbuf[w * NT + g] = (w < 2) ? fmax(x, y) : x + y;
+            }
+        }
+        if (w < 4 && g == 0) a.red[(size_t)blockIdx.x * 4 + w] = rbuf[w * NT];
     }
 }
 

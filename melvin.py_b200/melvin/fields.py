@@ -303,7 +303,9 @@ class Variable:
         if not fused:
             return self._vec_dot_nabla_eager(ux, uz, out, convert_to_physical)
         ctx = self._ctx
-        _run_x_inverse(ctx, [v for v in (uxo, uzo, self) if v._i_state == _I_PENDING])
+        # scalar first: when it is the vorticity itself the kernel reads the column once,
+        # then turns its copy into psi for the two velocity components
+        _run_x_inverse(ctx, [v for v in (self, uxo, uzo) if v._i_state == _I_PENDING])
         ia, ib = ctx.take_i(), ctx.take_i()
         red4 = _backend.empty((4,), np.float64)
         ctx.call("mlv_advect_z", ctypes.c_void_p(uxo._i.data_ptr()), ctypes.c_void_p(uzo._i.data_ptr()),
