@@ -370,6 +370,109 @@ def gpu_arm(args, rank, world):
         dist.destroy_process_group()
 
 
+def sharded_arm(args, rank, world):
+    """N > 1: the same Kelvin-Helmholtz workload, slab-decomposed over the GPUs of the
+    box (kz-slabs / x-slabs, NCCL all-to-all between the passes; melvin/sharded.py)."""
+    import torch
+    import torch.distributed as dist
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import __graft_entry__ as ge
+    if ge._stale() and rank == 0:
+        ge.build()
+    dist.barrier()
+    from melvin import _backend
+    from melvin.sharded import ShardedScalarStepper
+    from oracle import melvin_oracle as mo
+
+    nx, nz = args.nx, args.nz
+    pd = kh_params(nx, nz)
+    st = ShardedScalarStepper(nx, nz, pd["lx"], pd["lz"], 1.0 / RE, pd["initial_dt"])
+    g = mo.Grid(nx, nz, pd["lx"], pd["lz"])
+    # initial condition: transformed once on a full-size context, then only this rank's
+    # column slab is kept (set-up, outside every timed region)
+    full_ctx = _backend.Context(nx, nz, pd["lx"], pd["lz"], False, 2)
+    import ctypes
+    phys = _backend.from_host(mo.ic_kelvin_helmholtz(g))
+    spec = _backend.empty(full_ctx.spec_shape, np.complex128)
+    full_ctx.call("mlv_to_spectral", ctypes.c_void_p(phys.data_ptr()),
+                  ctypes.c_void_p(full_ctx.scratch_i().data_ptr()), ctypes.c_void_p(spec.data_ptr()))
+    st.load_spectral(_backend.to_host(spec))
+    del phys, spec, full_ctx
+    torch.cuda.empty_cache()
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        for _ in range(max(args.warmup, 3)):
+            st.step()
+        barrier()
+        n_before = _backend.launches()
+        t_begin = clk.mark()
+        e0.record()
+        for _ in range(args.steps):
+            st.step()
+        e1.record()
+        barrier()
+        t_end = clk.mark()
+        launches = _backend.launches() - n_before
+    t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = nx * nz * args.steps / (ms * 1e-3)          # strong scaling: one field for the whole job
+
+    # end to end with host buffers: every step uploads this rank's slab and reads it back
+    host = torch.from_numpy(_backend.to_host(st.w[st.cur])).pin_memory()
+    e2e_steps = max(3, min(args.steps, 20))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        st.w[st.cur].copy_(host, non_blocking=False)
+        st.step()
+        host.copy_(st.w[st.cur], non_blocking=False)
+    barrier()
+    tt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    slab_bytes = st.rows * st.nml * 16
+    bm = byte_model(nx, nz)
+    peak, peak_src = peaks()
+    if rank == 0:
+        ms_per_step = ms / args.steps
+        xbytes = st.bytes_exchanged_per_step / world        # sent per rank and step
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": f"Kelvin-Helmholtz {nx}x{nz} fully spectral, AB2 + semi-implicit diffusion "
+                            "(BASELINE configs[1]), slab-decomposed",
+                "grid": [nx, nz], "parallelism": f"kz-slabs / x-slabs over {world} GPUs, 2 NCCL "
+                "all-to-all per step (3 + 2 fields)", "cfl_cadence": st.cfl_cadence,
+                "tracker_cadence": st.tracker_cadence,
+                "l2": "working set per rank and step larger than the 126 MB L2; no flush",
+            },
+            "clocks": clk.summary(t_begin, t_end),
+            "roofline": {
+                "bound": "hbm", "kernel": "whole step (per GPU)", "unit": "GB/s", "peak": peak,
+                "achieved": bm["step"] / world / (ms_per_step * 1e-3) / 1e9,
+                "frac": bm["step"] / world / (ms_per_step * 1e-3) / 1e9 / peak, "traffic": None,
+                "peak_source": peak_src,
+                "nvlink": {"sent_bytes_per_gpu_per_step": xbytes,
+                           "ms_at_770GBps": xbytes / 770e9 * 1e3},
+            },
+            "cpu_baseline": None,
+            "e2e": {"value": nx * nz * e2e_steps / float(tt.item()), "unit": UNIT,
+                    "h2d_bytes_per_step": slab_bytes, "d2h_bytes_per_step": slab_bytes, "steps": e2e_steps},
+            "gpu_launches": launches,
+        }
+        print(json.dumps(line), flush=True)
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -386,7 +489,10 @@ def main():
         reference_arm(args, rank)
     else:
         with contextlib.redirect_stdout(sys.stderr) if rank != 0 else contextlib.nullcontext():
-            gpu_arm(args, rank, world)
+            if world > 1:
+                sharded_arm(args, rank, world)
+            else:
+                gpu_arm(args, rank, world)
 
 
 if __name__ == "__main__":

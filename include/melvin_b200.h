@@ -93,8 +93,8 @@ typedef struct mlv_info {
     int32_t nn, nm;                 /* truncation (nm = -1 in FDM-z mode) */
     int32_t spec_rows, spec_cols;   /* spectral_shape */
     int32_t ipitch;                 /* row pitch (complex elements) of I buffers */
-    int32_t reserved;
-    int64_t ibytes;                 /* bytes of one I buffer */
+    int32_t nm_local;               /* retained columns owned by this rank (= nm when unsharded) */
+    int64_t ibytes;                 /* bytes of one field of an I / exchange buffer */
 } mlv_info;
 
 typedef struct mlv_view {           /* 2-D strided view, strides in elements */
@@ -145,6 +145,16 @@ int mlv_create(const mlv_params* p, mlv_ctx** ctx);
 int mlv_destroy(mlv_ctx* ctx);
 int mlv_set_stream(mlv_ctx* ctx, void* cuda_stream);
 int mlv_get_info(const mlv_ctx* ctx, mlv_info* out);
+/* Slab decomposition over `nranks` processes (one per GPU; fully spectral mode).  The
+ * reference is single-device, so this has no counterpart there.  Afterwards
+ * every call works on local slabs: spectral arrays are (2nn+1, nml) column slabs
+ * (kz-slabs), the z stage sees nx/nranks rows (x-slabs).  `mlv_x_inverse` writes and
+ * `mlv_advect_z` reads the inverse exchange buffer [peer][field][rows][nml];
+ * `mlv_advect_z` writes and `mlv_x_forward` reads the forward exchange buffer
+ * [peer][field][tiles][rows][CT]; the caller moves the peer blocks with one all-to-all
+ * per direction (NCCL) between those calls.  inv_fields / fwd_fields = fields batched
+ * per exchange (block strides).  mlv_get_info then reports the local shapes. */
+int mlv_set_sharding(mlv_ctx* ctx, int rank, int nranks, int inv_fields, int fwd_fields);
 const char* mlv_last_error(void);
 int mlv_abi_version(void);
 long long mlv_launch_count(void);   /* kernels launched by the library so far (process-wide) */

@@ -42,6 +42,13 @@ struct mlv_ctx {
     double* tri_inv = nullptr;
     double* red = nullptr;      // reduction partials
     size_t red_cap = 0;
+    // slab decomposition (mlv_set_sharding); defaults describe the unsharded case
+    int rank = 0, nranks = 1;
+    int nml = 0;                // local column pitch of spectral arrays / inverse buffers
+    int nm_loc = 0;             // valid local columns
+    int nxl = 0;                // local rows
+    int inv_fields = 1, fwd_fields = 1;
+    mlv::Shard sh{};
     mlv::stream_t stream = 0;
 };
 
@@ -146,6 +153,35 @@ static int ensure_red(mlv_ctx* c, size_t n) {
     if (rc) return rc;
     c->red_cap = n;
     return 0;
+}
+
+// Partition: column tiles of width CT are dealt out in equal contiguous runs of tpr tiles,
+// rows in equal runs of nx/G.
+static void configure_shard(mlv_ctx* c, int rank, int nranks, int inv_fields, int fwd_fields) {
+    const int ct = c->ct;
+    const int ntile = (c->nm + ct - 1) / ct;
+    const int tpr = (ntile + nranks - 1) / nranks;
+    c->rank = rank; c->nranks = nranks;
+    c->inv_fields = inv_fields; c->fwd_fields = fwd_fields;
+    c->nxl = c->p.nx / nranks;
+    if (nranks == 1) {
+        c->nml = c->ipitch;
+        c->nm_loc = c->nm;
+    } else {
+        c->nml = tpr * ct;
+        int left = c->nm - rank * c->nml;
+        c->nm_loc = left < 0 ? 0 : (left > c->nml ? c->nml : left);
+    }
+    int shift = 0;
+    while ((1 << shift) < c->nxl) ++shift;
+    c->sh.m_off = rank * (nranks == 1 ? 0 : c->nml);
+    c->sh.nm_glob = c->nm;
+    c->sh.nml = c->nml;
+    c->sh.rpc_shift = shift;
+    c->sh.tpr = tpr;
+    c->sh.inv_chunk = nranks == 1 ? 0 : (long long)inv_fields * c->nxl * c->nml;
+    c->sh.fwd_chunk = nranks == 1 ? 0 : (long long)fwd_fields * tpr * c->nxl * ct;
+    c->spec_cols = c->p.fdm_z ? c->p.nz : (nranks == 1 ? c->nm : c->nml);
 }
 
 static int need_2d(const mlv_ctx* c, const char* fn) {
@@ -391,6 +427,7 @@ int mlv_create(const mlv_params* p, mlv_ctx** out) {
         if (!rc) rc = rt_h2d(c->tri_inv, inv.data(), tot * sizeof(double), c->stream);
     }
     if (!rc) rc = ensure_red(c, 148 * 16 * 4);
+    if (!rc && !p->fdm_z) configure_shard(c, 0, 1, 1, 1);
 
     if (rc) { mlv_destroy(c); return rc; }
     *out = c;
@@ -416,12 +453,29 @@ int mlv_set_stream(mlv_ctx* c, void* s) {
     return MLV_OK;
 }
 
+int mlv_set_sharding(mlv_ctx* c, int rank, int nranks, int inv_fields, int fwd_fields) {
+    if (!c) { set_error("null context"); return MLV_ERR_INVALID; }
+    if (int rc = need_2d(c, "mlv_set_sharding")) return rc;
+    if (nranks < 1 || rank < 0 || rank >= nranks || (nranks & (nranks - 1)) || c->p.nx / nranks < 2 ||
+        inv_fields < 1 || fwd_fields < 1) {
+        set_error("mlv_set_sharding: need a power-of-two rank count dividing nx/2 and field counts >= 1");
+        return MLV_ERR_INVALID;
+    }
+    configure_shard(c, rank, nranks, inv_fields, fwd_fields);
+    return MLV_OK;
+}
+
 int mlv_get_info(const mlv_ctx* c, mlv_info* o) {
     if (!c || !o) { set_error("null argument"); return MLV_ERR_INVALID; }
     o->nn = c->nn; o->nm = c->nm;
     o->spec_rows = c->spec_rows; o->spec_cols = c->spec_cols;
-    o->ipitch = c->ipitch; o->reserved = 0;
-    o->ibytes = (int64_t)c->p.nx * c->ipitch * (int64_t)sizeof(cplx);
+    o->ipitch = c->nranks == 1 ? c->ipitch : c->nml; o->nm_local = c->nm_loc;
+    // one field of an exchange buffer: inverse nx*nml, forward nranks*tpr*nxl*ct (<= the former + pad)
+    {
+        const int64_t inv = (int64_t)c->p.nx * (c->nranks == 1 ? c->ipitch : c->nml);
+        const int64_t fwd = (int64_t)c->nranks * c->sh.tpr * c->nxl * c->ct;
+        o->ibytes = (inv > fwd ? inv : fwd) * (int64_t)sizeof(cplx);
+    }
     return MLV_OK;
 }
 
@@ -431,7 +485,9 @@ int mlv_x_inverse(mlv_ctx* c, int nf, const void* const* spec, const int32_t* op
     if (int rc = need_2d(c, "mlv_x_inverse")) return rc;
     if (nf < 1 || nf > MLV_XMAXF) { set_error("mlv_x_inverse: 1..%d fields", MLV_XMAXF); return MLV_ERR_INVALID; }
     XInvArgs a;
-    a.nn = c->nn; a.nm = c->nm; a.spitch = c->nm; a.ipitch = c->ipitch; a.nf = nf;
+    a.nn = c->nn; a.nm = c->nm_loc; a.spitch = c->spec_cols; a.ipitch = c->nml; a.nf = nf;
+    a.sh = c->sh;
+    if (c->nm_loc <= 0) return MLV_OK;              // this rank owns no retained column
     for (int f = 0; f < nf; ++f) {
         if (!spec[f] || !idst[f] || op[f] < MLV_OP_IDENT || op[f] > MLV_OP_INVLAP) {
             set_error("mlv_x_inverse: bad field %d", f);
@@ -450,7 +506,7 @@ int mlv_z_inverse(mlv_ctx* c, const void* isrc, double* phys) {
     if (!c || !isrc || !phys) { set_error("mlv_z_inverse: null argument"); return MLV_ERR_INVALID; }
     if (int rc = need_2d(c, "mlv_z_inverse")) return rc;
     ZArgs a{};
-    a.nx = c->p.nx; a.nm = c->nm; a.ipitch = c->ipitch; a.ct = c->ct;
+    a.nx = c->nxl; a.nm = c->nm; a.ipitch = c->nml; a.ct = c->ct; a.sh = c->sh;
     a.I = (const cplx*)isrc; a.P = phys; a.tw = c->planz.tw;
 #define MLV_GO(L) return launch_zc2r<L>(c, a)
     MLV_SWITCH_LOG2(c->log2nz, MLV_GO)
@@ -462,7 +518,7 @@ int mlv_z_forward(mlv_ctx* c, const double* phys, void* idst) {
     if (!c || !idst || !phys) { set_error("mlv_z_forward: null argument"); return MLV_ERR_INVALID; }
     if (int rc = need_2d(c, "mlv_z_forward")) return rc;
     ZArgs a{};
-    a.nx = c->p.nx; a.nm = c->nm; a.ipitch = c->ipitch; a.ct = c->ct;
+    a.nx = c->nxl; a.nm = c->nm; a.ipitch = c->nml; a.ct = c->ct; a.sh = c->sh;
     a.Pin = phys; a.Iout = (cplx*)idst; a.tw = c->planz.tw;
 #define MLV_GO(L) return launch_zr2c<L>(c, a)
     MLV_SWITCH_LOG2(c->log2nz, MLV_GO)
@@ -475,7 +531,9 @@ int mlv_x_forward(mlv_ctx* c, const mlv_xfwd* d) {
     if (int rc = need_2d(c, "mlv_x_forward")) return rc;
     if (d->nf < 1 || d->nf > MLV_XMAXF) { set_error("mlv_x_forward: 1..%d fields", MLV_XMAXF); return MLV_ERR_INVALID; }
     XFwdArgs a;
-    a.nn = c->nn; a.nm = c->nm; a.spitch = c->nm; a.ipitch = c->ipitch; a.nf = d->nf;
+    a.nn = c->nn; a.nm = c->nm_loc; a.spitch = c->spec_cols; a.ipitch = c->nml; a.nf = d->nf;
+    a.sh = c->sh;
+    if (c->nm_loc <= 0) return MLV_OK;
     for (int f = 0; f < d->nf; ++f) {
         if (!d->src[f] || d->sym[f] < MLV_SYM_ONE || d->sym[f] > MLV_SYM_FDZ) {
             set_error("mlv_x_forward: bad field %d", f);
@@ -551,7 +609,7 @@ int mlv_advect_z(mlv_ctx* c, const void* iux, const void* iuz, const void* iq, v
     if (!c || !iux || !iuz || !iq || !ia || !ib) { set_error("mlv_advect_z: null argument"); return MLV_ERR_INVALID; }
     if (int rc = need_2d(c, "mlv_advect_z")) return rc;
     ZAdvArgs a{};
-    a.nx = c->p.nx; a.nm = c->nm; a.ipitch = c->ipitch; a.ct = c->ct;
+    a.nx = c->nxl; a.nm = c->nm; a.ipitch = c->nml; a.ct = c->ct; a.sh = c->sh;
     a.Iux = (const cplx*)iux; a.Iuz = (const cplx*)iuz; a.Iq = (const cplx*)iq;
     a.IA = (cplx*)ia; a.IB = (cplx*)ib; a.tw = c->planz.tw;
     unsigned grid = 0;
@@ -584,6 +642,7 @@ int mlv_spec_lincomb(mlv_ctx* c, const mlv_lin_terms* t, void* out) {
     if (int rc = check_lin(c, t, "mlv_spec_lincomb")) return rc;
     SpecLinArgs a;
     a.rows = c->spec_rows; a.cols = c->spec_cols; a.nn = c->nn; a.fdm = c->p.fdm_z;
+    a.m_off = c->sh.m_off; a.nm_glob = c->p.fdm_z ? 0 : c->nm;
     fill_lin(a.lin, t);
     a.out = (cplx*)out; a.k = c->k;
     auto kfn = k_spec_lincomb;
@@ -596,7 +655,7 @@ int mlv_lap_array(mlv_ctx* c, double coef, double* out) {
     if (int rc = need_2d(c, "mlv_lap_array")) return rc;
     auto kfn = k_lap_array;
     MLV_LAUNCH(kfn, grid1d((size_t)c->spec_rows * c->spec_cols), 256u, 0, c->stream, out,
-               c->spec_rows, c->spec_cols, c->nn, c->k, coef);
+               c->spec_rows, c->spec_cols, c->nn, c->k, coef, c->sh.m_off);
     return MLV_OK;
 }
 
@@ -636,6 +695,7 @@ int mlv_integrate(mlv_ctx* c, const mlv_lin_terms* extra, const mlv_integ* g) {
     if (int rc = check_integ(c, g, "mlv_integrate")) return rc;
     IntegKArgs a;
     a.rows = c->spec_rows; a.cols = c->spec_cols; a.nn = c->nn; a.fdm = c->p.fdm_z;
+    a.m_off = c->sh.m_off;
     fill_lin(a.lin, extra);
     fill_integ(a.integ, g);
     a.k = c->k;

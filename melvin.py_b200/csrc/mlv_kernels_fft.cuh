@@ -80,9 +80,32 @@ MLV_DEV bool xrow_of(int k, int N, int nn, int& r, int& n) {
     return false;
 }
 
-// element (x, m) of a forward intermediate in tile layout [m/CT][nx][CT]
-MLV_DEV size_t tile_off(int x, int m, int nx, int ct) {
-    return ((size_t)(m / ct) * nx + x) * ct + (m % ct);
+// Slab decomposition over G ranks (G = 1: one chunk, everything local).
+//   spectral state : kz-slabs, rank g owns columns [g*nml, (g+1)*nml) (nml = tpr*CT)
+//   physical side  : x-slabs,  rank g owns rows    [g*nxl, (g+1)*nxl)
+// Exchange buffers are laid out so that the block for every peer is contiguous:
+//   inverse (x pass -> z stage): [peer h][field][nxl rows of h][nml cols]  (row layout)
+//   forward (z stage -> x pass): [peer h][field][tpr tiles of h][nxl rows][CT]  (tile layout)
+struct Shard {
+    int m_off;            // global index of local column 0
+    int nm_glob;          // global number of retained columns (nm)
+    int nml;              // columns per rank = pitch of local spectral arrays / inverse buffers
+    int rpc_shift;        // log2(rows per rank)
+    int tpr;              // column tiles per rank
+    long long inv_chunk;  // elements between the blocks of consecutive peers, inverse buffers
+    long long fwd_chunk;  // same, forward buffers
+};
+
+// element (local row xl, global column m) of a forward intermediate, tile layout
+MLV_DEV size_t fwd_off(int xl, int m, int nxl, int ct, const Shard& sh) {
+    const int t = m / ct;
+    const int h = t / sh.tpr, tl = t - h * sh.tpr;
+    return (size_t)h * sh.fwd_chunk + ((size_t)tl * nxl + xl) * ct + (m % ct);
+}
+// element m (global column) of a row of an inverse intermediate whose chunk-0 part starts at `row`
+MLV_DEV size_t inv_col_off(int m, const Shard& sh) {
+    const int h = m / sh.nml;
+    return (size_t)h * sh.inv_chunk + (m - h * sh.nml);
 }
 
 // ------------------------------------------------------ time integration
@@ -174,6 +197,7 @@ struct XInvArgs {
     const cplx* src[MLV_XMAXF];
     int op[MLV_XMAXF];
     cplx* dst[MLV_XMAXF];
+    Shard sh;                    // nm = local valid columns; spectral ops use m + sh.m_off
     SpecConsts k;
     FftTw tw;
 };
@@ -201,6 +225,8 @@ k_xinv(const XInvArgs a) {
         for (int r = threadIdx.x; r < rows; r += C * F::T)
             l2_prefetch_line(a.src[0] + (size_t)r * a.spitch + (size_t)(blockIdx.x + a.wave) * C);
     }
+    const int mg = m + a.sh.m_off;                   // global column (spectral symbols)
+    const int rmask = (1 << a.sh.rpc_shift) - 1;
     bool stash_psi = false;     // stash holds psi = -src/lap instead of the raw column
     for (int f = 0; f < a.nf; ++f) {
         cplx v[16];
@@ -239,11 +265,11 @@ k_xinv(const XInvArgs a) {
                 if (!xrow_of(kk, F::N, a.nn, r, n)) continue;
                 cplx psi = v[j];
                 if (!have_psi) {
-                    psi = spectral_op(XOP_PSI, v[j], n, m, a.k);
+                    psi = spectral_op(XOP_PSI, v[j], n, mg, a.k);
                     if (park_psi) stash[(size_t)r * C + c] = psi;
                 }
                 // ux = -(i kz m) psi, uz = (i kx n) psi   (utility.py:71,78)
-                if (op == XOP_UX) { const double b = a.k.kz0 * m; v[j] = mk(b * psi.y, -b * psi.x); }
+                if (op == XOP_UX) { const double b = a.k.kz0 * mg; v[j] = mk(b * psi.y, -b * psi.x); }
                 else if (op == XOP_UZ) { const double b = a.k.kx0 * n; v[j] = mk(-b * psi.y, b * psi.x); }
                 else v[j] = psi;
             }
@@ -253,14 +279,17 @@ k_xinv(const XInvArgs a) {
             for (int j = 0; j < 16; ++j) {
                 const int kk = tau + F::T * j;
                 int r, n;
-                if (xrow_of(kk, F::N, a.nn, r, n)) v[j] = spectral_op(op, v[j], n, m, a.k);
+                if (xrow_of(kk, F::N, a.nn, r, n)) v[j] = spectral_op(op, v[j], n, mg, a.k);
             }
         }
         fft_line<LOG2N, true>(v, tau, a.tw, xc);
         if (valid) {
             cplx* __restrict__ dst = a.dst[f];
             MLV_UNROLL
-            for (int j = 0; j < 16; ++j) dst[(size_t)(tau + F::T * j) * a.ipitch + m] = v[j];
+            for (int j = 0; j < 16; ++j) {
+                const int x = tau + F::T * j;          // global row -> block of its owner
+                dst[(size_t)(x >> a.sh.rpc_shift) * a.sh.inv_chunk + (size_t)(x & rmask) * a.ipitch + m] = v[j];
+            }
         }
     }
 }
@@ -279,6 +308,7 @@ struct XFwdArgs {
     cplx* dst;                   // mode 0: spectral (2nn+1, nm)
     LinTerms lin;                // mode 1
     IntegArgs integ;             // mode 1
+    Shard sh;                    // nm = local valid columns; symbols use m + sh.m_off
     SpecConsts k;
     FftTw tw;
 };
@@ -301,14 +331,15 @@ k_xfwd(const XFwdArgs a) {
     xc.buf = reinterpret_cast<cplx*>(MLV_SMEM_BASE());
     xc.c = c;
     cplx* tile = xc.buf + (size_t)F::XSLOTS * C;      // (2nn+1)*C entries
-    const double sz = a.symz[m];
+    const double sz = a.symz[m + a.sh.m_off];
+    const int rpc = 1 << a.sh.rpc_shift;              // rows per peer block
     {   // L2 prefetch: the other fields' blocks, the next CTA's first block, and the
         // state / history columns the epilogue will read
         constexpr unsigned CHUNK = 16384;
         constexpr unsigned BLOCK = (unsigned)F::N * C * (unsigned)sizeof(cplx);
         constexpr int NCH = (int)(BLOCK / CHUNK) > 0 ? (int)(BLOCK / CHUNK) : 1;
         const int t = threadIdx.x;
-        if (t < NCH * a.nf) {
+        if (rpc == F::N && t < NCH * a.nf) {
             const int f = t / NCH, ch = t % NCH;
             const unsigned bytes = BLOCK < CHUNK ? BLOCK : CHUNK;
             if (f > 0) {
@@ -331,7 +362,11 @@ k_xfwd(const XFwdArgs a) {
         const cplx* __restrict__ src = a.src[f];
         MLV_UNROLL
         for (int j = 0; j < 16; ++j)                       // tile layout: one contiguous block
-            v[j] = src[((size_t)blockIdx.x * F::N + (tau + F::T * j)) * C + c];
+        {
+            const int x = tau + F::T * j;              // global row -> block of its owner
+            v[j] = src[(size_t)(x >> a.sh.rpc_shift) * a.sh.fwd_chunk +
+                       ((size_t)blockIdx.x * rpc + (x & (rpc - 1))) * C + c];
+        }
         fft_line<LOG2N, false>(v, tau, a.tw, xc);
         const int sym = a.sym[f];
         const double cf = a.coef[f] * a.scale;
@@ -390,9 +425,10 @@ k_xfwd(const XFwdArgs a) {
             const int e = e0 + u * NT;
             const int r = e / C, mm = m0 + e % C;
             const int n = r <= a.nn ? r : r - rows;
-            const cplx f0 = cadd(t[u], lin_terms_at(a.lin, idx[u], n, mm, a.k));
+            const int mg = mm + a.sh.m_off;
+            const cplx f0 = cadd(t[u], lin_terms_at(a.lin, idx[u], n, mg, a.k));
             a.integ.f0[idx[u]] = f0;
-            a.integ.q_out[idx[u]] = integrate_value(a.integ, f0, q[u], f1[u], f2[u], f3[u], idx[u], n, mm, a.k);
+            a.integ.q_out[idx[u]] = integrate_value(a.integ, f0, q[u], f1[u], f2[u], f3[u], idx[u], n, mg, a.k);
         }
     }
 }
@@ -405,7 +441,7 @@ k_xfwd(const XFwdArgs a) {
 //   otherwise       : 0   (2/3-rule truncation)
 template <int LOG2N>
 MLV_DEV void zpair_load_line(cplx (&v)[16], const cplx* __restrict__ rowA,
-                             const cplx* __restrict__ rowB, int tau_, int nm) {
+                             const cplx* __restrict__ rowB, int tau_, int nm, const Shard& sh) {
     typedef FftCfg<LOG2N> F;
     const int tau = opaque_int(tau_);
     MLV_UNROLL
@@ -415,7 +451,8 @@ MLV_DEV void zpair_load_line(cplx (&v)[16], const cplx* __restrict__ rowA,
         v[j] = mk(0.0, 0.0);
         if (lo || hi) {
             const int mm = lo ? idx : F::N - idx;
-            const cplx A = rowA[mm], B = rowB[mm];
+            const size_t off = inv_col_off(mm, sh);
+            const cplx A = rowA[off], B = rowB[off];
             v[j] = lo ? (idx == 0 ? mk(A.x, B.x) : mk(A.x - B.y, A.y + B.x))
                       : mk(A.x + B.y, B.x - A.y);
         }
@@ -442,7 +479,8 @@ MLV_DEV void zpair_unpack(cplx Zk, cplx P, cplx& A, cplx& B) {
 }
 
 struct ZArgs {
-    int nx, nm, ipitch, ct;
+    int nx, nm, ipitch, ct;      // nx = local rows, nm = global retained columns
+    Shard sh;
     const cplx* I;     // c2r input / unused
     cplx* Iout;        // r2c output
     const double* Pin; // r2c input
@@ -464,7 +502,7 @@ k_z_c2r(const ZArgs a) {
     const cplx* rowA = a.I + (size_t)(2 * rp) * a.ipitch;
     const cplx* rowB = rowA + a.ipitch;
     cplx v[16];
-    zpair_load_line<LOG2N>(v, rowA, rowB, tau, a.nm);
+    zpair_load_line<LOG2N>(v, rowA, rowB, tau, a.nm, a.sh);
     fft_line<LOG2N, true>(v, tau, a.tw, xc);
     if (valid) {
         double* pa = a.P + (size_t)(2 * rp) * F::N;
@@ -508,7 +546,7 @@ k_z_r2c(const ZArgs a) {
                 const cplx P = (kk == 0) ? v[j] : pbuf[kk];
                 cplx A, B;
                 zpair_unpack(v[j], P, A, B);
-                cplx* o = a.Iout + tile_off(2 * rp, kk, a.nx, a.ct);
+                cplx* o = a.Iout + fwd_off(2 * rp, kk, a.nx, a.ct, a.sh);
                 o[0] = A;
                 o[a.ct] = B;                                   // row 2rp+1
             }
@@ -621,7 +659,8 @@ k_x1d_r2c(const X1dArgs a) {
 // Also produces the reductions the tickers need (Integrator.py:35-44 signed max
 // of ux, uz; utility.py:42-59 sum ux^2, uz^2) as per-CTA partials.
 struct ZAdvArgs {
-    int nx, nm, ipitch, ct;
+    int nx, nm, ipitch, ct;        // nx = local rows, nm = global retained columns
+    Shard sh;
     int wave;                      // CTAs resident at once (prefetch distance)
     const cplx* Iux;
     const cplx* Iuz;
@@ -653,7 +692,7 @@ k_z_advect(const ZAdvArgs a) {
 
     // announce the rows of the two velocity components (needed one and two transforms
     // from now) and the scalar rows of the CTA that will follow this one on the SM
-    if (tau < 6) {
+    if (tau < 6 && a.sh.nml >= a.nm) {           // rows are contiguous only when unsharded
         const unsigned rowbytes = (unsigned)a.nm * (unsigned)sizeof(cplx);
         if (tau < 4) {
             l2_prefetch_bulk((tau < 2 ? a.Iux : a.Iuz) + rowoff + (size_t)(tau & 1) * a.ipitch, rowbytes);
@@ -667,7 +706,7 @@ k_z_advect(const ZAdvArgs a) {
     cplx v[16];
     {   // q -> physical, parked in the thread-private stash
         const cplx* rowA = a.Iq + rowoff;
-        zpair_load_line<LOG2N>(v, rowA, rowA + a.ipitch, tau, a.nm);
+        zpair_load_line<LOG2N>(v, rowA, rowA + a.ipitch, tau, a.nm, a.sh);
         fft_line<LOG2N, true>(v, tau, a.tw, xc);
         MLV_UNROLL
         for (int j = 0; j < 16; ++j) stash[j * F::T] = v[j];
@@ -676,7 +715,7 @@ k_z_advect(const ZAdvArgs a) {
         MLV_SCHED_FENCE();
         {
             const cplx* src = (pass == 0 ? a.Iux : a.Iuz) + rowoff;
-            zpair_load_line<LOG2N>(v, src, src + a.ipitch, tau, a.nm);
+            zpair_load_line<LOG2N>(v, src, src + a.ipitch, tau, a.nm, a.sh);
         }
         MLV_SCHED_FENCE();
         fft_line<LOG2N, true>(v, tau, a.tw, xc);
@@ -706,7 +745,7 @@ k_z_advect(const ZAdvArgs a) {
                     const cplx P = (kk == 0) ? v[j] : pbuf[kk];
                     cplx A, B;
                     zpair_unpack(v[j], P, A, B);
-                    cplx* o = out + tile_off(2 * rp, kk, a.nx, a.ct);
+                    cplx* o = out + fwd_off(2 * rp, kk, a.nx, a.ct, a.sh);
                     o[0] = A;
                     o[a.ct] = B;                               // row 2rp+1
                 }

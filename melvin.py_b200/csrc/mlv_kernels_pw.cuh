@@ -19,6 +19,7 @@ struct View2 {
 // FDM-z: rows n = 0..nn-1, cols are z points (ops that need m are rejected by host).
 struct SpecLinArgs {
     int rows, cols, nn, fdm;
+    int m_off, nm_glob;          // slab decomposition: global column = m_off + local column
     LinTerms lin;
     cplx* out;
     SpecConsts k;
@@ -30,25 +31,27 @@ __global__ void __launch_bounds__(256) k_spec_lincomb(const SpecLinArgs a) {
          i += (size_t)gridDim.x * blockDim.x) {
         const int r = (int)(i / a.cols), m = (int)(i % a.cols);
         const int n = a.fdm ? r : (r <= a.nn ? r : r - 2 * a.nn - 1);
-        a.out[i] = lin_terms_at(a.lin, i, n, a.fdm ? 0 : m, a.k);
+        const int mg = a.fdm ? 0 : m + a.m_off;
+        a.out[i] = (a.fdm || mg < a.nm_glob) ? lin_terms_at(a.lin, i, n, mg, a.k) : mk(0.0, 0.0);
     }
 }
 
 // real array of the Laplacian symbol (SpatialDifferentiator.py:70-74)
 __global__ void __launch_bounds__(256)
-k_lap_array(double* out, int rows, int cols, int nn, SpecConsts k, double coef) {
+k_lap_array(double* out, int rows, int cols, int nn, SpecConsts k, double coef, int m_off) {
     const size_t total = (size_t)rows * cols;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (size_t)gridDim.x * blockDim.x) {
         const int r = (int)(i / cols), m = (int)(i % cols);
         const int n = (r <= nn ? r : r - 2 * nn - 1);
-        out[i] = coef * lap_symbol(n, m, k);
+        out[i] = coef * lap_symbol(n, m + m_off, k);
     }
 }
 
 // f0 += lin terms (optional); q_out = integrate(q_in, history)   (Integrator.py:53-63)
 struct IntegKArgs {
     int rows, cols, nn, fdm;
+    int m_off;
     LinTerms lin;
     IntegArgs integ;
     SpecConsts k;
@@ -60,12 +63,13 @@ __global__ void __launch_bounds__(256) k_integrate(const IntegKArgs a) {
          i += (size_t)gridDim.x * blockDim.x) {
         const int r = (int)(i / a.cols), m = (int)(i % a.cols);
         const int n = a.fdm ? r : (r <= a.nn ? r : r - 2 * a.nn - 1);
+        const int mg = a.fdm ? 0 : m + a.m_off;
         cplx f0 = a.integ.f0[i];
         if (a.lin.n > 0) {
-            f0 = cadd(f0, lin_terms_at(a.lin, i, n, a.fdm ? 0 : m, a.k));
+            f0 = cadd(f0, lin_terms_at(a.lin, i, n, mg, a.k));
             a.integ.f0[i] = f0;
         }
-        integrate_point(a.integ, f0, i, n, a.fdm ? 0 : m, a.k);
+        integrate_point(a.integ, f0, i, n, mg, a.k);
     }
 }
 

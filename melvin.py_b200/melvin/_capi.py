@@ -18,7 +18,7 @@ KIND_REAL, KIND_CPLX, KIND_SCALAR = range(3)
 RED_SUM, RED_MAX, RED_MIN, RED_SUMSQ, RED_SUMPROD = range(5)
 
 EXPORTS = [
-    "mlv_create", "mlv_destroy", "mlv_set_stream", "mlv_get_info", "mlv_last_error",
+    "mlv_create", "mlv_destroy", "mlv_set_stream", "mlv_get_info", "mlv_set_sharding", "mlv_last_error",
     "mlv_abi_version", "mlv_launch_count", "mlv_to_physical", "mlv_to_spectral", "mlv_x_inverse",
     "mlv_z_inverse", "mlv_z_forward", "mlv_x_forward", "mlv_advect_z", "mlv_advect_phys",
     "mlv_spec_lincomb", "mlv_lap_array", "mlv_stencil", "mlv_solve_fdm", "mlv_integrate",
@@ -39,7 +39,7 @@ class Params(C.Structure):
 
 class Info(C.Structure):
     _fields_ = [("nn", C.c_int32), ("nm", C.c_int32), ("spec_rows", C.c_int32),
-                ("spec_cols", C.c_int32), ("ipitch", C.c_int32), ("reserved", C.c_int32),
+                ("spec_cols", C.c_int32), ("ipitch", C.c_int32), ("nm_local", C.c_int32),
                 ("ibytes", C.c_int64)]
 
 
@@ -97,6 +97,7 @@ def declare(lib):
         "mlv_destroy": [vp],
         "mlv_set_stream": [vp, vp],
         "mlv_get_info": [vp, C.POINTER(Info)],
+        "mlv_set_sharding": [vp, i32, i32, i32, i32],
         "mlv_abi_version": [],
         "mlv_to_physical": [vp, vp, vp, vp],
         "mlv_to_spectral": [vp, vp, vp, vp],

@@ -1,0 +1,171 @@
+"""Slab-decomposed fused step: one process per GPU, spectral state in kz-slabs
+(column slabs), physical side in x-slabs (row slabs), one all-to-all of the
+x-transformed intermediate per direction and step.
+
+The reference is single-device; this module is the multi-GPU form of the loop body of
+its single-scalar examples (examples/taylor_green_vortex.py:85-95,
+examples/kelvin_helmholtz_instability.py:115-131):
+
+    calc_velocity_from_vorticity(w, psi, ux, uz, solver)
+    lin_op = coef * w.lap()
+    dw[:] = -w.vec_dot_nabla(ux.getp(), uz.getp())
+    integrator.integrate(w, dw, lin_op)
+    simulation.end_loop()          # CFL every cfl_cadence loops, tracker every tracker_cadence
+
+Per step and rank:  mlv_x_inverse (local columns, 3 fields)  ->  all-to-all  ->
+mlv_advect_z (local rows)  ->  all-to-all  ->  mlv_x_forward (local columns, fused RHS +
+AB + theta-scheme).  The x stencil of the conservative form is applied as its Fourier
+symbol, so no halo exchange exists.  Reductions (CFL max, kinetic energy)
+are 4-double all-reduces at ticker cadence.  Collectives go through torch.distributed
+(NCCL on GPUs; gloo in the CPU tests of the host logic).
+"""
+import ctypes
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _backend, _capi
+
+
+class ShardedScalarStepper:
+    def __init__(self, nx, nz, lx, lz, coef, dt, fd_order=2, ab_order=2, alpha=0.51,
+                 cfl_cutoff=0.5, cfl_cadence=10, tracker_cadence=100, group=None):
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.nx, self.nz, self.lx, self.lz = nx, nz, lx, lz
+        self.coef, self.dt, self.alpha, self.order = float(coef), float(dt), float(alpha), int(ab_order)
+        self.cfl_cutoff, self.cfl_cadence, self.tracker_cadence = cfl_cutoff, cfl_cadence, tracker_cadence
+        self.dx, self.dz = lx / nx, lz / nz
+        self.ctx = _backend.Context(nx, nz, lx, lz, False, fd_order)
+        self.ctx.call("mlv_set_sharding", self.rank, self.world, 3, 2, count=False)
+        info = _capi.Info()
+        _capi.check(self.ctx.lib, self.ctx.lib.mlv_get_info(self.ctx.handle, ctypes.byref(info)))
+        self.nn, self.nm = info.nn, info.nm
+        self.rows, self.nml, self.nm_local = info.spec_rows, info.spec_cols, info.nm_local
+        self.m_off = self.rank * self.nml if self.world > 1 else 0
+        self.nxl = nx // self.world
+        field = info.ibytes // 16                      # elements of one field of an exchange buffer
+        self.inv_field = self.nxl * info.ipitch        # per peer and field
+        tiles = field // (self.world * self.nxl)       # tpr * ct
+        self.fwd_field = tiles * self.nxl
+        cplx = np.complex128
+        self.inv_send = _backend.zeros((self.world * 3 * self.inv_field,), cplx)
+        self.fwd_send = _backend.zeros((self.world * 2 * self.fwd_field,), cplx)
+        if self.world > 1:
+            self.inv_recv = _backend.zeros((self.world * 3 * self.inv_field,), cplx)
+            self.fwd_recv = _backend.zeros((self.world * 2 * self.fwd_field,), cplx)
+        else:
+            self.inv_recv, self.fwd_recv = self.inv_send, self.fwd_send
+        self.w = [_backend.zeros((self.rows, self.nml), cplx), _backend.zeros((self.rows, self.nml), cplx)]
+        self.cur = 0
+        self.hist = _backend.zeros((self.order, self.rows, self.nml), cplx)
+        self.hidx = 0
+        self.red4 = _backend.zeros((4,), np.float64)
+        self.t = 0.0
+        self.loop = 0
+        self._cfl_counter = 0
+        self._trk_counter = 0
+        self.ke_times, self.ke = [], []
+        self.bytes_exchanged_per_step = 16 * (3 * self.inv_field + 2 * self.fwd_field) * (self.world - 1)
+
+    # ------------------------------------------------------------------ state
+    def load_spectral(self, w_full):
+        """Keep this rank's column slab of a full (2nn+1, nm) spectral array (host)."""
+        w_full = np.asarray(w_full)
+        slab = np.zeros((self.rows, self.nml), dtype=np.complex128)
+        n = self.nm_local
+        if n > 0:
+            slab[:, :n] = w_full[:, self.m_off:self.m_off + n]
+        self.w[self.cur].copy_(_backend.from_host(slab))
+        self.hist.zero_()
+        self.hidx = 0
+
+    def gather_spectral(self):
+        """Full (2nn+1, nm) spectral state on the host of every rank."""
+        local = self.w[self.cur]
+        if self.world == 1:
+            return _backend.to_host(local)[:, : self.nm]
+        parts = [torch.empty_like(local) for _ in range(self.world)]
+        dist.all_gather([torch.view_as_real(p) for p in parts], torch.view_as_real(local), group=self.group)
+        full = np.concatenate([_backend.to_host(p) for p in parts], axis=1)
+        return full[:, : self.nm]
+
+    # ------------------------------------------------------------------- step
+    def _ptr(self, t, offset_elems=0):
+        return ctypes.c_void_p(t.data_ptr() + 16 * offset_elems)
+
+    def _all_to_all(self, recv, send):
+        if self.world > 1:
+            dist.all_to_all_single(torch.view_as_real(recv), torch.view_as_real(send), group=self.group)
+
+    def step(self):
+        ctx, vp = self.ctx, ctypes.c_void_p
+        w_in, w_out = self.w[self.cur], self.w[1 - self.cur]
+        wp = w_in.data_ptr()
+        # 1. inverse x pass on the local columns: q = w, ux, uz (psi shared inside the kernel)
+        srcs = (vp * 3)(wp, wp, wp)
+        ops = (ctypes.c_int32 * 3)(_capi.OP_IDENT, _capi.OP_UX, _capi.OP_UZ)
+        dsts = (vp * 3)(*[self.inv_send.data_ptr() + 16 * f * self.inv_field for f in range(3)])
+        ctx.call("mlv_x_inverse", 3, srcs, ops, dsts)
+        # 2. transpose: row block h of every field goes to rank h
+        self._all_to_all(self.inv_recv, self.inv_send)
+        # 3. physical-space stage on the local rows
+        ctx.call("mlv_advect_z", self._ptr(self.inv_recv, 1 * self.inv_field),
+                 self._ptr(self.inv_recv, 2 * self.inv_field), self._ptr(self.inv_recv, 0),
+                 self._ptr(self.fwd_send, 0), self._ptr(self.fwd_send, self.fwd_field),
+                 self._ptr(self.red4))
+        # 4. transpose back: tile block h goes to rank h
+        self._all_to_all(self.fwd_recv, self.fwd_send)
+        # 5. forward x pass + RHS + AB + theta-scheme on the local columns
+        d = _capi.XFwd()
+        d.nf, d.mode = 2, 1
+        d.src[0] = self.fwd_recv.data_ptr()
+        d.src[1] = self.fwd_recv.data_ptr() + 16 * self.fwd_field
+        d.sym[0], d.sym[1] = _capi.SYM_FDX, _capi.SYM_FDZ
+        d.coef[0] = d.coef[1] = -1.0
+        d.lin = _capi.make_lin_terms([])
+        g = d.integ
+        g.ab_order, g.scheme = self.order, _capi.SCHEME_SI_LAP
+        g.dt, g.alpha, g.lcoef = self.dt, self.alpha, self.coef
+        g.q_in, g.q_out = wp, w_out.data_ptr()
+        lv = [self.hist[(self.hidx - k) % self.order].data_ptr() for k in range(self.order)]
+        g.f0, g.fm1 = lv[0], lv[1]
+        if self.order == 4:
+            g.fm2, g.fm3 = lv[2], lv[3]
+        ctx.call("mlv_x_forward", ctypes.byref(d))
+        self.cur = 1 - self.cur
+        self.hidx = (self.hidx + 1) % self.order
+        self.end_loop()
+
+    # ------------------------------------------------- tickers (Simulation.end_loop)
+    def _global_reductions(self):
+        r = self.red4.clone()
+        if self.world > 1:
+            mx, sm = r[:2].clone(), r[2:].clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=self.group)
+            dist.all_reduce(sm, op=dist.ReduceOp.SUM, group=self.group)
+            r = torch.cat([mx, sm])
+        return _backend.to_host(r)
+
+    def end_loop(self):
+        self.loop += 1
+        self.t += self.dt
+        need_cfl = self._cfl_counter < self.loop
+        need_trk = self._trk_counter < self.loop
+        if not (need_cfl or need_trk):
+            return
+        mx, mz, sx, sz = self._global_reductions()
+        if need_cfl:                                   # Integrator.set_dt (Integrator.py:35-44)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                cfl_dt = min(np.float64(self.dx) / mx, np.float64(self.dz) / mz)
+            if self.dt > cfl_dt or np.isnan(cfl_dt):
+                raise Exception("CFL condition breached")
+            while self.dt > self.cfl_cutoff * cfl_dt:
+                self.dt = self.dt * 0.9
+            self._cfl_counter += self.cfl_cadence
+        if need_trk:                                   # calc_kinetic_energy (utility.py:42-59)
+            self.ke_times.append(self.t)
+            self.ke.append(0.5 * (sz + sx) / (self.nx * self.nz))
+            self._trk_counter += self.tracker_cadence
