@@ -155,6 +155,18 @@ int mlv_get_info(const mlv_ctx* ctx, mlv_info* out);
  * per direction (NCCL) between those calls.  inv_fields / fwd_fields = fields batched
  * per exchange (block strides).  mlv_get_info then reports the local shapes. */
 int mlv_set_sharding(mlv_ctx* ctx, int rank, int nranks, int inv_fields, int fwd_fields);
+/* Compute + collective in one kernel: receive buffers allocated with mlv_p2p_alloc are
+ * exported to the peer processes (64-byte CUDA IPC handle), opened there with
+ * mlv_p2p_open and registered with mlv_set_peer_buffers (which = 0: inverse exchange,
+ * 1: forward exchange; bufs[h] = rank h's receive buffer, own entry = own buffer).
+ * From then on mlv_x_inverse / mlv_advect_z store every peer's block straight into
+ * that peer's receive buffer over NVLink (destination pointers passed to those calls
+ * must point into the caller's own receive buffer); the caller only has to order the
+ * producer and consumer kernels across ranks (a barrier), no all-to-all is needed. */
+int mlv_p2p_alloc(mlv_ctx* ctx, int64_t bytes, void** ptr, void* handle64);
+int mlv_p2p_open(mlv_ctx* ctx, const void* handle64, void** ptr);
+int mlv_p2p_close(mlv_ctx* ctx, void* ptr, int opened);
+int mlv_set_peer_buffers(mlv_ctx* ctx, int which, void* const* bufs);
 const char* mlv_last_error(void);
 int mlv_abi_version(void);
 long long mlv_launch_count(void);   /* kernels launched by the library so far (process-wide) */

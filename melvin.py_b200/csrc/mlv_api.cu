@@ -49,6 +49,10 @@ struct mlv_ctx {
     int nxl = 0;                // local rows
     int inv_fields = 1, fwd_fields = 1;
     mlv::Shard sh{};
+    // peer-mapped receive buffers (mlv_set_peer_buffers); null = exchange by all-to-all
+    mlv::cplx* peer_inv[MLV_MAXPEER] = {};
+    mlv::cplx* peer_fwd[MLV_MAXPEER] = {};
+    bool p2p_inv = false, p2p_fwd = false;
     mlv::stream_t stream = 0;
 };
 
@@ -456,12 +460,57 @@ int mlv_set_stream(mlv_ctx* c, void* s) {
 int mlv_set_sharding(mlv_ctx* c, int rank, int nranks, int inv_fields, int fwd_fields) {
     if (!c) { set_error("null context"); return MLV_ERR_INVALID; }
     if (int rc = need_2d(c, "mlv_set_sharding")) return rc;
-    if (nranks < 1 || rank < 0 || rank >= nranks || (nranks & (nranks - 1)) || c->p.nx / nranks < 2 ||
+    if (nranks < 1 || nranks > MLV_MAXPEER || rank < 0 || rank >= nranks || (nranks & (nranks - 1)) || c->p.nx / nranks < 2 ||
         inv_fields < 1 || fwd_fields < 1) {
         set_error("mlv_set_sharding: need a power-of-two rank count dividing nx/2 and field counts >= 1");
         return MLV_ERR_INVALID;
     }
     configure_shard(c, rank, nranks, inv_fields, fwd_fields);
+    return MLV_OK;
+}
+
+// ---- peer memory (CUDA IPC): receive buffers that other ranks' kernels store into
+int mlv_p2p_alloc(mlv_ctx* c, int64_t bytes, void** ptr, void* handle64) {
+    if (!c || !ptr || !handle64 || bytes <= 0) { set_error("mlv_p2p_alloc: bad argument"); return MLV_ERR_INVALID; }
+#ifdef MLV_EMU
+    set_error("peer memory is not available in the emulation build");
+    return MLV_ERR_UNSUPPORTED;
+#else
+    if (int rc = rt_check(cudaMalloc(ptr, (size_t)bytes), "cudaMalloc")) return rc;
+    if (int rc = rt_check(cudaMemset(*ptr, 0, (size_t)bytes), "cudaMemset")) return rc;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    return rt_check(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)handle64, *ptr), "cudaIpcGetMemHandle");
+#endif
+}
+
+int mlv_p2p_open(mlv_ctx* c, const void* handle64, void** ptr) {
+    if (!c || !ptr || !handle64) { set_error("mlv_p2p_open: bad argument"); return MLV_ERR_INVALID; }
+#ifdef MLV_EMU
+    set_error("peer memory is not available in the emulation build");
+    return MLV_ERR_UNSUPPORTED;
+#else
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    return rt_check(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
+#endif
+}
+
+int mlv_p2p_close(mlv_ctx* c, void* ptr, int opened) {
+    if (!c || !ptr) return MLV_OK;
+#ifdef MLV_EMU
+    return MLV_OK;
+#else
+    return rt_check(opened ? cudaIpcCloseMemHandle(ptr) : cudaFree(ptr), "mlv_p2p_close");
+#endif
+}
+
+int mlv_set_peer_buffers(mlv_ctx* c, int which, void* const* bufs) {
+    if (!c || (which != 0 && which != 1)) { set_error("mlv_set_peer_buffers: bad argument"); return MLV_ERR_INVALID; }
+    if (c->nranks > MLV_MAXPEER) { set_error("at most %d peers", MLV_MAXPEER); return MLV_ERR_UNSUPPORTED; }
+    bool& flag = which == 0 ? c->p2p_inv : c->p2p_fwd;
+    cplx** tab = which == 0 ? c->peer_inv : c->peer_fwd;
+    flag = bufs != nullptr;
+    for (int h = 0; h < c->nranks; ++h) tab[h] = bufs ? (cplx*)bufs[h] : nullptr;
     return MLV_OK;
 }
 
@@ -494,6 +543,15 @@ int mlv_x_inverse(mlv_ctx* c, int nf, const void* const* spec, const int32_t* op
             return MLV_ERR_INVALID;
         }
         a.src[f] = (const cplx*)spec[f]; a.op[f] = op[f]; a.dst[f] = (cplx*)idst[f];
+    }
+    for (int f = 0; f < nf; ++f) a.dstoff[f] = (cplx*)idst[f] - (cplx*)idst[0];
+    for (int h = 0; h < c->nranks; ++h) {
+        if (c->p2p_inv) {   // idst[] point into this rank's own receive buffer (block 0 position)
+            a.out.blk[h] = c->peer_inv[h] + (size_t)c->rank * c->sh.inv_chunk +
+                           ((cplx*)idst[0] - c->peer_inv[c->rank]);
+        } else {
+            a.out.blk[h] = (cplx*)idst[0] + (size_t)h * c->sh.inv_chunk;
+        }
     }
     a.k = c->k; a.tw = c->planx.tw;
 #define MLV_GO(L) return launch_xinv<L>(c, a)
@@ -612,6 +670,15 @@ int mlv_advect_z(mlv_ctx* c, const void* iux, const void* iuz, const void* iq, v
     a.nx = c->nxl; a.nm = c->nm; a.ipitch = c->nml; a.ct = c->ct; a.sh = c->sh;
     a.Iux = (const cplx*)iux; a.Iuz = (const cplx*)iuz; a.Iq = (const cplx*)iq;
     a.IA = (cplx*)ia; a.IB = (cplx*)ib; a.tw = c->planz.tw;
+    a.outoff[0] = 0; a.outoff[1] = (cplx*)ib - (cplx*)ia;
+    for (int h = 0; h < c->nranks; ++h) {
+        if (c->p2p_fwd) {
+            a.out.blk[h] = c->peer_fwd[h] + (size_t)c->rank * c->sh.fwd_chunk +
+                           ((cplx*)ia - c->peer_fwd[c->rank]);
+        } else {
+            a.out.blk[h] = (cplx*)ia + (size_t)h * c->sh.fwd_chunk;
+        }
+    }
     unsigned grid = 0;
     int rc = 0;
 #define MLV_GO(L) rc = launch_zadv<L>(c, a, grid)

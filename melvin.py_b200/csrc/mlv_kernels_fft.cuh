@@ -96,6 +96,15 @@ struct Shard {
     long long fwd_chunk;  // same, forward buffers
 };
 
+// Where the producer kernels store the block destined for peer h.  Without peer
+// memory: blk[h] = local send buffer + h*chunk (an all-to-all follows).  With peer
+// memory (mlv_set_peer_buffers): blk[h] = peer h's receive buffer + rank*chunk, i.e. the
+// exchange is fused into the stores of the kernel and crosses NVLink directly.
+#define MLV_MAXPEER 8
+struct PeerBlocks {
+    cplx* blk[MLV_MAXPEER];
+};
+
 // element (local row xl, global column m) of a forward intermediate, tile layout
 MLV_DEV size_t fwd_off(int xl, int m, int nxl, int ct, const Shard& sh) {
     const int t = m / ct;
@@ -198,6 +207,8 @@ struct XInvArgs {
     int op[MLV_XMAXF];
     cplx* dst[MLV_XMAXF];
     Shard sh;                    // nm = local valid columns; spectral ops use m + sh.m_off
+    PeerBlocks out;              // destination block per row owner; dst[f] are offsets into it
+    long long dstoff[MLV_XMAXF];
     SpecConsts k;
     FftTw tw;
 };
@@ -284,11 +295,11 @@ k_xinv(const XInvArgs a) {
         }
         fft_line<LOG2N, true>(v, tau, a.tw, xc);
         if (valid) {
-            cplx* __restrict__ dst = a.dst[f];
+            const size_t off = (size_t)a.dstoff[f] + m;
             MLV_UNROLL
             for (int j = 0; j < 16; ++j) {
                 const int x = tau + F::T * j;          // global row -> block of its owner
-                dst[(size_t)(x >> a.sh.rpc_shift) * a.sh.inv_chunk + (size_t)(x & rmask) * a.ipitch + m] = v[j];
+                a.out.blk[x >> a.sh.rpc_shift][off + (size_t)(x & rmask) * a.ipitch] = v[j];
             }
         }
     }
@@ -665,6 +676,8 @@ struct ZAdvArgs {
     const cplx* Iux;
     const cplx* Iuz;
     const cplx* Iq;
+    PeerBlocks out;                // destination block per tile owner; IA/IB given as offsets
+    long long outoff[2];
     cplx* IA;                      // out: z-spectrum of ux q   (tile layout)
     cplx* IB;                      // out: z-spectrum of uz q
     double* red;                   // [gridDim.x][4] partials: max ux, max uz, sum ux^2, sum uz^2
@@ -737,7 +750,7 @@ k_z_advect(const ZAdvArgs a) {
         zpair_publish<LOG2N>(v, tau, a.nm, pbuf);
         __syncthreads();
         if (valid) {
-            cplx* out = (pass == 0 ? a.IA : a.IB);
+            const size_t foff = (size_t)a.outoff[pass];
             MLV_UNROLL
             for (int j = 0; j < 16; ++j) {
                 const int kk = tau + F::T * j;
@@ -745,7 +758,9 @@ k_z_advect(const ZAdvArgs a) {
                     const cplx P = (kk == 0) ? v[j] : pbuf[kk];
                     cplx A, B;
                     zpair_unpack(v[j], P, A, B);
-                    cplx* o = out + fwd_off(2 * rp, kk, a.nx, a.ct, a.sh);
+                    const int t = kk / a.ct;
+                    const int h = t / a.sh.tpr, tl = t - h * a.sh.tpr;     // tile owner
+                    cplx* o = a.out.blk[h] + foff + ((size_t)tl * a.nx + 2 * rp) * a.ct + (kk % a.ct);
                     o[0] = A;
                     o[a.ct] = B;                               // row 2rp+1
                 }

@@ -20,6 +20,7 @@ are 4-double all-reduces at ticker cadence.  Collectives go through torch.distri
 (NCCL on GPUs; gloo in the CPU tests of the host logic).
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -30,7 +31,7 @@ from . import _backend, _capi
 
 class ShardedScalarStepper:
     def __init__(self, nx, nz, lx, lz, coef, dt, fd_order=2, ab_order=2, alpha=0.51,
-                 cfl_cutoff=0.5, cfl_cadence=10, tracker_cadence=100, group=None):
+                 cfl_cutoff=0.5, cfl_cadence=10, tracker_cadence=100, group=None, p2p=None):
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -51,13 +52,27 @@ class ShardedScalarStepper:
         tiles = field // (self.world * self.nxl)       # tpr * ct
         self.fwd_field = tiles * self.nxl
         cplx = np.complex128
-        self.inv_send = _backend.zeros((self.world * 3 * self.inv_field,), cplx)
-        self.fwd_send = _backend.zeros((self.world * 2 * self.fwd_field,), cplx)
-        if self.world > 1:
-            self.inv_recv = _backend.zeros((self.world * 3 * self.inv_field,), cplx)
-            self.fwd_recv = _backend.zeros((self.world * 2 * self.fwd_field,), cplx)
+        if p2p is None:
+            p2p = self.world > 1 and _backend.is_cuda() and not os.environ.get("MLV_NO_P2P")
+        self.p2p = bool(p2p) and self.world > 1
+        self._ipc = []
+        if self.p2p:
+            # receive buffers live in peer-mapped memory; the producer kernels of every rank
+            # store straight into them over NVLink (compute + exchange in one kernel)
+            self.inv_recv_ptr = self._setup_peers(0, self.world * 3 * self.inv_field * 16)
+            self.fwd_recv_ptr = self._setup_peers(1, self.world * 2 * self.fwd_field * 16)
+            self.inv_send_ptr, self.fwd_send_ptr = self.inv_recv_ptr, self.fwd_recv_ptr
+            self._sync = _backend.zeros((1,), np.float64)
         else:
-            self.inv_recv, self.fwd_recv = self.inv_send, self.fwd_send
+            self.inv_send = _backend.zeros((self.world * 3 * self.inv_field,), cplx)
+            self.fwd_send = _backend.zeros((self.world * 2 * self.fwd_field,), cplx)
+            if self.world > 1:
+                self.inv_recv = _backend.zeros((self.world * 3 * self.inv_field,), cplx)
+                self.fwd_recv = _backend.zeros((self.world * 2 * self.fwd_field,), cplx)
+            else:
+                self.inv_recv, self.fwd_recv = self.inv_send, self.fwd_send
+            self.inv_send_ptr, self.inv_recv_ptr = self.inv_send.data_ptr(), self.inv_recv.data_ptr()
+            self.fwd_send_ptr, self.fwd_recv_ptr = self.fwd_send.data_ptr(), self.fwd_recv.data_ptr()
         self.w = [_backend.zeros((self.rows, self.nml), cplx), _backend.zeros((self.rows, self.nml), cplx)]
         self.cur = 0
         self.hist = _backend.zeros((self.order, self.rows, self.nml), cplx)
@@ -68,7 +83,40 @@ class ShardedScalarStepper:
         self._cfl_counter = 0
         self._trk_counter = 0
         self.ke_times, self.ke = [], []
+        # bytes this rank sends to its peers per step (3 inverse + 2 forward fields)
         self.bytes_exchanged_per_step = 16 * (3 * self.inv_field + 2 * self.fwd_field) * (self.world - 1)
+        self._prebuild()
+
+    def _setup_peers(self, which, nbytes):
+        """Allocate this rank's receive buffer, exchange CUDA IPC handles, open the peers'."""
+        lib, h = self.ctx.lib, self.ctx.handle
+        own = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(64)
+        _capi.check(lib, lib.mlv_p2p_alloc(h, nbytes, ctypes.byref(own), handle))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle.raw, group=self.group)
+        ptrs = (ctypes.c_void_p * self.world)()
+        for r, raw in enumerate(handles):
+            if r == self.rank:
+                ptrs[r] = own.value
+            else:
+                peer = ctypes.c_void_p()
+                _capi.check(lib, lib.mlv_p2p_open(h, ctypes.create_string_buffer(raw, 64), ctypes.byref(peer)))
+                ptrs[r] = peer.value
+                self._ipc.append((peer.value, 1))
+        self._ipc.append((own.value, 0))
+        _capi.check(lib, lib.mlv_set_peer_buffers(h, which, ptrs))
+        return own.value
+
+    def close(self):
+        """Release peer mappings (call on every rank, after a barrier)."""
+        if self._ipc:
+            _backend.synchronize()
+            if dist.is_initialized():
+                dist.barrier(group=self.group)
+            for ptr, opened in self._ipc:
+                self.ctx.lib.mlv_p2p_close(self.ctx.handle, ctypes.c_void_p(ptr), opened)
+            self._ipc = []
 
     # ------------------------------------------------------------------ state
     def load_spectral(self, w_full):
@@ -93,44 +141,60 @@ class ShardedScalarStepper:
         return full[:, : self.nm]
 
     # ------------------------------------------------------------------- step
-    def _ptr(self, t, offset_elems=0):
-        return ctypes.c_void_p(t.data_ptr() + 16 * offset_elems)
+    def _exchange(self, which):
+        """Make the blocks produced on every rank visible to their consumers."""
+        if self.world == 1:
+            return
+        if self.p2p:
+            # data already sits in the consumers' buffers: order producer and consumer kernels
+            # across ranks with a one-element all-reduce (stream-ordered, no host sync)
+            dist.all_reduce(self._sync, group=self.group)
+        elif which == 0:
+            dist.all_to_all_single(torch.view_as_real(self.inv_recv), torch.view_as_real(self.inv_send),
+                                   group=self.group)
+        else:
+            dist.all_to_all_single(torch.view_as_real(self.fwd_recv), torch.view_as_real(self.fwd_send),
+                                   group=self.group)
 
-    def _all_to_all(self, recv, send):
-        if self.world > 1:
-            dist.all_to_all_single(torch.view_as_real(recv), torch.view_as_real(send), group=self.group)
-
-    def step(self):
-        ctx, vp = self.ctx, ctypes.c_void_p
-        w_in, w_out = self.w[self.cur], self.w[1 - self.cur]
-        wp = w_in.data_ptr()
-        # 1. inverse x pass on the local columns: q = w, ux, uz (psi shared inside the kernel)
-        srcs = (vp * 3)(wp, wp, wp)
-        ops = (ctypes.c_int32 * 3)(_capi.OP_IDENT, _capi.OP_UX, _capi.OP_UZ)
-        dsts = (vp * 3)(*[self.inv_send.data_ptr() + 16 * f * self.inv_field for f in range(3)])
-        ctx.call("mlv_x_inverse", 3, srcs, ops, dsts)
-        # 2. transpose: row block h of every field goes to rank h
-        self._all_to_all(self.inv_recv, self.inv_send)
-        # 3. physical-space stage on the local rows
-        ctx.call("mlv_advect_z", self._ptr(self.inv_recv, 1 * self.inv_field),
-                 self._ptr(self.inv_recv, 2 * self.inv_field), self._ptr(self.inv_recv, 0),
-                 self._ptr(self.fwd_send, 0), self._ptr(self.fwd_send, self.fwd_field),
-                 self._ptr(self.red4))
-        # 4. transpose back: tile block h goes to rank h
-        self._all_to_all(self.fwd_recv, self.fwd_send)
-        # 5. forward x pass + RHS + AB + theta-scheme on the local columns
+    def _prebuild(self):
+        """ctypes argument blocks that do not change from step to step."""
+        vp = ctypes.c_void_p
+        self._ops = (ctypes.c_int32 * 3)(_capi.OP_IDENT, _capi.OP_UX, _capi.OP_UZ)
+        self._dsts = (vp * 3)(*[self.inv_send_ptr + 16 * f * self.inv_field for f in range(3)])
+        self._srcs = [(vp * 3)(w.data_ptr(), w.data_ptr(), w.data_ptr()) for w in self.w]
+        ir, fs = self.inv_recv_ptr, self.fwd_send_ptr
+        self._zargs = (vp(ir + 16 * self.inv_field), vp(ir + 32 * self.inv_field), vp(ir),
+                       vp(fs), vp(fs + 16 * self.fwd_field), vp(self.red4.data_ptr()))
         d = _capi.XFwd()
         d.nf, d.mode = 2, 1
-        d.src[0] = self.fwd_recv.data_ptr()
-        d.src[1] = self.fwd_recv.data_ptr() + 16 * self.fwd_field
+        d.src[0] = self.fwd_recv_ptr
+        d.src[1] = self.fwd_recv_ptr + 16 * self.fwd_field
         d.sym[0], d.sym[1] = _capi.SYM_FDX, _capi.SYM_FDZ
         d.coef[0] = d.coef[1] = -1.0
         d.lin = _capi.make_lin_terms([])
+        d.integ.ab_order, d.integ.scheme = self.order, _capi.SCHEME_SI_LAP
+        d.integ.alpha, d.integ.lcoef = self.alpha, self.coef
+        self._xfwd = d
+        self._hist_ptrs = [self.hist[k].data_ptr() for k in range(self.order)]
+
+    def step(self):
+        ctx = self.ctx
+        w_in, w_out = self.w[self.cur], self.w[1 - self.cur]
+        wp = w_in.data_ptr()
+        # 1. inverse x pass on the local columns: q = w, ux, uz (psi shared inside the kernel)
+        ctx.call("mlv_x_inverse", 3, self._srcs[self.cur], self._ops, self._dsts)
+        # 2. transpose: row block h of every field goes to rank h
+        self._exchange(0)
+        # 3. physical-space stage on the local rows
+        ctx.call("mlv_advect_z", *self._zargs)
+        # 4. transpose back: tile block h goes to rank h
+        self._exchange(1)
+        # 5. forward x pass + RHS + AB + theta-scheme on the local columns
+        d = self._xfwd
         g = d.integ
-        g.ab_order, g.scheme = self.order, _capi.SCHEME_SI_LAP
-        g.dt, g.alpha, g.lcoef = self.dt, self.alpha, self.coef
+        g.dt = self.dt
         g.q_in, g.q_out = wp, w_out.data_ptr()
-        lv = [self.hist[(self.hidx - k) % self.order].data_ptr() for k in range(self.order)]
+        lv = [self._hist_ptrs[(self.hidx - k) % self.order] for k in range(self.order)]
         g.f0, g.fm1 = lv[0], lv[1]
         if self.order == 4:
             g.fm2, g.fm3 = lv[2], lv[3]

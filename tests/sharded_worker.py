@@ -69,6 +69,7 @@ elif case == "kh":
     if rank == 0:
         print(f"SHARDED world={world} field_err={err:.2e} ke_err={ke_err:.2e} {'OK' if ok else 'FAIL'}",
               flush=True)
+st.close()
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
