@@ -219,7 +219,7 @@ struct XInvArgs {
 // the vorticity) load it from global memory once and re-read it from the
 // thread-private stash.
 template <int LOG2N, int C>
-__global__ void __launch_bounds__(C * FftCfg<LOG2N>::T, 1)
+__global__ void __launch_bounds__(C * FftCfg<LOG2N>::T, (C * FftCfg<LOG2N>::T <= 256) ? 2 : 1)
 k_xinv(const XInvArgs a) {
     typedef FftCfg<LOG2N> F;
     const int c = threadIdx.x % C, tau = threadIdx.x / C;
@@ -331,7 +331,7 @@ struct XFwdArgs {
 // (right-hand-side assembly + time integration) over the tile with C*16-byte
 // coalesced global accesses.
 template <int LOG2N, int C>
-__global__ void __launch_bounds__(C * FftCfg<LOG2N>::T, 1)
+__global__ void __launch_bounds__(C * FftCfg<LOG2N>::T, (C * FftCfg<LOG2N>::T <= 256) ? 2 : 1)
 k_xfwd(const XFwdArgs a) {
     typedef FftCfg<LOG2N> F;
     const int c = threadIdx.x % C, tau = threadIdx.x / C;
@@ -580,7 +580,7 @@ struct X1dArgs {
 };
 
 template <int LOG2N, int C>
-__global__ void __launch_bounds__(C * FftCfg<LOG2N>::T, 1)
+__global__ void __launch_bounds__(C * FftCfg<LOG2N>::T, (C * FftCfg<LOG2N>::T <= 256) ? 2 : 1)
 k_x1d_c2r(const X1dArgs a) {
     typedef FftCfg<LOG2N> F;
     const int c = threadIdx.x % C, tau = threadIdx.x / C;
@@ -618,7 +618,7 @@ k_x1d_c2r(const X1dArgs a) {
 }
 
 template <int LOG2N, int C>
-__global__ void __launch_bounds__(C * FftCfg<LOG2N>::T, 1)
+__global__ void __launch_bounds__(C * FftCfg<LOG2N>::T, (C * FftCfg<LOG2N>::T <= 256) ? 2 : 1)
 k_x1d_r2c(const X1dArgs a) {
     typedef FftCfg<LOG2N> F;
     const int c = threadIdx.x % C, tau = threadIdx.x / C;
