@@ -35,6 +35,8 @@ extern emu_dim3 blockDim;
 extern emu_dim3 gridDim;
 extern unsigned char* emu_smem_base;
 void __syncthreads();
+void emu_bar_sync(int id, int count);
+void emu_bar_arrive(int id, int count);
 #define MLV_SMEM_BASE() (emu_smem_base)
 static inline double __ldg(const double* p) { return *p; }
 static inline double2 __ldg(const double2* p) { return *p; }
@@ -88,6 +90,23 @@ MLV_HD cplx cmulc(cplx a, cplx b) {
 MLV_HD cplx cmuli(cplx a) { return mk(-a.y, a.x); }
 // multiply by -i
 MLV_HD cplx cmulni(cplx a) { return mk(a.y, -a.x); }
+
+// Named barriers (PTX bar.sync / bar.arrive): sub-CTA synchronisation and
+// producer/consumer hand-off between the two transform lines of a ping-pong CTA.
+MLV_DEV void bar_sync(int id, int count) {
+#ifdef MLV_EMU
+    emu_bar_sync(id, count);
+#else
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+#endif
+}
+MLV_DEV void bar_arrive(int id, int count) {
+#ifdef MLV_EMU
+    emu_bar_arrive(id, count);
+#else
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+#endif
+}
 
 // L2 prefetch hints (no registers, no shared memory): the kernels keep only two
 // transform lines per SM in flight, so loads that would otherwise expose a DRAM round

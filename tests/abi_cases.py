@@ -16,7 +16,7 @@ from oracle import melvin_oracle as mo
 SIZES_2D = [(16, 16), (32, 64), (64, 32), (128, 16), (256, 128), (512, 32), (16, 1024),
             (2048, 16), (16, 2048), (4096, 16), (16, 4096), (8192, 16), (16, 8192)]
 SIZES_1D = [(16, 16), (64, 13), (64, 32), (256, 24), (1024, 6)]
-SIZES_FUSED = [(32, 64), (64, 32), (256, 64)]
+SIZES_FUSED = [(32, 64), (64, 32), (256, 64), (32, 512), (16, 1024), (18 * 0 + 16, 2048)]
 
 
 def rel(a, b):

@@ -37,7 +37,25 @@ void trampoline() {
 }
 }  // namespace
 
-void __syncthreads() { swapcontext(&g_fibers[g_cur].ctx, &g_sched); }
+// ---- barriers: counting, generation based (bar.sync / bar.arrive semantics)
+namespace {
+constexpr int kMaxBar = 16;
+int g_bar_cnt[kMaxBar];
+unsigned g_bar_gen[kMaxBar];
+void yield_fiber() { swapcontext(&g_fibers[g_cur].ctx, &g_sched); }
+}  // namespace
+
+void emu_bar_arrive(int id, int count) {
+    if (++g_bar_cnt[id] == count) { g_bar_cnt[id] = 0; ++g_bar_gen[id]; }
+}
+
+void emu_bar_sync(int id, int count) {
+    const unsigned gen = g_bar_gen[id];
+    if (++g_bar_cnt[id] == count) { g_bar_cnt[id] = 0; ++g_bar_gen[id]; return; }
+    while (g_bar_gen[id] == gen) yield_fiber();
+}
+
+void __syncthreads() { emu_bar_sync(0, (int)blockDim.x); }
 
 namespace mlv {
 void emu_launch(unsigned grid, unsigned block, size_t smem, const std::function<void()>& body) {
@@ -65,6 +83,7 @@ void emu_launch(unsigned grid, unsigned block, size_t smem, const std::function<
             f.ctx.uc_link = nullptr;
             makecontext(&f.ctx, trampoline, 0);
         }
+        for (int i = 0; i < kMaxBar; ++i) { g_bar_cnt[i] = 0; g_bar_gen[i] = 0; }
         bool all_done = false;
         while (!all_done) {
             all_done = true;
