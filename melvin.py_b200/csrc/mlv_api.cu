@@ -273,7 +273,7 @@ static int launch_xfwd(mlv_ctx* c, XFwdArgs& a) {
     constexpr int C = xcols(L);
     typedef FftCfg<L> F;
     auto kfn = k_xfwd<L, C>;
-    const size_t smem = ((size_t)F::XSLOTS + (size_t)(2 * a.nn + 1)) * C * sizeof(cplx);
+    const size_t smem = (size_t)F::XSLOTS * C * sizeof(cplx);
     const unsigned grid = (unsigned)((a.nm + C - 1) / C);
     a.wave = 148 * (smem > 113 * 1024 ? 1 : 2);
     MLV_LAUNCH(kfn, grid, (unsigned)(C * F::T), smem, c->stream, a);
@@ -600,7 +600,7 @@ int mlv_x_forward(mlv_ctx* c, const mlv_xfwd* d) {
         }
         a.src[f] = (const cplx*)d->src[f]; a.sym[f] = d->sym[f]; a.coef[f] = d->coef[f];
     }
-    a.symx = c->symx; a.symz = c->symz;
+    a.symz = c->symz; a.order = c->p.fd_order; a.rdx = 1.0 / c->dx;
     a.scale = 1.0 / ((double)c->p.nx * (double)c->p.nz);      // SpectralTransformer.py:191
     a.mode = d->mode;
     a.dst = (cplx*)d->dst;

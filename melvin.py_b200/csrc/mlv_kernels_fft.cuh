@@ -311,8 +311,9 @@ struct XFwdArgs {
     const cplx* src[MLV_XMAXF];
     int sym[MLV_XMAXF];
     double coef[MLV_XMAXF];      // real coefficient per field
-    const double* symx;          // [N]  imaginary part of the x stencil symbol per FFT index
     const double* symz;          // [nm] imaginary part of the z stencil symbol
+    int order;                   // central x stencil: 2 or 4 (SpatialDifferentiator.py:76-104,130-185)
+    double rdx;                  // 1/dx
     double scale;                // 1/(nx nz)
     int wave;                    // CTAs resident at once (prefetch distance)
     int mode;                    // 0: dst = value; 1: f0 = value + lin terms, then integrate
@@ -324,12 +325,14 @@ struct XFwdArgs {
     FftTw tw;
 };
 
-// I (tile layout) x nf -> spectral: value = scale * sum_f coef_f * sym_f * FFT_x(src_f),
-// rows truncated to |n| <= nn.  The per-field results are accumulated in a
-// shared-memory tile indexed by spectral row (each (row, column) slot is owned
-// by one thread until the barrier), then a compact rolled loop runs the epilogue
-// (right-hand-side assembly + time integration) over the tile with C*16-byte
-// coalesced global accesses.
+// I (tile layout) x nf -> spectral: value = scale * FFT_x( sum_f coef_f * D_f[src_f] ), rows
+// truncated to |n| <= nn, where D_f is the identity, the multiplication by the z stencil
+// symbol i*symz[m] (a constant of the line) or the reference's periodic central x stencil
+// (SpatialDifferentiator.py:76-104 order 2, :130-185 order 4) applied along the line
+// *before* the transform -- the x stencil commutes with the z transform that produced the
+// intermediate, so all fields of a right-hand side share ONE transform per column.
+// The epilogue (right-hand-side assembly + time integration, Integrator.py:5-63) runs
+// from the registers that hold the transform output.
 template <int LOG2N, int C>
 __global__ void __launch_bounds__(C * FftCfg<LOG2N>::T, (C * FftCfg<LOG2N>::T <= 256) ? 2 : 1)
 k_xfwd(const XFwdArgs a) {
@@ -341,7 +344,6 @@ k_xfwd(const XFwdArgs a) {
     XchgFull<C> xc;
     xc.buf = reinterpret_cast<cplx*>(MLV_SMEM_BASE());
     xc.c = c;
-    cplx* tile = xc.buf + (size_t)F::XSLOTS * C;      // (2nn+1)*C entries
     const double sz = a.symz[m + a.sh.m_off];
     const int rpc = 1 << a.sh.rpc_shift;              // rows per peer block
     {   // L2 prefetch: the other fields' blocks, the next CTA's first block, and the
@@ -368,80 +370,107 @@ k_xfwd(const XFwdArgs a) {
             }
         }
     }
+    cplx v[16];
+    MLV_UNROLL
+    for (int j = 0; j < 16; ++j) v[j] = mk(0.0, 0.0);
+    const size_t blk0 = (size_t)blockIdx.x * rpc * C + c;
     for (int f = 0; f < a.nf; ++f) {
-        cplx v[16];
         const cplx* __restrict__ src = a.src[f];
-        MLV_UNROLL
-        for (int j = 0; j < 16; ++j)                       // tile layout: one contiguous block
-        {
-            const int x = tau + F::T * j;              // global row -> block of its owner
-            v[j] = src[(size_t)(x >> a.sh.rpc_shift) * a.sh.fwd_chunk +
-                       ((size_t)blockIdx.x * rpc + (x & (rpc - 1))) * C + c];
-        }
-        fft_line<LOG2N, false>(v, tau, a.tw, xc);
         const int sym = a.sym[f];
-        const double cf = a.coef[f] * a.scale;
+        const double cf = a.coef[f];
+        // element x (global row, periodic) of this thread's column: block of the row owner
+        const int rshift = a.sh.rpc_shift;
+        const size_t chunk = (size_t)a.sh.fwd_chunk;
+        auto at = [=](int x) -> cplx {
+            x &= F::N - 1;
+            return src[(size_t)(x >> rshift) * chunk + blk0 + (size_t)(x & (rpc - 1)) * C];
+        };
+        // groups of 4 points: bounds the number of loads in flight (registers)
         MLV_UNROLL
-        for (int j = 0; j < 16; ++j) {
-            const int kk = tau + F::T * j;
-            int r, n;
-            if (!xrow_of(kk, F::N, a.nn, r, n)) continue;
-            cplx t;
-            if (sym == XSYM_ONE) {
-                t = cscale(v[j], cf);
+        for (int j0 = 0; j0 < 16; j0 += 4) {
+            MLV_SCHED_FENCE();
+            const int tq = opaque_int(tau);      // address arithmetic stays inside the group
+            if (sym == XSYM_FDX) {
+                if (a.order == 2) {
+                    const double w1 = cf * (0.5 * a.rdx);
+                    MLV_UNROLL
+                    for (int j = j0; j < j0 + 4; ++j) {
+                        const int x = tq + F::T * j;
+                        const cplx p = at(x + 1), q = at(x - 1);
+                        v[j] = mk(fma(w1, p.x - q.x, v[j].x), fma(w1, p.y - q.y, v[j].y));
+                    }
+                } else {
+                    const double w1 = cf * (2.0 / 3.0 * a.rdx), w2 = cf * (-0.25 / 3.0 * a.rdx);
+                    MLV_UNROLL
+                    for (int j = j0; j < j0 + 4; ++j) {
+                        const int x = tq + F::T * j;
+                        const cplx p1 = at(x + 1), q1 = at(x - 1), p2 = at(x + 2), q2 = at(x - 2);
+                        v[j] = mk(fma(w1, p1.x - q1.x, fma(w2, p2.x - q2.x, v[j].x)),
+                                  fma(w1, p1.y - q1.y, fma(w2, p2.y - q2.y, v[j].y)));
+                    }
+                }
+            } else if (sym == XSYM_FDZ) {
+                const double s = sz * cf;                         // * (i s)
+                MLV_UNROLL
+                for (int j = j0; j < j0 + 4; ++j) {
+                    const cplx t = at(tq + F::T * j);
+                    v[j] = mk(fma(-s, t.y, v[j].x), fma(s, t.x, v[j].y));
+                }
             } else {
-                const double s = (sym == XSYM_FDX ? a.symx[kk] : sz) * cf;
-                t = mk(-s * v[j].y, s * v[j].x);          // * (i s)
+                MLV_UNROLL
+                for (int j = j0; j < j0 + 4; ++j) {
+                    const cplx t = at(tq + F::T * j);
+                    v[j] = mk(fma(cf, t.x, v[j].x), fma(cf, t.y, v[j].y));
+                }
             }
-            cplx* slot = &tile[(size_t)r * C + c];
-            if (f > 0) t = cadd(*slot, t);
-            *slot = t;
         }
     }
-    __syncthreads();
-    // ---- epilogue over the (2nn+1) x C tile: 4 elements per thread per trip, all global
-    //      loads of a trip issued before the arithmetic (memory-level parallelism)
+    MLV_SCHED_FENCE();
+    fft_line<LOG2N, false>(v, tau, a.tw, xc);
+    if (!valid) return;                                   // no barrier below
+    // ---- epilogue from registers: UN outputs per trip, all global loads of a trip issued
+    //      before the arithmetic (memory-level parallelism)
     const int rows = 2 * a.nn + 1;
-    const int m0 = blockIdx.x * C;
-    constexpr int NT = C * F::T;
-    constexpr int UN = 4;
-    for (int e0 = threadIdx.x; e0 < rows * C; e0 += UN * NT) {
-        cplx t[UN], q[UN], f1[UN], f2[UN], f3[UN];
+    const int mg = m + a.sh.m_off;
+    constexpr int UN = 2;
+    MLV_UNROLL
+    for (int j0 = 0; j0 < 16; j0 += UN) {
+        cplx q[UN], f1[UN];
         size_t idx[UN];
+        int nmode[UN];
         bool ok[UN];
+        MLV_SCHED_FENCE();
+        const int tq = opaque_int(tau);
         MLV_UNROLL
         for (int u = 0; u < UN; ++u) {
-            const int e = e0 + u * NT;
-            const int r = e / C, mm = m0 + e % C;
-            ok[u] = e < rows * C && mm < a.nm;
-            idx[u] = ok[u] ? (size_t)r * a.spitch + mm : 0;
+            int r = 0, n = 0;
+            ok[u] = xrow_of(tq + F::T * (j0 + u), F::N, a.nn, r, n);
+            nmode[u] = n;
+            idx[u] = ok[u] ? (size_t)r * a.spitch + m : (size_t)m;
         }
         if (a.mode == 1) {
             MLV_UNROLL
             for (int u = 0; u < UN; ++u) {
                 q[u] = a.integ.q_in[idx[u]];
                 f1[u] = a.integ.fm1[idx[u]];
-                if (a.integ.ab_order == 4) { f2[u] = a.integ.fm2[idx[u]]; f3[u] = a.integ.fm3[idx[u]]; }
             }
         }
-        MLV_UNROLL
-        for (int u = 0; u < UN; ++u) t[u] = ok[u] ? tile[e0 + u * NT] : mk(0.0, 0.0);
         MLV_UNROLL
         for (int u = 0; u < UN; ++u) {
             if (!ok[u]) continue;
+            const cplx t = cscale(v[j0 + u], a.scale);
+            cplx f2 = mk(0.0, 0.0), f3 = f2;
+            if (a.mode == 1 && a.integ.ab_order == 4) { f2 = a.integ.fm2[idx[u]]; f3 = a.integ.fm3[idx[u]]; }
             if (a.mode == 0) {
-                a.dst[idx[u]] = t[u];
+                a.dst[idx[u]] = t;
                 continue;
             }
-            const int e = e0 + u * NT;
-            const int r = e / C, mm = m0 + e % C;
-            const int n = r <= a.nn ? r : r - rows;
-            const int mg = mm + a.sh.m_off;
-            const cplx f0 = cadd(t[u], lin_terms_at(a.lin, idx[u], n, mg, a.k));
+            const cplx f0 = cadd(t, lin_terms_at(a.lin, idx[u], nmode[u], mg, a.k));
             a.integ.f0[idx[u]] = f0;
-            a.integ.q_out[idx[u]] = integrate_value(a.integ, f0, q[u], f1[u], f2[u], f3[u], idx[u], n, mg, a.k);
+            a.integ.q_out[idx[u]] = integrate_value(a.integ, f0, q[u], f1[u], f2, f3, idx[u], nmode[u], mg, a.k);
         }
     }
+    (void)rows;
 }
 
 // ===================================================================== z passes

@@ -1,0 +1,7 @@
+# quick GPU session: parity tests (fail fast) + kernel micro-bench + bench
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+tail -4 gpurun_out/pytest_gpu.log
+timeout 300 python tools/kbench.py > gpurun_out/kbench.log 2>&1; cat gpurun_out/kbench.log
+timeout 600 python bench.py ${BENCH_ARGS:---steps 200 --warmup 10 --no-cpu-baseline} > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?" >> gpurun_out/bench.err
+cat gpurun_out/bench.json; tail -3 gpurun_out/bench.err
