@@ -126,6 +126,29 @@ MLV_DEV void l2_prefetch_line(const void* p) {
 #endif
 }
 
+// log2 of a power of two
+MLV_DEV int log2_pow2(int x) {
+#ifdef MLV_EMU
+    return __builtin_ctz((unsigned)x);
+#else
+    return __ffs(x) - 1;
+#endif
+}
+
+// Predicated 16-byte global load: returns 0 where `pred` is false, without a branch.  A load
+// inside a divergent `if` cannot be hoisted by the compiler, so a run of conditional loads
+// becomes a chain of dependent memory round trips; predicated loads all issue back to back.
+MLV_DEV cplx ldg_pred(const cplx* p, bool pred) {
+#ifdef MLV_EMU
+    return pred ? *p : mk(0.0, 0.0);
+#else
+    double x = 0.0, y = 0.0;
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %3, 0;\n\t@q ld.global.v2.f64 {%0, %1}, [%2];\n\t}"
+                 : "+d"(x), "+d"(y) : "l"(p), "r"((int)pred));
+    return mk(x, y);
+#endif
+}
+
 // Reciprocal to ~1 ulp without the branchy IEEE division sequence: 20-bit hardware
 // seed + two Newton steps (operands here are O(1)..O(1e9), never denormal or zero).
 MLV_DEV double fast_rcp(double x) {

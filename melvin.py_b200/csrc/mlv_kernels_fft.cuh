@@ -73,6 +73,14 @@ MLV_DEV cplx spectral_op(int op, cplx s, int n, int m, const SpecConsts& k) {
     /* XOP_UZ */ { const double c = (k.kx0 * n) * r; return mk(c * s.y, -c * s.x); }
 }
 
+// 2/3-rule invariant used for static pruning: a transform of length N keeps at most
+// (N-1)/3 modes per side (Parameters.py:67-70), and thread tau owns the FFT indices
+// tau + (N/16) j.  Indices with j = 6..9 lie in [6N/16, 10N/16) and are therefore ALWAYS
+// truncated; retained low modes have j <= 5, retained high (negative) modes j >= 10.  Loops
+// skip those j statically, so the zeros also fold through the first butterflies of the
+// inverse transforms and the unused outputs of the forward transforms are never computed.
+#define MLV_MID(j) ((j) >= 6 && (j) <= 9)
+
 // FFT index k (0..N-1) -> spectral row r and signed mode n; false if truncated.
 MLV_DEV bool xrow_of(int k, int N, int nn, int& r, int& n) {
     if (k <= nn) { r = k; n = k; return true; }
@@ -250,17 +258,29 @@ k_xinv(const XInvArgs a) {
         const bool keep = f + 1 < a.nf && a.src[f + 1] == a.src[f];
         const int opn = keep ? a.op[f + 1] : -1;
         const bool next_wants_psi = (opn == XOP_PSI || opn == XOP_UX || opn == XOP_UZ);
-        MLV_UNROLL
-        for (int j = 0; j < 16; ++j) {
-            const int kk = tau + F::T * j;
-            int r, n;
-            v[j] = mk(0.0, 0.0);
-            if (xrow_of(kk, F::N, a.nn, r, n))
-                v[j] = reuse ? stash[(size_t)r * C + c] : src[(size_t)r * a.spitch + m];
+        // branch-free loads (all issued before the first is consumed); truncated rows read 0
+        if (reuse) {
+            MLV_UNROLL
+            for (int j = 0; j < 16; ++j) {
+                if (MLV_MID(j)) { v[j] = mk(0.0, 0.0); continue; }
+                int r = 0, n = 0;
+                const bool ok = xrow_of(tau + F::T * j, F::N, a.nn, r, n);
+                const cplx t = stash[(size_t)(ok ? r : 0) * C + c];
+                v[j] = ok ? t : mk(0.0, 0.0);
+            }
+        } else {
+            MLV_UNROLL
+            for (int j = 0; j < 16; ++j) {
+                if (MLV_MID(j)) { v[j] = mk(0.0, 0.0); continue; }
+                int r = 0, n = 0;
+                const bool ok = xrow_of(tau + F::T * j, F::N, a.nn, r, n);
+                v[j] = ldg_pred(src + (size_t)(ok ? r : 0) * a.spitch + m, ok);
+            }
         }
         if (keep && !reuse && !(wants_psi && next_wants_psi)) {      // park the raw column
             MLV_UNROLL
             for (int j = 0; j < 16; ++j) {
+                if (MLV_MID(j)) continue;
                 const int kk = tau + F::T * j;
                 int r, n;
                 if (xrow_of(kk, F::N, a.nn, r, n)) stash[(size_t)r * C + c] = v[j];
@@ -271,6 +291,7 @@ k_xinv(const XInvArgs a) {
             const bool park_psi = keep && next_wants_psi && !have_psi;
             MLV_UNROLL
             for (int j = 0; j < 16; ++j) {
+                if (MLV_MID(j)) continue;
                 const int kk = tau + F::T * j;
                 int r, n;
                 if (!xrow_of(kk, F::N, a.nn, r, n)) continue;
@@ -288,6 +309,7 @@ k_xinv(const XInvArgs a) {
         } else if (op != XOP_IDENT) {
             MLV_UNROLL
             for (int j = 0; j < 16; ++j) {
+                if (MLV_MID(j)) continue;
                 const int kk = tau + F::T * j;
                 int r, n;
                 if (xrow_of(kk, F::N, a.nn, r, n)) v[j] = spectral_op(op, v[j], n, mg, a.k);
@@ -435,6 +457,7 @@ k_xfwd(const XFwdArgs a) {
     constexpr int UN = 2;
     MLV_UNROLL
     for (int j0 = 0; j0 < 16; j0 += UN) {
+        if (MLV_MID(j0) && MLV_MID(j0 + UN - 1)) continue;       // always truncated
         cplx q[UN], f1[UN];
         size_t idx[UN];
         int nmode[UN];
@@ -479,24 +502,30 @@ k_xfwd(const XFwdArgs a) {
 //   idx < nm        : A[idx] + i B[idx]            (idx = 0: Re A + i Re B)
 //   idx > N - nm    : conj(A[N-idx]) + i conj(B[N-idx])
 //   otherwise       : 0   (2/3-rule truncation)
-template <int LOG2N>
-MLV_DEV void zpair_load_line(cplx (&v)[16], const cplx* __restrict__ rowA,
-                             const cplx* __restrict__ rowB, int tau_, int nm, const Shard& sh) {
+template <int LOG2N, bool SHARDED>
+MLV_DEV void zpair_load_line_(cplx (&v)[16], const cplx* __restrict__ rowA,
+                              const cplx* __restrict__ rowB, int tau_, int nm, const Shard& sh) {
     typedef FftCfg<LOG2N> F;
     const int tau = opaque_int(tau_);
+    // branch-free: the loads are all issued before the first one is consumed
     MLV_UNROLL
     for (int j = 0; j < 16; ++j) {
+        if (MLV_MID(j)) { v[j] = mk(0.0, 0.0); continue; }
         const int idx = tau + F::T * j;
         const bool lo = idx < nm, hi = idx > F::N - nm;
-        v[j] = mk(0.0, 0.0);
-        if (lo || hi) {
-            const int mm = lo ? idx : F::N - idx;
-            const size_t off = inv_col_off(mm, sh);
-            const cplx A = rowA[off], B = rowB[off];
-            v[j] = lo ? (idx == 0 ? mk(A.x, B.x) : mk(A.x - B.y, A.y + B.x))
-                      : mk(A.x + B.y, B.x - A.y);
-        }
+        const int mm = lo ? idx : (hi ? F::N - idx : 0);
+        const size_t off = SHARDED ? inv_col_off(mm, sh) : (size_t)mm;
+        const cplx A = ldg_pred(rowA + off, lo || hi), B = ldg_pred(rowB + off, lo || hi);
+        const double s = lo ? 1.0 : -1.0;            // hi: conj(A) + i conj(B)
+        const double ay = idx == 0 ? 0.0 : A.y, by = idx == 0 ? 0.0 : B.y;   // F4: Im of bin 0 dropped
+        v[j] = mk(A.x - s * by, s * ay + B.x);
     }
+}
+template <int LOG2N>
+MLV_DEV void zpair_load_line(cplx (&v)[16], const cplx* __restrict__ rowA,
+                             const cplx* __restrict__ rowB, int tau, int nm, const Shard& sh) {
+    if (sh.inv_chunk == 0) zpair_load_line_<LOG2N, false>(v, rowA, rowB, tau, nm, sh);   // one block per row
+    else zpair_load_line_<LOG2N, true>(v, rowA, rowB, tau, nm, sh);
 }
 
 // After a forward transform of z = a + ib every thread holds Zf[tau + T j].
@@ -507,7 +536,7 @@ template <int LOG2N>
 MLV_DEV void zpair_publish(const cplx (&v)[16], int tau, int nm, cplx* pbuf) {
     typedef FftCfg<LOG2N> F;
     MLV_UNROLL
-    for (int j = 0; j < 16; ++j) {
+    for (int j = 10; j < 16; ++j) {                      // retained high modes: j >= 10
         const int kk = tau + F::T * j;
         if (kk > F::N - nm) pbuf[F::N - kk] = v[j];
     }
@@ -580,7 +609,7 @@ k_z_r2c(const ZArgs a) {
     __syncthreads();
     if (valid) {
         MLV_UNROLL
-        for (int j = 0; j < 16; ++j) {
+        for (int j = 0; j < 6; ++j) {                        // retained low modes: j <= 5
             const int kk = tau + F::T * j;
             if (kk < a.nm) {
                 const cplx P = (kk == 0) ? v[j] : pbuf[kk];
@@ -623,7 +652,7 @@ k_x1d_c2r(const X1dArgs a) {
     for (int j = 0; j < 16; ++j) {
         const int kk = tau + F::T * j;
         v[j] = mk(0.0, 0.0);
-        if (!valid) continue;
+        if (!valid || MLV_MID(j)) continue;
         if (kk < a.nn) {
             const cplx A = a.S[(size_t)kk * a.nz + z0];
             const cplx B = has2 ? a.S[(size_t)kk * a.nz + z0 + 1] : mk(0.0, 0.0);
@@ -668,14 +697,14 @@ k_x1d_r2c(const X1dArgs a) {
     fft_line<LOG2N, false>(v, tau, a.tw, xc);
     __syncthreads();
     MLV_UNROLL
-    for (int j = 0; j < 16; ++j) {
+    for (int j = 10; j < 16; ++j) {
         const int kk = tau + F::T * j;
         if (kk > F::N - a.nn) xc.buf[(size_t)(F::N - kk) * C + c] = v[j];
     }
     __syncthreads();
     if (valid) {
         MLV_UNROLL
-        for (int j = 0; j < 16; ++j) {
+        for (int j = 0; j < 6; ++j) {
             const int kk = tau + F::T * j;
             if (kk < a.nn) {
                 const cplx P = (kk == 0) ? v[j] : xc.buf[(size_t)kk * C + c];
@@ -731,6 +760,8 @@ k_z_advect(const ZAdvArgs a) {
     double* rbuf = reinterpret_cast<double*>(base + (size_t)LPC * F::XSLOTS * sizeof(double) +
                                              (size_t)LPC * F::N * sizeof(cplx));
     const size_t rowoff = (size_t)(2 * rp) * a.ipitch;
+    const int cts = log2_pow2(a.ct);                 // tile width is a power of two
+    const bool sharded = a.sh.fwd_chunk != 0;
 
     // announce the rows of the two velocity components (needed one and two transforms
     // from now) and the scalar rows of the CTA that will follow this one on the SM
@@ -781,17 +812,27 @@ k_z_advect(const ZAdvArgs a) {
         if (valid) {
             const size_t foff = (size_t)a.outoff[pass];
             MLV_UNROLL
-            for (int j = 0; j < 16; ++j) {
-                const int kk = tau + F::T * j;
-                if (kk < a.nm) {
-                    const cplx P = (kk == 0) ? v[j] : pbuf[kk];
-                    cplx A, B;
-                    zpair_unpack(v[j], P, A, B);
-                    const int t = kk / a.ct;
-                    const int h = t / a.sh.tpr, tl = t - h * a.sh.tpr;     // tile owner
-                    cplx* o = a.out.blk[h] + foff + ((size_t)tl * a.nx + 2 * rp) * a.ct + (kk % a.ct);
-                    o[0] = A;
-                    o[a.ct] = B;                               // row 2rp+1
+            for (int j0 = 0; j0 < 6; j0 += 3) {            // retained low modes: j <= 5
+                cplx P[3];
+                MLV_UNROLL
+                for (int u = 0; u < 3; ++u) {              // partner values: unconditional reads
+                    const int kk = tau + F::T * (j0 + u);
+                    P[u] = pbuf[kk < a.nm ? kk : 0];
+                }
+                MLV_UNROLL
+                for (int u = 0; u < 3; ++u) {
+                    const int j = j0 + u;
+                    const int kk = tau + F::T * j;
+                    if (kk < a.nm) {
+                        cplx A, B;
+                        zpair_unpack(v[j], (kk == 0) ? v[j] : P[u], A, B);
+                        const int t = kk >> cts;
+                        int h = 0, tl = t;                                       // tile owner
+                        if (sharded) { h = t / a.sh.tpr; tl = t - h * a.sh.tpr; }
+                        cplx* o = a.out.blk[h] + foff + ((size_t)tl * a.nx + 2 * rp) * a.ct + (kk & (a.ct - 1));
+                        o[0] = A;
+                        o[a.ct] = B;                               // row 2rp+1
+                    }
                 }
             }
         }
