@@ -145,6 +145,10 @@ int mlv_create(const mlv_params* p, mlv_ctx** ctx);
 int mlv_destroy(mlv_ctx* ctx);
 int mlv_set_stream(mlv_ctx* ctx, void* cuda_stream);
 int mlv_get_info(const mlv_ctx* ctx, mlv_info* out);
+/* bit 0: x passes run as two half-length transforms, bit 1: z stage runs on single real
+ * rows (lines of 16384 points, which one SM cannot hold in registers; no reference
+ * counterpart -- the reference calls numpy.fft, SpectralTransformer.py:132,191) */
+int mlv_long_lines(const mlv_ctx* ctx);
 /* Slab decomposition over `nranks` processes (one per GPU; fully spectral mode).  The
  * reference is single-device, so this has no counterpart there.  Afterwards
  * every call works on local slabs: spectral arrays are (2nn+1, nml) column slabs

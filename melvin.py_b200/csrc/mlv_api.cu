@@ -2,6 +2,7 @@
 #include "../../include/melvin_b200.h"
 
 #include "mlv_kernels_pw.cuh"
+#include "mlv_kernels_split.cuh"
 #include "mlv_rt.h"
 
 #include <stdarg.h>
@@ -33,6 +34,12 @@ struct mlv_ctx {
     mlv_params p;
     int nn, nm, spec_rows, spec_cols, ipitch, ct;
     int log2nx, log2nz;
+    // lines too long for the register transform (mlv_kernels_split.cuh): x passes in two
+    // half-length transforms, z stage on single real rows; plan lengths are log2 - 1 then
+    bool xsplit = false, zreal = false;
+    int planlx = 0, planlz = 0;
+    mlv::cplx* tws_x = nullptr;   // e^{-2 pi i k/nx}, k < nx/2
+    mlv::cplx* tws_z = nullptr;   // e^{-2 pi i k/nz}, k < nz/2
     double dx, dz;
     mlv::SpecConsts k;
     mlv::Plan planx, planz;
@@ -109,6 +116,18 @@ static int make_plan(Plan& plan, int log2n, stream_t s) {
     return 0;
 }
 
+// e^{-2 pi i k/nfull}, k < nfull/2: the twiddles of the radix-2 step around the register transform
+static int make_split_table(cplx** dev, int nfull, stream_t s) {
+    std::vector<cplx> host((size_t)nfull / 2);
+    for (int k = 0; k < nfull / 2; ++k) {
+        const long double ang = -2.0L * 3.14159265358979323846264338327950288L * (long double)k / (long double)nfull;
+        host[k] = mk((double)cosl(ang), (double)sinl(ang));
+    }
+    int rc = rt_malloc((void**)dev, host.size() * sizeof(cplx));
+    if (!rc) rc = rt_h2d(*dev, host.data(), host.size() * sizeof(cplx), s);
+    return rc;
+}
+
 // imaginary part of the Fourier symbol of the reference's central stencils
 // (SpatialDifferentiator.py:76-104 order 2, :130-185 order 4); SURVEY F2.
 static double stencil_symbol(int order, long long mode, long long npts, double h) {
@@ -139,6 +158,16 @@ static constexpr int zlines(int log2n) {         // row pairs per z-pass CTA
         case 12: MACRO(12); break;                                                        \
         case 13: MACRO(13); break;                                                        \
         default: set_error("unsupported transform length 2^%d", (L)); return MLV_ERR_UNSUPPORTED; \
+    }
+
+// the split kernels are instantiated for the production length (2 x 8192) and two small
+// lengths that the tests force through them (MLV_FORCE_SPLIT)
+#define MLV_SWITCH_SPLIT(L, MACRO)                                                        \
+    switch (L) {                                                                          \
+        case 6: MACRO(6); break;                                                          \
+        case 7: MACRO(7); break;                                                          \
+        case 13: MACRO(13); break;                                                        \
+        default: set_error("split transforms: unsupported half length 2^%d", (L)); return MLV_ERR_UNSUPPORTED; \
     }
 
 static unsigned grid1d(size_t total, unsigned block = 256) {
@@ -269,10 +298,63 @@ static int launch_xinv(mlv_ctx* c, XInvArgs& a) {
 }
 
 template <int L>
+static int launch_xinv_split(mlv_ctx* c, XInvArgs& a) {
+    constexpr int C = xcols(L);
+    typedef FftCfg<L> F;
+    auto kfn = k_xinv_split<L, C>;
+    const size_t smem = (size_t)F::XSLOTS * C * sizeof(cplx);
+    const unsigned grid = (unsigned)((a.nm + C - 1) / C);
+    a.wave = 148;
+    MLV_LAUNCH(kfn, grid, (unsigned)(C * F::T), smem, c->stream, a);
+    return 0;
+}
+
+template <int L>
+static int launch_xfwd_split(mlv_ctx* c, XFwdArgs& a) {
+    constexpr int C = xcols(L);
+    typedef FftCfg<L> F;
+    auto kfn = k_xfwd<L, C, 2>;
+    const size_t smem = (size_t)F::XSLOTS * C * sizeof(cplx);
+    const unsigned grid = (unsigned)((a.nm + C - 1) / C);
+    a.wave = 148 * (smem > 113 * 1024 ? 1 : 2);
+    MLV_LAUNCH(kfn, grid, (unsigned)(C * F::T), smem, c->stream, a);
+    return 0;
+}
+
+template <int L>
+static int launch_zreal(mlv_ctx* c, ZRealArgs& a, bool inverse) {
+    typedef FftCfg<L> F;
+    const size_t smem = (size_t)F::XSLOTS * sizeof(double);
+    if (inverse) {
+        auto kfn = k_zr_c2r<L>;
+        MLV_LAUNCH(kfn, (unsigned)a.nx, (unsigned)F::T, smem, c->stream, a);
+    } else {
+        auto kfn = k_zr_r2c<L>;
+        MLV_LAUNCH(kfn, (unsigned)a.nx, (unsigned)F::T, smem, c->stream, a);
+    }
+    return 0;
+}
+
+template <int L>
+static int launch_zadv_real(mlv_ctx* c, ZAdvArgs& a, unsigned& grid_out) {
+    typedef FftCfg<L> F;
+    auto kfn = k_zr_advect<L>;
+    const size_t smem = F::XSLOTS * sizeof(double) + (size_t)F::N * sizeof(cplx) + (size_t)4 * F::T * sizeof(double);
+    const unsigned grid = (unsigned)a.nx;
+    grid_out = grid;
+    int rc = ensure_red(c, (size_t)grid * 4);
+    if (rc) return rc;
+    a.red = c->red;
+    a.wave = 148;
+    MLV_LAUNCH(kfn, grid, (unsigned)F::T, smem, c->stream, a);
+    return 0;
+}
+
+template <int L>
 static int launch_xfwd(mlv_ctx* c, XFwdArgs& a) {
     constexpr int C = xcols(L);
     typedef FftCfg<L> F;
-    auto kfn = k_xfwd<L, C>;
+    auto kfn = k_xfwd<L, C, 1>;
     const size_t smem = (size_t)F::XSLOTS * C * sizeof(cplx);
     const unsigned grid = (unsigned)((a.nm + C - 1) / C);
     a.wave = 148 * (smem > 113 * 1024 ? 1 : 2);
@@ -365,25 +447,35 @@ int mlv_create(const mlv_params* p, mlv_ctx** out) {
     }
     const int lx = ilog2_exact(p->nx);
     const int lz = ilog2_exact(p->nz);
-    if (lx < 4 || lx > 13) {
-        set_error("mlv_create: nx=%d unsupported (power of two, 16..8192)", p->nx);
+    const int lxmax = p->fdm_z ? 13 : 14;
+    if (lx < 4 || lx > lxmax) {
+        set_error("mlv_create: nx=%d unsupported (power of two, 16..%d)", p->nx, 1 << lxmax);
         return MLV_ERR_UNSUPPORTED;
     }
-    if (!p->fdm_z && (lz < 4 || lz > 13)) {
-        set_error("mlv_create: nz=%d unsupported (power of two, 16..8192)", p->nz);
+    if (!p->fdm_z && (lz < 4 || lz > 14)) {
+        set_error("mlv_create: nz=%d unsupported (power of two, 16..16384)", p->nz);
         return MLV_ERR_UNSUPPORTED;
     }
+    // test hook: MLV_FORCE_SPLIT (bit 0: x passes, bit 1: z stage) sends small grids through
+    // the long-line kernels (instantiated for half lengths 64, 128 and 8192)
+    int force = 0;
+    if (const char* e = getenv("MLV_FORCE_SPLIT")) force = atoi(e);
+    const bool xsplit = !p->fdm_z && (lx > 13 || ((force & 1) && (lx == 7 || lx == 8)));
+    const bool zreal = !p->fdm_z && (lz > 13 || ((force & 2) && (lz == 7 || lz == 8)));
     if (p->fdm_z && p->nz < 5) { set_error("mlv_create: nz too small"); return MLV_ERR_INVALID; }
     mlv_ctx* c = new (std::nothrow) mlv_ctx();
     if (!c) { set_error("out of host memory"); return MLV_ERR_NOMEM; }
     c->p = *p;
     c->log2nx = lx;
     c->log2nz = lz;
+    c->xsplit = xsplit; c->zreal = zreal;
+    c->planlx = lx - (xsplit ? 1 : 0);
+    c->planlz = lz - (zreal ? 1 : 0);
     c->nn = (p->nx - 1) / 3;                       // Parameters.py:67-70
     c->nm = p->fdm_z ? -1 : (p->nz - 1) / 3;
     c->spec_rows = p->fdm_z ? c->nn : 2 * c->nn + 1;
     c->spec_cols = p->fdm_z ? p->nz : c->nm;
-    c->ct = xcols(lx);                               // columns per x-pass CTA = tile width
+    c->ct = xcols(c->planlx);                        // columns per x-pass CTA = tile width
     {   // pitch: multiple of the tile width (and even: 32-byte aligned column pairs)
         const int q = c->ct > 2 ? c->ct : 2;
         c->ipitch = p->fdm_z ? 0 : ((c->nm + q - 1) / q) * q;
@@ -391,8 +483,10 @@ int mlv_create(const mlv_params* p, mlv_ctx** out) {
     c->dx = p->lx / p->nx;
     c->dz = p->lz / p->nz;
     c->k.kx0 = p->kx0; c->k.kz0 = p->kz0; c->k.d2x = p->d2x; c->k.d2z = p->d2z;
-    int rc = make_plan(c->planx, lx, c->stream);
-    if (!rc && !p->fdm_z) rc = make_plan(c->planz, lz, c->stream);
+    int rc = make_plan(c->planx, c->planlx, c->stream);
+    if (!rc && !p->fdm_z) rc = make_plan(c->planz, c->planlz, c->stream);
+    if (!rc && xsplit) rc = make_split_table(&c->tws_x, p->nx, c->stream);
+    if (!rc && zreal) rc = make_split_table(&c->tws_z, p->nz, c->stream);
     if (!rc) {
         std::vector<double> sx(p->nx);
         for (int kk = 0; kk < p->nx; ++kk) {
@@ -443,6 +537,8 @@ int mlv_destroy(mlv_ctx* c) {
     if (!c) return MLV_OK;
     if (c->planx.dev) rt_free(c->planx.dev);
     if (c->planz.dev) rt_free(c->planz.dev);
+    if (c->tws_x) rt_free(c->tws_x);
+    if (c->tws_z) rt_free(c->tws_z);
     if (c->symx) rt_free(c->symx);
     if (c->symz) rt_free(c->symz);
     if (c->tri_cp) rt_free(c->tri_cp);
@@ -515,6 +611,10 @@ int mlv_set_peer_buffers(mlv_ctx* c, int which, void* const* bufs) {
     return MLV_OK;
 }
 
+int mlv_long_lines(const mlv_ctx* c) {
+    return c ? ((c->xsplit ? 1 : 0) | (c->zreal ? 2 : 0)) : 0;
+}
+
 int mlv_get_info(const mlv_ctx* c, mlv_info* o) {
     if (!c || !o) { set_error("null argument"); return MLV_ERR_INVALID; }
     o->nn = c->nn; o->nm = c->nm;
@@ -554,7 +654,12 @@ int mlv_x_inverse(mlv_ctx* c, int nf, const void* const* spec, const int32_t* op
             a.out.blk[h] = (cplx*)idst[0] + (size_t)h * c->sh.inv_chunk;
         }
     }
-    a.k = c->k; a.tw = c->planx.tw;
+    a.k = c->k; a.tw = c->planx.tw; a.tws = c->tws_x;
+    if (c->xsplit) {
+#define MLV_GO(L) return launch_xinv_split<L>(c, a)
+        MLV_SWITCH_SPLIT(c->planlx, MLV_GO)
+#undef MLV_GO
+    }
 #define MLV_GO(L) return launch_xinv<L>(c, a)
     MLV_SWITCH_LOG2(c->log2nx, MLV_GO)
 #undef MLV_GO
@@ -564,6 +669,14 @@ int mlv_x_inverse(mlv_ctx* c, int nf, const void* const* spec, const int32_t* op
 int mlv_z_inverse(mlv_ctx* c, const void* isrc, double* phys) {
     if (!c || !isrc || !phys) { set_error("mlv_z_inverse: null argument"); return MLV_ERR_INVALID; }
     if (int rc = need_2d(c, "mlv_z_inverse")) return rc;
+    if (c->zreal) {
+        ZRealArgs r{};
+        r.nx = c->nxl; r.nm = c->nm; r.ipitch = c->nml; r.ct = c->ct; r.sh = c->sh;
+        r.I = (const cplx*)isrc; r.P = phys; r.tw = c->planz.tw; r.tws = c->tws_z;
+#define MLV_GO(L) return launch_zreal<L>(c, r, true)
+        MLV_SWITCH_SPLIT(c->planlz, MLV_GO)
+#undef MLV_GO
+    }
     ZArgs a{};
     a.nx = c->nxl; a.nm = c->nm; a.ipitch = c->nml; a.ct = c->ct; a.sh = c->sh;
     a.I = (const cplx*)isrc; a.P = phys; a.tw = c->planz.tw;
@@ -576,6 +689,14 @@ int mlv_z_inverse(mlv_ctx* c, const void* isrc, double* phys) {
 int mlv_z_forward(mlv_ctx* c, const double* phys, void* idst) {
     if (!c || !idst || !phys) { set_error("mlv_z_forward: null argument"); return MLV_ERR_INVALID; }
     if (int rc = need_2d(c, "mlv_z_forward")) return rc;
+    if (c->zreal) {
+        ZRealArgs r{};
+        r.nx = c->nxl; r.nm = c->nm; r.ipitch = c->nml; r.ct = c->ct; r.sh = c->sh;
+        r.Pin = phys; r.Iout = (cplx*)idst; r.tw = c->planz.tw; r.tws = c->tws_z;
+#define MLV_GO(L) return launch_zreal<L>(c, r, false)
+        MLV_SWITCH_SPLIT(c->planlz, MLV_GO)
+#undef MLV_GO
+    }
     ZArgs a{};
     a.nx = c->nxl; a.nm = c->nm; a.ipitch = c->nml; a.ct = c->ct; a.sh = c->sh;
     a.Pin = phys; a.Iout = (cplx*)idst; a.tw = c->planz.tw;
@@ -617,7 +738,12 @@ int mlv_x_forward(mlv_ctx* c, const mlv_xfwd* d) {
         set_error("mlv_x_forward: bad mode %d", d->mode);
         return MLV_ERR_INVALID;
     }
-    a.k = c->k; a.tw = c->planx.tw;
+    a.k = c->k; a.tw = c->planx.tw; a.tws = c->tws_x;
+    if (c->xsplit) {
+#define MLV_GO(L) return launch_xfwd_split<L>(c, a)
+        MLV_SWITCH_SPLIT(c->planlx, MLV_GO)
+#undef MLV_GO
+    }
 #define MLV_GO(L) return launch_xfwd<L>(c, a)
     MLV_SWITCH_LOG2(c->log2nx, MLV_GO)
 #undef MLV_GO
@@ -682,9 +808,16 @@ int mlv_advect_z(mlv_ctx* c, const void* iux, const void* iuz, const void* iq, v
     }
     unsigned grid = 0;
     int rc = 0;
-#define MLV_GO(L) rc = launch_zadv<L>(c, a, grid)
-    MLV_SWITCH_LOG2(c->log2nz, MLV_GO)
+    a.tws = c->tws_z;
+    if (c->zreal) {
+#define MLV_GO(L) rc = launch_zadv_real<L>(c, a, grid)
+        MLV_SWITCH_SPLIT(c->planlz, MLV_GO)
 #undef MLV_GO
+    } else {
+#define MLV_GO(L) rc = launch_zadv<L>(c, a, grid)
+        MLV_SWITCH_LOG2(c->log2nz, MLV_GO)
+#undef MLV_GO
+    }
     if (rc) return rc;
     if (red4) {
         auto kfn = k_reduce_final4;

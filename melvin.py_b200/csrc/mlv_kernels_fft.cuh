@@ -219,6 +219,7 @@ struct XInvArgs {
     long long dstoff[MLV_XMAXF];
     SpecConsts k;
     FftTw tw;
+    const cplx* tws;             // split lines: e^{-2 pi i k/nx}, k < nx/2
 };
 
 // spectral (2nn+1, nm) -> I (nx, ipitch); nf fields, each with its own prologue.
@@ -345,6 +346,7 @@ struct XFwdArgs {
     Shard sh;                    // nm = local valid columns; symbols use m + sh.m_off
     SpecConsts k;
     FftTw tw;
+    const cplx* tws;             // SPLIT = 2: e^{-2 pi i p/nx}, p < nx/2
 };
 
 // I (tile layout) x nf -> spectral: value = scale * FFT_x( sum_f coef_f * D_f[src_f] ), rows
@@ -355,10 +357,13 @@ struct XFwdArgs {
 // intermediate, so all fields of a right-hand side share ONE transform per column.
 // The epilogue (right-hand-side assembly + time integration, Integrator.py:5-63) runs
 // from the registers that hold the transform output.
-template <int LOG2N, int C>
+// SPLIT = 2: lines of 2N points through two N-point transforms (mlv_kernels_split.cuh):
+//   X[2q+s] = DFT_N( (x[p] + (-1)^s x[p+N]) e^{-2 pi i s p/2N} )[q],  s = 0, 1.
+template <int LOG2N, int C, int SPLIT>
 __global__ void __launch_bounds__(C * FftCfg<LOG2N>::T, (C * FftCfg<LOG2N>::T <= 256) ? 2 : 1)
 k_xfwd(const XFwdArgs a) {
     typedef FftCfg<LOG2N> F;
+    constexpr int NF = F::N * SPLIT;                  // line length
     const int c = threadIdx.x % C, tau = threadIdx.x / C;
     const int mreal = blockIdx.x * C + c;
     const bool valid = mreal < a.nm;
@@ -371,16 +376,16 @@ k_xfwd(const XFwdArgs a) {
     {   // L2 prefetch: the other fields' blocks, the next CTA's first block, and the
         // state / history columns the epilogue will read
         constexpr unsigned CHUNK = 16384;
-        constexpr unsigned BLOCK = (unsigned)F::N * C * (unsigned)sizeof(cplx);
+        constexpr unsigned BLOCK = (unsigned)NF * C * (unsigned)sizeof(cplx);
         constexpr int NCH = (int)(BLOCK / CHUNK) > 0 ? (int)(BLOCK / CHUNK) : 1;
         const int t = threadIdx.x;
-        if (rpc == F::N && t < NCH * a.nf) {
+        if (rpc == NF && t < NCH * a.nf) {
             const int f = t / NCH, ch = t % NCH;
             const unsigned bytes = BLOCK < CHUNK ? BLOCK : CHUNK;
             if (f > 0) {
-                l2_prefetch_bulk(reinterpret_cast<const char*>(a.src[f] + (size_t)blockIdx.x * F::N * C) + (size_t)ch * CHUNK, bytes);
+                l2_prefetch_bulk(reinterpret_cast<const char*>(a.src[f] + (size_t)blockIdx.x * NF * C) + (size_t)ch * CHUNK, bytes);
             } else if ((int)(blockIdx.x + a.wave) < (int)gridDim.x) {
-                l2_prefetch_bulk(reinterpret_cast<const char*>(a.src[0] + (size_t)(blockIdx.x + a.wave) * F::N * C) + (size_t)ch * CHUNK, bytes);
+                l2_prefetch_bulk(reinterpret_cast<const char*>(a.src[0] + (size_t)(blockIdx.x + a.wave) * NF * C) + (size_t)ch * CHUNK, bytes);
             }
         }
         if (a.mode == 1) {
@@ -392,108 +397,123 @@ k_xfwd(const XFwdArgs a) {
             }
         }
     }
-    cplx v[16];
-    MLV_UNROLL
-    for (int j = 0; j < 16; ++j) v[j] = mk(0.0, 0.0);
     const size_t blk0 = (size_t)blockIdx.x * rpc * C + c;
-    for (int f = 0; f < a.nf; ++f) {
-        const cplx* __restrict__ src = a.src[f];
-        const int sym = a.sym[f];
-        const double cf = a.coef[f];
-        // element x (global row, periodic) of this thread's column: block of the row owner
-        const int rshift = a.sh.rpc_shift;
-        const size_t chunk = (size_t)a.sh.fwd_chunk;
-        auto at = [=](int x) -> cplx {
-            x &= F::N - 1;
-            return src[(size_t)(x >> rshift) * chunk + blk0 + (size_t)(x & (rpc - 1)) * C];
-        };
-        // groups of 4 points: bounds the number of loads in flight (registers)
+    const int mg = m + a.sh.m_off;
+    for (int s = 0; s < SPLIT; ++s) {
+        cplx v[16];
         MLV_UNROLL
-        for (int j0 = 0; j0 < 16; j0 += 4) {
-            MLV_SCHED_FENCE();
-            const int tq = opaque_int(tau);      // address arithmetic stays inside the group
-            if (sym == XSYM_FDX) {
-                if (a.order == 2) {
-                    const double w1 = cf * (0.5 * a.rdx);
-                    MLV_UNROLL
-                    for (int j = j0; j < j0 + 4; ++j) {
-                        const int x = tq + F::T * j;
-                        const cplx p = at(x + 1), q = at(x - 1);
-                        v[j] = mk(fma(w1, p.x - q.x, v[j].x), fma(w1, p.y - q.y, v[j].y));
+        for (int j = 0; j < 16; ++j) v[j] = mk(0.0, 0.0);
+        const double sg = s ? -1.0 : 1.0;
+        for (int f = 0; f < a.nf; ++f) {
+            const cplx* __restrict__ src = a.src[f];
+            const int sym = a.sym[f];
+            const double cf = a.coef[f];
+            // element x (global row, periodic) of this thread's column: block of the row owner
+            const int rshift = a.sh.rpc_shift;
+            const size_t chunk = (size_t)a.sh.fwd_chunk;
+            auto at = [=](int x) -> cplx {
+                x &= NF - 1;
+                return src[(size_t)(x >> rshift) * chunk + blk0 + (size_t)(x & (rpc - 1)) * C];
+            };
+            const double w1 = a.order == 2 ? 0.5 * a.rdx : 2.0 / 3.0 * a.rdx;
+            const double w2 = a.order == 2 ? 0.0 : -0.25 / 3.0 * a.rdx;
+            // D_f at row x, without the coefficient
+            auto d2 = [=](int x) -> cplx {                    // central stencil, order 2
+                const cplx p = at(x + 1), q = at(x - 1);
+                return mk(w1 * (p.x - q.x), w1 * (p.y - q.y));
+            };
+            auto d4 = [=](int x) -> cplx {                    // central stencil, order 4
+                const cplx p1 = at(x + 1), q1 = at(x - 1), p2 = at(x + 2), q2 = at(x - 2);
+                return mk(fma(w1, p1.x - q1.x, w2 * (p2.x - q2.x)), fma(w1, p1.y - q1.y, w2 * (p2.y - q2.y)));
+            };
+            // groups of 4 points: bounds the number of loads in flight (registers)
+            MLV_UNROLL
+            for (int j0 = 0; j0 < 16; j0 += 4) {
+                MLV_SCHED_FENCE();
+                const int tq = opaque_int(tau);      // address arithmetic stays inside the group
+                if (sym == XSYM_FDX) {
+                    if (a.order == 2) {
+                        MLV_UNROLL
+                        for (int j = j0; j < j0 + 4; ++j) {
+                            const int x = tq + F::T * j;
+                            cplx t = d2(x);
+                            if constexpr (SPLIT == 2) { const cplx u = d2(x + F::N); t = mk(t.x + sg * u.x, t.y + sg * u.y); }
+                            v[j] = mk(fma(cf, t.x, v[j].x), fma(cf, t.y, v[j].y));
+                        }
+                    } else {
+                        MLV_UNROLL
+                        for (int j = j0; j < j0 + 4; ++j) {
+                            const int x = tq + F::T * j;
+                            cplx t = d4(x);
+                            if constexpr (SPLIT == 2) { const cplx u = d4(x + F::N); t = mk(t.x + sg * u.x, t.y + sg * u.y); }
+                            v[j] = mk(fma(cf, t.x, v[j].x), fma(cf, t.y, v[j].y));
+                        }
                     }
                 } else {
-                    const double w1 = cf * (2.0 / 3.0 * a.rdx), w2 = cf * (-0.25 / 3.0 * a.rdx);
+                    // identity, or * (i sz) for the z stencil symbol
+                    const double cr = sym == XSYM_FDZ ? 0.0 : cf, ci = sym == XSYM_FDZ ? sz * cf : 0.0;
                     MLV_UNROLL
                     for (int j = j0; j < j0 + 4; ++j) {
                         const int x = tq + F::T * j;
-                        const cplx p1 = at(x + 1), q1 = at(x - 1), p2 = at(x + 2), q2 = at(x - 2);
-                        v[j] = mk(fma(w1, p1.x - q1.x, fma(w2, p2.x - q2.x, v[j].x)),
-                                  fma(w1, p1.y - q1.y, fma(w2, p2.y - q2.y, v[j].y)));
+                        cplx t = at(x);
+                        if constexpr (SPLIT == 2) { const cplx u = at(x + F::N); t = mk(t.x + sg * u.x, t.y + sg * u.y); }
+                        v[j] = mk(fma(cr, t.x, fma(-ci, t.y, v[j].x)), fma(cr, t.y, fma(ci, t.x, v[j].y)));
                     }
                 }
-            } else if (sym == XSYM_FDZ) {
-                const double s = sz * cf;                         // * (i s)
-                MLV_UNROLL
-                for (int j = j0; j < j0 + 4; ++j) {
-                    const cplx t = at(tq + F::T * j);
-                    v[j] = mk(fma(-s, t.y, v[j].x), fma(s, t.x, v[j].y));
-                }
-            } else {
-                MLV_UNROLL
-                for (int j = j0; j < j0 + 4; ++j) {
-                    const cplx t = at(tq + F::T * j);
-                    v[j] = mk(fma(cf, t.x, v[j].x), fma(cf, t.y, v[j].y));
-                }
             }
         }
-    }
-    MLV_SCHED_FENCE();
-    fft_line<LOG2N, false>(v, tau, a.tw, xc);
-    if (!valid) return;                                   // no barrier below
-    // ---- epilogue from registers: UN outputs per trip, all global loads of a trip issued
-    //      before the arithmetic (memory-level parallelism)
-    const int rows = 2 * a.nn + 1;
-    const int mg = m + a.sh.m_off;
-    constexpr int UN = 2;
-    MLV_UNROLL
-    for (int j0 = 0; j0 < 16; j0 += UN) {
-        if (MLV_MID(j0) && MLV_MID(j0 + UN - 1)) continue;       // always truncated
-        cplx q[UN], f1[UN];
-        size_t idx[UN];
-        int nmode[UN];
-        bool ok[UN];
         MLV_SCHED_FENCE();
-        const int tq = opaque_int(tau);
-        MLV_UNROLL
-        for (int u = 0; u < UN; ++u) {
-            int r = 0, n = 0;
-            ok[u] = xrow_of(tq + F::T * (j0 + u), F::N, a.nn, r, n);
-            nmode[u] = n;
-            idx[u] = ok[u] ? (size_t)r * a.spitch + m : (size_t)m;
+        if constexpr (SPLIT == 2) {
+            if (s) {
+                const int tq = opaque_int(tau);
+                MLV_UNROLL
+                for (int j = 0; j < 16; ++j) v[j] = cmul(v[j], a.tws[tq + F::T * j]);   // e^{-2 pi i p/NF}
+            }
         }
-        if (a.mode == 1) {
+        fft_line<LOG2N, false>(v, tau, a.tw, xc);
+        if (!valid) continue;                                 // no barrier below in this trip
+        // ---- epilogue from registers: UN outputs per trip, all global loads of a trip issued
+        //      before the arithmetic (memory-level parallelism)
+        constexpr int UN = 2;
+        MLV_UNROLL
+        for (int j0 = 0; j0 < 16; j0 += UN) {
+            if (SPLIT == 1 && MLV_MID(j0) && MLV_MID(j0 + UN - 1)) continue;       // always truncated
+            cplx q[UN], f1[UN];
+            size_t idx[UN];
+            int nmode[UN];
+            bool ok[UN];
+            MLV_SCHED_FENCE();
+            const int tq = opaque_int(tau);
             MLV_UNROLL
             for (int u = 0; u < UN; ++u) {
-                q[u] = a.integ.q_in[idx[u]];
-                f1[u] = a.integ.fm1[idx[u]];
+                int r = 0, n = 0;
+                ok[u] = xrow_of(SPLIT * (tq + F::T * (j0 + u)) + s, NF, a.nn, r, n);
+                nmode[u] = n;
+                idx[u] = ok[u] ? (size_t)r * a.spitch + m : (size_t)m;
             }
-        }
-        MLV_UNROLL
-        for (int u = 0; u < UN; ++u) {
-            if (!ok[u]) continue;
-            const cplx t = cscale(v[j0 + u], a.scale);
-            cplx f2 = mk(0.0, 0.0), f3 = f2;
-            if (a.mode == 1 && a.integ.ab_order == 4) { f2 = a.integ.fm2[idx[u]]; f3 = a.integ.fm3[idx[u]]; }
-            if (a.mode == 0) {
-                a.dst[idx[u]] = t;
-                continue;
+            if (a.mode == 1) {
+                MLV_UNROLL
+                for (int u = 0; u < UN; ++u) {
+                    q[u] = a.integ.q_in[idx[u]];
+                    f1[u] = a.integ.fm1[idx[u]];
+                }
             }
-            const cplx f0 = cadd(t, lin_terms_at(a.lin, idx[u], nmode[u], mg, a.k));
-            a.integ.f0[idx[u]] = f0;
-            a.integ.q_out[idx[u]] = integrate_value(a.integ, f0, q[u], f1[u], f2, f3, idx[u], nmode[u], mg, a.k);
+            MLV_UNROLL
+            for (int u = 0; u < UN; ++u) {
+                if (!ok[u]) continue;
+                const cplx t = cscale(v[j0 + u], a.scale);
+                cplx f2 = mk(0.0, 0.0), f3 = f2;
+                if (a.mode == 1 && a.integ.ab_order == 4) { f2 = a.integ.fm2[idx[u]]; f3 = a.integ.fm3[idx[u]]; }
+                if (a.mode == 0) {
+                    a.dst[idx[u]] = t;
+                    continue;
+                }
+                const cplx f0 = cadd(t, lin_terms_at(a.lin, idx[u], nmode[u], mg, a.k));
+                a.integ.f0[idx[u]] = f0;
+                a.integ.q_out[idx[u]] = integrate_value(a.integ, f0, q[u], f1[u], f2, f3, idx[u], nmode[u], mg, a.k);
+            }
         }
     }
-    (void)rows;
 }
 
 // ===================================================================== z passes
@@ -740,6 +760,7 @@ struct ZAdvArgs {
     cplx* IB;                      // out: z-spectrum of uz q
     double* red;                   // [gridDim.x][4] partials: max ux, max uz, sum ux^2, sum uz^2
     FftTw tw;
+    const cplx* tws;               // real-row lines: e^{-2 pi i k/nz}, k < nz/2
 };
 
 template <int LOG2N, int LPC>

@@ -19,6 +19,39 @@ SIZES_1D = [(16, 16), (64, 13), (64, 32), (256, 24), (1024, 6)]
 SIZES_FUSED = [(32, 64), (64, 32), (256, 64), (32, 512), (16, 1024), (18 * 0 + 16, 2048)]
 
 
+# long-line kernels (16384-point lines: x passes split in two half-length transforms, z stage
+# on single real rows) forced onto small grids through MLV_FORCE_SPLIT (bit 0: x, bit 1: z)
+SIZES_SPLIT = [(128, 128, 3), (256, 128, 1), (128, 256, 2), (256, 256, 3), (128, 32, 1), (32, 128, 2)]
+
+
+class forced_split:
+    """Context manager: contexts created inside take the long-line code paths."""
+
+    def __init__(self, bits):
+        self.bits = bits
+
+    def __enter__(self):
+        import os
+        self.old = os.environ.get("MLV_FORCE_SPLIT")
+        os.environ["MLV_FORCE_SPLIT"] = str(self.bits)
+
+    def __exit__(self, *exc):
+        import os
+        if self.old is None:
+            os.environ.pop("MLV_FORCE_SPLIT", None)
+        else:
+            os.environ["MLV_FORCE_SPLIT"] = self.old
+
+
+def case_split_lines(H, nx, nz, bits, order):
+    with forced_split(bits):
+        ctx = H.Ctx(nx, nz, 1.5, 1.0)
+        assert ctx.lib.mlv_long_lines(ctx.h) == bits      # the long-line kernels really run
+        ctx.close()
+        case_transforms_2d(H, nx, nz)
+        case_fused_advection_step(H, nx, nz, order)
+
+
 def rel(a, b):
     return np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-300)
 

@@ -40,6 +40,12 @@ def test_fused_advection_step(nx, nz, order):
     ac.case_fused_advection_step(H, nx, nz, order)
 
 
+@pytest.mark.parametrize("order", [2, 4])
+@pytest.mark.parametrize("nx,nz,bits", ac.SIZES_SPLIT)
+def test_split_lines(nx, nz, bits, order):
+    ac.case_split_lines(H, nx, nz, bits, order)
+
+
 def test_pointwise_and_stencils():
     ac.case_pointwise_and_stencils(H)
 

@@ -38,6 +38,20 @@ def test_fused_advection_step(H, nx, nz, order):
     ac.case_fused_advection_step(H, nx, nz, order)
 
 
+@pytest.mark.parametrize("order", [2, 4])
+@pytest.mark.parametrize("nx,nz,bits", ac.SIZES_SPLIT)
+def test_split_lines_forced(H, nx, nz, bits, order):
+    """long-line kernels forced onto small grids (same cases as the emulation build)"""
+    ac.case_split_lines(H, nx, nz, bits, order)
+
+
+@pytest.mark.parametrize("nx,nz", [(16384, 32), (32, 16384)])
+def test_lines_of_16384_points(H, nx, nz):
+    """BASELINE config-5 line length: transforms and the fused advection step vs the oracle"""
+    ac.case_transforms_2d(H, nx, nz)
+    ac.case_fused_advection_step(H, nx, nz, 2)
+
+
 def test_pointwise_and_stencils(H):
     ac.case_pointwise_and_stencils(H)
 
