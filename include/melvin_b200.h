@@ -81,7 +81,7 @@ typedef struct mlv_ctx mlv_ctx;
 /* melvin/Parameters.py:63-92 + melvin/BasisFunctions.py:26-59 (derived on the host
  * by the Python layer so the constants are bit-identical to the reference's) */
 typedef struct mlv_params {
-    int32_t nx, nz;        /* power of two, 16..8192, along every transformed axis */
+    int32_t nx, nz;        /* power of two along every transformed axis: 16..16384 (fully spectral), nx 16..8192 (FDM-z) */
     int32_t fdm_z;         /* 0: ["spectral","spectral"]   1: ["spectral","fdm"] */
     int32_t fd_order;      /* spatial_derivative_order: 2 or 4 */
     double lx, lz;

@@ -160,12 +160,13 @@ static constexpr int zlines(int log2n) {         // row pairs per z-pass CTA
         default: set_error("unsupported transform length 2^%d", (L)); return MLV_ERR_UNSUPPORTED; \
     }
 
-// the split kernels are instantiated for the production length (2 x 8192) and two small
-// lengths that the tests force through them (MLV_FORCE_SPLIT)
+// the long-line kernels are instantiated for the production lengths (8192 = 2 x 4096,
+// 16384 = 2 x 8192) and two small lengths that the tests force through them (MLV_FORCE_SPLIT)
 #define MLV_SWITCH_SPLIT(L, MACRO)                                                        \
     switch (L) {                                                                          \
         case 6: MACRO(6); break;                                                          \
         case 7: MACRO(7); break;                                                          \
+        case 12: MACRO(12); break;                                                        \
         case 13: MACRO(13); break;                                                        \
         default: set_error("split transforms: unsupported half length 2^%d", (L)); return MLV_ERR_UNSUPPORTED; \
     }
@@ -460,8 +461,11 @@ int mlv_create(const mlv_params* p, mlv_ctx** out) {
     // the long-line kernels (instantiated for half lengths 64, 128 and 8192)
     int force = 0;
     if (const char* e = getenv("MLV_FORCE_SPLIT")) force = atoi(e);
-    const bool xsplit = !p->fdm_z && (lx > 13 || ((force & 1) && (lx == 7 || lx == 8)));
-    const bool zreal = !p->fdm_z && (lz > 13 || ((force & 2) && (lz == 7 || lz == 8)));
+    // 8192-point lines fit the register transform, but only as one 512-thread line per SM;
+    // measured at 8192^2 the long-line forms are faster (x inverse 1.37 -> 1.01 ms, fused z
+    // stage 1.60 -> 1.20 ms, whole step 3.71 -> 3.06 ms), so they start at 8192
+    const bool xsplit = !p->fdm_z && (lx >= 13 || ((force & 1) && (lx == 7 || lx == 8)));
+    const bool zreal = !p->fdm_z && (lz >= 13 || ((force & 2) && (lz == 7 || lz == 8)));
     if (p->fdm_z && p->nz < 5) { set_error("mlv_create: nz too small"); return MLV_ERR_INVALID; }
     mlv_ctx* c = new (std::nothrow) mlv_ctx();
     if (!c) { set_error("out of host memory"); return MLV_ERR_NOMEM; }

@@ -52,14 +52,20 @@ if case == "tg64":
     if rank == 0:
         print(f"SHARDED world={world} field_err={max(errs.values()):.2e} ke_err={ke_err:.2e} "
               f"{'OK' if ok else 'FAIL'}", flush=True)
-elif case == "kh":
-    # uneven column split (nm not a multiple of the rank count), order-2 KH vs the oracle
+elif case in ("kh", "khlong"):
+    # uneven column split (nm not a multiple of the rank count), order-2 KH vs the oracle;
+    # "khlong": the long-line kernels (16384-point lines) forced onto a small grid
     nx, nz = (128, 64) if backend == "emu" else (1024, 512)
+    if case == "khlong":
+        os.environ["MLV_FORCE_SPLIT"] = "3"
+        nx, nz = 128, 256
     g = mo.Grid(nx, nz, 16.0 / 9.0, 1.0)
     w0 = mo.ic_kelvin_helmholtz(g)
     dt = 0.05 * g.lx / nx
     want, run, _ = mo.run_single_scalar(g, w0, 1e-5, dt, 12, tracker_cadence=1)
     st = ShardedScalarStepper(nx, nz, g.lx, g.lz, 1e-5, dt, tracker_cadence=1)
+    if case == "khlong":
+        assert st.ctx.lib.mlv_long_lines(st.ctx.handle) == 3
     st.load_spectral(mo.to_spectral(g, w0))
     for _ in range(12):
         st.step()

@@ -264,6 +264,22 @@ def test_one_step_at_baseline_size_4096():
     np.testing.assert_allclose(out["ke"], run.ke, rtol=SERIES_TOL)
 
 
+@pytest.mark.parametrize("nx,nz", [(16384, 64), (64, 16384)])
+def test_steps_with_16384_point_lines(nx, nz):
+    """BASELINE config-5 line length through the public API (long-line kernels: split x
+    passes / real-row z stage): three Kelvin-Helmholtz steps vs the oracle."""
+    lx, lz = 16.0 / 9.0, 1.0
+    g = mo.Grid(nx, nz, lx, lz)
+    w0 = mo.ic_kelvin_helmholtz(g)
+    dt = 0.05 * min(lx / nx, lz / nz)
+    want, run, snaps = mo.run_single_scalar(g, w0, 1e-5, dt, 3, tracker_cadence=1, snapshots=(1, 3))
+    with pc.scratch_cwd():
+        out = pc.run_single_scalar(nx, nz, lx, lz, 1e-5, dt, 3, w0, snaps=(1, 3))
+    for k in (1, 3):
+        assert rel_l2(out[f"w_step{k}"], snaps[k]) < FIELD_TOL, k
+    np.testing.assert_allclose(out["ke"], run.ke, rtol=SERIES_TOL)
+
+
 # --------------------------------------------------------------- edge cases
 def test_edge_cases_and_errors():
     from melvin import Parameters, Simulation

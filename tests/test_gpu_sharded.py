@@ -15,7 +15,7 @@ def _ngpu():
     return torch.cuda.device_count() if torch.cuda.is_available() else 0
 
 
-@pytest.mark.parametrize("case", ["tg64", "kh"])
+@pytest.mark.parametrize("case", ["tg64", "kh", "khlong"])
 def test_sharded_step_nccl(case):
     n = _ngpu()
     if n < 2:

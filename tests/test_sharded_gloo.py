@@ -33,3 +33,8 @@ def test_taylor_green_sharded_matches_reference_golden(world):
 
 def test_kelvin_helmholtz_sharded_uneven_split():
     run_world(2, "kh", 29611)
+
+
+def test_long_line_kernels_sharded():
+    """split x passes + real-row z stage under the slab decomposition (world 2)"""
+    run_world(2, "khlong", 29612)
