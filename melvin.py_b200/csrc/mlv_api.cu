@@ -294,6 +294,18 @@ static int launch_xinv(mlv_ctx* c, XInvArgs& a) {
     const size_t smem = ((size_t)F::XSLOTS + (size_t)(2 * a.nn + 1)) * C * sizeof(cplx);
     const unsigned grid = (unsigned)((a.nm + C - 1) / C);
     a.wave = 148 * (smem > 113 * 1024 ? 1 : 2);
+    a.use_tma = 0;
+#ifndef MLV_EMU
+    if (c->nranks == 1 && rt_tma_enabled()) {
+        // column tiles leave through tensor stores: one (rows x 2C doubles) box per 256 rows
+        a.tma_rows = F::N < 256 ? F::N : 256;
+        a.use_tma = 1;
+        for (int f = 0; f < a.nf && a.use_tma; ++f)
+            if (!rt_make_tmap(&a.tmap[f], a.dst[f], 2ull * a.ipitch, (unsigned long long)F::N,
+                              16ull * a.ipitch, 2u * C, (unsigned)a.tma_rows))
+                a.use_tma = 0;
+    }
+#endif
     MLV_LAUNCH(kfn, grid, (unsigned)(C * F::T), smem, c->stream, a);
     return 0;
 }

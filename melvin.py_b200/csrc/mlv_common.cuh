@@ -16,6 +16,8 @@
 #ifdef MLV_EMU
 // ------------------------------------------------------------------ emulation
 #include <cstring>
+#define __grid_constant__
+struct alignas(64) CUtensorMap { unsigned long long opaque[16]; };
 #include <functional>
 #include <vector>
 #define __global__
@@ -42,9 +44,10 @@ static inline double __ldg(const double* p) { return *p; }
 static inline double2 __ldg(const double2* p) { return *p; }
 #else
 // ----------------------------------------------------------------------- CUDA
+#include <cuda.h>            // CUtensorMap (types only; the driver entry point is looked up at run time)
 #include <cuda_runtime.h>
 #define MLV_UNROLL _Pragma("unroll")
-extern __shared__ __align__(16) unsigned char mlv_dyn_smem[];
+extern __shared__ __align__(128) unsigned char mlv_dyn_smem[];
 #define MLV_SMEM_BASE() (mlv_dyn_smem)
 #endif
 
@@ -146,6 +149,35 @@ MLV_DEV cplx ldg_pred(const cplx* p, bool pred) {
     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %3, 0;\n\t@q ld.global.v2.f64 {%0, %1}, [%2];\n\t}"
                  : "+d"(x), "+d"(y) : "l"(p), "r"((int)pred));
     return mk(x, y);
+#endif
+}
+
+// ---- TMA tensor stores (shared -> global, asynchronous, off the LSU pipe).  A column tile
+// of an x pass is C*16 bytes wide and thousands of rows tall: as ordinary stores every warp
+// instruction touches 16-32 different 128-byte lines; as one tensor store per 256 rows the
+// copy engine walks the rows while the SM starts on the next transform.
+MLV_DEV void tma_fence_smem() {        // generic-proxy smem writes -> visible to the async proxy
+#ifndef MLV_EMU
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+}
+MLV_DEV void tma_store_2d(const CUtensorMap* map, const void* smem, int c0, int c1) {
+#ifndef MLV_EMU
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"((unsigned long long)map), "r"(s), "r"(c0), "r"(c1) : "memory");
+#else
+    (void)map; (void)smem; (void)c0; (void)c1;
+#endif
+}
+MLV_DEV void tma_commit() {
+#ifndef MLV_EMU
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+#endif
+}
+MLV_DEV void tma_wait_read() {         // the shared-memory source of every committed store is free again
+#ifndef MLV_EMU
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 #endif
 }
 

@@ -220,6 +220,9 @@ struct XInvArgs {
     SpecConsts k;
     FftTw tw;
     const cplx* tws;             // split lines: e^{-2 pi i k/nx}, k < nx/2
+    int use_tma;                 // 1: column tiles leave through TMA tensor stores (unsharded, GPU build)
+    int tma_rows;                // rows per tensor-store box (<= 256)
+    CUtensorMap tmap[MLV_XMAXF]; // per destination: (nx, 2*ipitch) float64, box (tma_rows, 2*C)
 };
 
 // spectral (2nn+1, nm) -> I (nx, ipitch); nf fields, each with its own prologue.
@@ -229,7 +232,7 @@ struct XInvArgs {
 // thread-private stash.
 template <int LOG2N, int C>
 __global__ void __launch_bounds__(C * FftCfg<LOG2N>::T, (C * FftCfg<LOG2N>::T <= 256) ? 2 : 1)
-k_xinv(const XInvArgs a) {
+k_xinv(const __grid_constant__ XInvArgs a) {
     typedef FftCfg<LOG2N> F;
     const int c = threadIdx.x % C, tau = threadIdx.x / C;
     const int mreal = blockIdx.x * C + c;
@@ -248,6 +251,7 @@ k_xinv(const XInvArgs a) {
     const int mg = m + a.sh.m_off;                   // global column (spectral symbols)
     const int rmask = (1 << a.sh.rpc_shift) - 1;
     bool stash_psi = false;     // stash holds psi = -src/lap instead of the raw column
+    bool tma_pending = false;
     for (int f = 0; f < a.nf; ++f) {
         cplx v[16];
         const cplx* __restrict__ src = a.src[f];
@@ -316,8 +320,23 @@ k_xinv(const XInvArgs a) {
                 if (xrow_of(kk, F::N, a.nn, r, n)) v[j] = spectral_op(op, v[j], n, mg, a.k);
             }
         }
+        if (tma_pending && threadIdx.x == 0) tma_wait_read();   // previous tile has left the buffer
         fft_line<LOG2N, true>(v, tau, a.tw, xc);
-        if (valid) {
+        if (a.use_tma) {
+            // park the tile in the exchange buffer (dense [row][C]) and hand it to the copy
+            // engine; the stores overlap the next field's loads, prologue and first butterflies
+            __syncthreads();
+            MLV_UNROLL
+            for (int j = 0; j < 16; ++j) xc.buf[(size_t)(tau + F::T * j) * C + c] = v[j];
+            tma_fence_smem();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                for (int r0 = 0; r0 < F::N; r0 += a.tma_rows)
+                    tma_store_2d(&a.tmap[f], xc.buf + (size_t)r0 * C, 2 * C * (int)blockIdx.x, r0);
+                tma_commit();
+            }
+            tma_pending = true;
+        } else if (valid) {
             const size_t off = (size_t)a.dstoff[f] + m;
             MLV_UNROLL
             for (int j = 0; j < 16; ++j) {
@@ -326,6 +345,7 @@ k_xinv(const XInvArgs a) {
             }
         }
     }
+    if (tma_pending && threadIdx.x == 0) tma_wait_read();       // shared memory must outlive the reads
 }
 
 // ===================================================================== x forward

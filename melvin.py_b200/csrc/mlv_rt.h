@@ -45,6 +45,40 @@ inline int rt_h2d(void* d, const void* h, size_t n, stream_t s) {
     return rt_check(cudaMemcpy(d, h, n, cudaMemcpyHostToDevice), "cudaMemcpy");
 }
 inline size_t rt_max_smem() { return 232448; }   // 227 KB opt-in per CTA on sm_100
+
+// TMA descriptor of a row-major float64 matrix (rows x inner doubles, row pitch in bytes) cut
+// into boxes of box_rows x box_inner.  cuTensorMapEncodeTiled is a driver entry point: it is
+// looked up at run time so that the library loads on machines without libcuda (build check).
+inline bool rt_tma_enabled() {
+    static int on = -1;
+    if (on < 0) on = getenv("MLV_NO_TMA") ? 0 : 1;
+    return on == 1;
+}
+inline bool rt_make_tmap(CUtensorMap* m, void* base, unsigned long long inner, unsigned long long rows,
+                         unsigned long long row_bytes, unsigned box_inner, unsigned box_rows) {
+    typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+    static encode_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (encode_fn)p;
+    }
+    if (!fn || ((uintptr_t)base & 15) || (row_bytes & 15) || box_inner > 256 || box_rows > 256) return false;
+    const cuuint64_t gdim[2] = {inner, rows};
+    const cuuint64_t gstride[1] = {row_bytes};
+    const cuuint32_t box[2] = {box_inner, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, gdim, gstride, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 #define MLV_LAUNCH(kfn, grid, block, smem, stream, ...)                                   \
     do {                                                                                  \
         if ((size_t)(smem) > mlv::rt_max_smem()) {                                        \
