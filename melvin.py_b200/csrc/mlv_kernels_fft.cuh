@@ -446,6 +446,34 @@ k_xfwd(const XFwdArgs a) {
                 const cplx p1 = at(x + 1), q1 = at(x - 1), p2 = at(x + 2), q2 = at(x - 2);
                 return mk(fma(w1, p1.x - q1.x, w2 * (p2.x - q2.x)), fma(w1, p1.y - q1.y, w2 * (p2.y - q2.y)));
             };
+            // the pair every advected scalar produces (Variable.py:119-128): d/dx of src[f] by the
+            // order-2 stencil + d/dz of src[f+1] by its symbol -- one fused sweep, so that the
+            // loads of both operands are in flight together
+            if (SPLIT == 1 && sym == XSYM_FDX && a.order == 2 && f + 1 < a.nf && a.sym[f + 1] == XSYM_FDZ) {
+                const cplx* __restrict__ srcb = a.src[f + 1];
+                const double ci = sz * a.coef[f + 1], cw = cf * w1;
+                MLV_UNROLL
+                for (int j0 = 0; j0 < 16; j0 += 4) {
+                    MLV_SCHED_FENCE();
+                    const int tq = opaque_int(tau);
+                    cplx p[4], q[4], b[4];
+                    MLV_UNROLL
+                    for (int u = 0; u < 4; ++u) {
+                        const int x = tq + F::T * (j0 + u);
+                        p[u] = at(x + 1);
+                        q[u] = at(x - 1);
+                        b[u] = srcb[(size_t)(x >> rshift) * chunk + blk0 + (size_t)(x & (rpc - 1)) * C];
+                    }
+                    MLV_UNROLL
+                    for (int u = 0; u < 4; ++u) {
+                        const int j = j0 + u;
+                        v[j] = mk(fma(cw, p[u].x - q[u].x, fma(-ci, b[u].y, v[j].x)),
+                                  fma(cw, p[u].y - q[u].y, fma(ci, b[u].x, v[j].y)));
+                    }
+                }
+                ++f;
+                continue;
+            }
             // groups of 4 points: bounds the number of loads in flight (registers)
             MLV_UNROLL
             for (int j0 = 0; j0 < 16; j0 += 4) {
