@@ -463,7 +463,8 @@ def sharded_arm(args, rank, world):
                 "parallelism": f"kz-slabs / x-slabs over {world} GPUs; exchange of the x-transformed "
                 + ("intermediates fused into the producer kernels (stores into peer memory over "
                    "NVLink), ordered by 2 one-element all-reduces per step" if st.p2p else
-                   "intermediates by 2 NCCL all-to-all per step (3 + 2 fields)"),
+                   "intermediates by one asynchronous NCCL all-to-all per field (3 + 2 per step); "
+                   "the transfer of an inverse field overlaps the x pass of the next field"),
                 "cfl_cadence": st.cfl_cadence,
                 "tracker_cadence": st.tracker_cadence,
                 "l2": "working set per rank and step larger than the 126 MB L2; no flush",

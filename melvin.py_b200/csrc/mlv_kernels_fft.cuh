@@ -88,6 +88,17 @@ MLV_DEV bool xrow_of(int k, int N, int nn, int& r, int& n) {
     return false;
 }
 
+// Same for the point j (compile-time after unrolling) of thread tau, k = tau + (N/16) j:
+// by the invariant above j <= 5 can only be a low mode and j >= 10 only a high one, so the
+// mapping is branch-free.
+template <int N>
+MLV_DEV bool xrow_static(int j, int k, int nn, int& r, int& n) {
+    if (j <= 5) { r = k; n = k; return k <= nn; }
+    if (j >= 10) { n = k - N; r = n + 2 * nn + 1; return k >= N - nn; }
+    r = 0; n = 0;
+    return false;
+}
+
 // Slab decomposition over G ranks (G = 1: one chunk, everything local).
 //   spectral state : kz-slabs, rank g owns columns [g*nml, (g+1)*nml) (nml = tpr*CT)
 //   physical side  : x-slabs,  rank g owns rows    [g*nxl, (g+1)*nxl)
@@ -269,7 +280,7 @@ k_xinv(const __grid_constant__ XInvArgs a) {
             for (int j = 0; j < 16; ++j) {
                 if (MLV_MID(j)) { v[j] = mk(0.0, 0.0); continue; }
                 int r = 0, n = 0;
-                const bool ok = xrow_of(tau + F::T * j, F::N, a.nn, r, n);
+                const bool ok = xrow_static<F::N>(j, tau + F::T * j, a.nn, r, n);
                 const cplx t = stash[(size_t)(ok ? r : 0) * C + c];
                 v[j] = ok ? t : mk(0.0, 0.0);
             }
@@ -278,7 +289,7 @@ k_xinv(const __grid_constant__ XInvArgs a) {
             for (int j = 0; j < 16; ++j) {
                 if (MLV_MID(j)) { v[j] = mk(0.0, 0.0); continue; }
                 int r = 0, n = 0;
-                const bool ok = xrow_of(tau + F::T * j, F::N, a.nn, r, n);
+                const bool ok = xrow_static<F::N>(j, tau + F::T * j, a.nn, r, n);
                 v[j] = ldg_pred(src + (size_t)(ok ? r : 0) * a.spitch + m, ok);
             }
         }
@@ -288,25 +299,30 @@ k_xinv(const __grid_constant__ XInvArgs a) {
                 if (MLV_MID(j)) continue;
                 const int kk = tau + F::T * j;
                 int r, n;
-                if (xrow_of(kk, F::N, a.nn, r, n)) stash[(size_t)r * C + c] = v[j];
+                if (xrow_static<F::N>(j, kk, a.nn, r, n)) stash[(size_t)r * C + c] = v[j];
             }
         }
         if (wants_psi) {
             const bool have_psi = reuse && stash_psi;
             const bool park_psi = keep && next_wants_psi && !have_psi;
+            // ux = -(i kz m) psi, uz = (i kx n) psi   (utility.py:71,78); branch-free over the
+            // points: truncated rows hold 0 and stay 0
+            const double bz = a.k.kz0 * mg;
             MLV_UNROLL
             for (int j = 0; j < 16; ++j) {
                 if (MLV_MID(j)) continue;
                 const int kk = tau + F::T * j;
                 int r, n;
-                if (!xrow_of(kk, F::N, a.nn, r, n)) continue;
+                const bool ok = xrow_static<F::N>(j, kk, a.nn, r, n);
                 cplx psi = v[j];
                 if (!have_psi) {
-                    psi = spectral_op(XOP_PSI, v[j], n, mg, a.k);
-                    if (park_psi) stash[(size_t)r * C + c] = psi;
+                    double lap = lap_symbol(n, mg, a.k);
+                    if (n == 0 && mg == 0) lap = 1.0;
+                    const double rl = -fast_rcp(lap);             // psi = (-w)/lap
+                    psi = mk(v[j].x * rl, v[j].y * rl);
+                    if (park_psi && ok) stash[(size_t)r * C + c] = psi;
                 }
-                // ux = -(i kz m) psi, uz = (i kx n) psi   (utility.py:71,78)
-                if (op == XOP_UX) { const double b = a.k.kz0 * mg; v[j] = mk(b * psi.y, -b * psi.x); }
+                if (op == XOP_UX) v[j] = mk(bz * psi.y, -bz * psi.x);
                 else if (op == XOP_UZ) { const double b = a.k.kx0 * n; v[j] = mk(-b * psi.y, b * psi.x); }
                 else v[j] = psi;
             }
@@ -317,7 +333,8 @@ k_xinv(const __grid_constant__ XInvArgs a) {
                 if (MLV_MID(j)) continue;
                 const int kk = tau + F::T * j;
                 int r, n;
-                if (xrow_of(kk, F::N, a.nn, r, n)) v[j] = spectral_op(op, v[j], n, mg, a.k);
+                xrow_static<F::N>(j, kk, a.nn, r, n);
+                v[j] = spectral_op(op, v[j], n, mg, a.k);      // truncated rows: 0 stays 0
             }
         }
         if (tma_pending && threadIdx.x == 0) tma_wait_read();   // previous tile has left the buffer
@@ -535,7 +552,8 @@ k_xfwd(const XFwdArgs a) {
             MLV_UNROLL
             for (int u = 0; u < UN; ++u) {
                 int r = 0, n = 0;
-                ok[u] = xrow_of(SPLIT * (tq + F::T * (j0 + u)) + s, NF, a.nn, r, n);
+                if constexpr (SPLIT == 1) ok[u] = xrow_static<NF>(j0 + u, tq + F::T * (j0 + u), a.nn, r, n);
+                else ok[u] = xrow_of(SPLIT * (tq + F::T * (j0 + u)) + s, NF, a.nn, r, n);
                 nmode[u] = n;
                 idx[u] = ok[u] ? (size_t)r * a.spitch + m : (size_t)m;
             }

@@ -12,12 +12,24 @@ examples/kelvin_helmholtz_instability.py:115-131):
     integrator.integrate(w, dw, lin_op)
     simulation.end_loop()          # CFL every cfl_cadence loops, tracker every tracker_cadence
 
-Per step and rank:  mlv_x_inverse (local columns, 3 fields)  ->  all-to-all  ->
-mlv_advect_z (local rows)  ->  all-to-all  ->  mlv_x_forward (local columns, fused RHS +
-AB + theta-scheme).  The x stencil of the conservative form is applied as its Fourier
-symbol, so no halo exchange exists.  Reductions (CFL max, kinetic energy)
-are 4-double all-reduces at ticker cadence.  Collectives go through torch.distributed
-(NCCL on GPUs; gloo in the CPU tests of the host logic).
+Per step and rank:  mlv_x_inverse (local columns, 3 fields)  ->  exchange  ->
+mlv_advect_z (local rows)  ->  exchange  ->  mlv_x_forward (local columns, fused RHS +
+AB + theta-scheme).  The x stencil of the conservative form is applied along the complete
+x lines of the forward pass, so no halo exchange exists.  Reductions (CFL max, kinetic
+energy) are 4-double all-reduces at ticker cadence.
+
+Exchange buffers are laid out [field][peer][block]; two ways to move the blocks:
+  * "p2p"  -- the producer kernels store every peer's block straight into that peer's
+    receive buffer (CUDA IPC mapping, NVLink); only a one-element all-reduce orders
+    producers and consumers.  Lowest latency: the choice for small grids, where a step is
+    a few hundred microseconds.
+  * "a2a"  -- blocks are written locally and moved by one NCCL all-to-all per field,
+    issued asynchronously so that the transfer of field f overlaps the inverse x pass of
+    field f+1.  Contiguous NVLink transfers: the choice for large grids (at 16384^2 the
+    16-byte pieces of the direct peer stores reach only ~200-300 GB/s per GPU).
+The mode is picked from the bytes a rank sends per step (MLV_EXCHANGE=p2p|a2a overrides).
+Collectives go through torch.distributed (NCCL on GPUs; gloo in the CPU tests of the host
+logic).
 """
 import ctypes
 import os
@@ -40,7 +52,7 @@ class ShardedScalarStepper:
         self.cfl_cutoff, self.cfl_cadence, self.tracker_cadence = cfl_cutoff, cfl_cadence, tracker_cadence
         self.dx, self.dz = lx / nx, lz / nz
         self.ctx = _backend.Context(nx, nz, lx, lz, False, fd_order)
-        self.ctx.call("mlv_set_sharding", self.rank, self.world, 3, 2, count=False)
+        self.ctx.call("mlv_set_sharding", self.rank, self.world, 1, 1, count=False)
         info = _capi.Info()
         _capi.check(self.ctx.lib, self.ctx.lib.mlv_get_info(self.ctx.handle, ctypes.byref(info)))
         self.nn, self.nm = info.nn, info.nm
@@ -48,27 +60,38 @@ class ShardedScalarStepper:
         self.m_off = self.rank * self.nml if self.world > 1 else 0
         self.nxl = nx // self.world
         field = info.ibytes // 16                      # elements of one field of an exchange buffer
-        self.inv_field = self.nxl * info.ipitch        # per peer and field
+        self.inv_field = self.nxl * info.ipitch        # one peer block of an inverse field
         tiles = field // (self.world * self.nxl)       # tpr * ct
-        self.fwd_field = tiles * self.nxl
+        self.fwd_field = tiles * self.nxl              # one peer block of a forward field
+        self.inv_stride = self.world * self.inv_field  # elements between consecutive fields
+        self.fwd_stride = self.world * self.fwd_field
         cplx = np.complex128
+        # bytes this rank sends to its peers per step (3 inverse + 2 forward fields)
+        self.bytes_exchanged_per_step = 16 * (3 * self.inv_field + 2 * self.fwd_field) * (self.world - 1)
+        mode = os.environ.get("MLV_EXCHANGE", "")
+        if os.environ.get("MLV_NO_P2P"):
+            mode = "a2a"
         if p2p is None:
-            p2p = self.world > 1 and _backend.is_cuda() and not os.environ.get("MLV_NO_P2P")
+            if mode in ("p2p", "a2a"):
+                p2p = mode == "p2p"
+            else:                                      # latency-bound steps: direct peer stores
+                p2p = self.bytes_exchanged_per_step < 256 * 1024 * 1024
+            p2p = p2p and self.world > 1 and _backend.is_cuda()
         self.p2p = bool(p2p) and self.world > 1
         self._ipc = []
         if self.p2p:
             # receive buffers live in peer-mapped memory; the producer kernels of every rank
             # store straight into them over NVLink (compute + exchange in one kernel)
-            self.inv_recv_ptr = self._setup_peers(0, self.world * 3 * self.inv_field * 16)
-            self.fwd_recv_ptr = self._setup_peers(1, self.world * 2 * self.fwd_field * 16)
+            self.inv_recv_ptr = self._setup_peers(0, 3 * self.inv_stride * 16)
+            self.fwd_recv_ptr = self._setup_peers(1, 2 * self.fwd_stride * 16)
             self.inv_send_ptr, self.fwd_send_ptr = self.inv_recv_ptr, self.fwd_recv_ptr
             self._sync = _backend.zeros((1,), np.float64)
         else:
-            self.inv_send = _backend.zeros((self.world * 3 * self.inv_field,), cplx)
-            self.fwd_send = _backend.zeros((self.world * 2 * self.fwd_field,), cplx)
+            self.inv_send = _backend.zeros((3, self.inv_stride), cplx)
+            self.fwd_send = _backend.zeros((2, self.fwd_stride), cplx)
             if self.world > 1:
-                self.inv_recv = _backend.zeros((self.world * 3 * self.inv_field,), cplx)
-                self.fwd_recv = _backend.zeros((self.world * 2 * self.fwd_field,), cplx)
+                self.inv_recv = _backend.zeros((3, self.inv_stride), cplx)
+                self.fwd_recv = _backend.zeros((2, self.fwd_stride), cplx)
             else:
                 self.inv_recv, self.fwd_recv = self.inv_send, self.fwd_send
             self.inv_send_ptr, self.inv_recv_ptr = self.inv_send.data_ptr(), self.inv_recv.data_ptr()
@@ -83,8 +106,6 @@ class ShardedScalarStepper:
         self._cfl_counter = 0
         self._trk_counter = 0
         self.ke_times, self.ke = [], []
-        # bytes this rank sends to its peers per step (3 inverse + 2 forward fields)
-        self.bytes_exchanged_per_step = 16 * (3 * self.inv_field + 2 * self.fwd_field) * (self.world - 1)
         self._prebuild()
 
     def _setup_peers(self, which, nbytes):
@@ -141,34 +162,30 @@ class ShardedScalarStepper:
         return full[:, : self.nm]
 
     # ------------------------------------------------------------------- step
-    def _exchange(self, which):
-        """Make the blocks produced on every rank visible to their consumers."""
-        if self.world == 1:
-            return
-        if self.p2p:
-            # data already sits in the consumers' buffers: order producer and consumer kernels
-            # across ranks with a one-element all-reduce (stream-ordered, no host sync)
-            dist.all_reduce(self._sync, group=self.group)
-        elif which == 0:
-            dist.all_to_all_single(torch.view_as_real(self.inv_recv), torch.view_as_real(self.inv_send),
-                                   group=self.group)
-        else:
-            dist.all_to_all_single(torch.view_as_real(self.fwd_recv), torch.view_as_real(self.fwd_send),
-                                   group=self.group)
+    def _a2a(self, recv, send, f):
+        """Asynchronous all-to-all of field f ([peer][block] on both sides): ordered after the
+        work already on the compute stream, overlaps what is launched next."""
+        return dist.all_to_all_single(torch.view_as_real(recv[f]), torch.view_as_real(send[f]),
+                                      group=self.group, async_op=True)
 
     def _prebuild(self):
         """ctypes argument blocks that do not change from step to step."""
         vp = ctypes.c_void_p
-        self._ops = (ctypes.c_int32 * 3)(_capi.OP_IDENT, _capi.OP_UX, _capi.OP_UZ)
-        self._dsts = (vp * 3)(*[self.inv_send_ptr + 16 * f * self.inv_field for f in range(3)])
+        ops = (_capi.OP_IDENT, _capi.OP_UX, _capi.OP_UZ)
+        self._ops = (ctypes.c_int32 * 3)(*ops)
+        self._dsts = (vp * 3)(*[self.inv_send_ptr + 16 * f * self.inv_stride for f in range(3)])
         self._srcs = [(vp * 3)(w.data_ptr(), w.data_ptr(), w.data_ptr()) for w in self.w]
+        # one field per launch (a2a mode: the exchange of a field overlaps the next launch)
+        self._ops1 = [(ctypes.c_int32 * 1)(o) for o in ops]
+        self._dsts1 = [(vp * 1)(self.inv_send_ptr + 16 * f * self.inv_stride) for f in range(3)]
+        self._srcs1 = [(vp * 1)(w.data_ptr()) for w in self.w]
         ir, fs = self.inv_recv_ptr, self.fwd_send_ptr
-        self._zargs = (vp(ir + 16 * self.inv_field), vp(ir + 32 * self.inv_field), vp(ir),
-                       vp(fs), vp(fs + 16 * self.fwd_field), vp(self.red4.data_ptr()))
+        self._zargs = (vp(ir + 16 * self.inv_stride), vp(ir + 32 * self.inv_stride), vp(ir),
+                       vp(fs), vp(fs + 16 * self.fwd_stride), vp(self.red4.data_ptr()))
         d = _capi.XFwd()
         d.nf, d.mode = 2, 1
         d.src[0] = self.fwd_recv_ptr
-        d.src[1] = self.fwd_recv_ptr + 16 * self.fwd_field
+        d.src[1] = self.fwd_recv_ptr + 16 * self.fwd_stride
         d.sym[0], d.sym[1] = _capi.SYM_FDX, _capi.SYM_FDZ
         d.coef[0] = d.coef[1] = -1.0
         d.lin = _capi.make_lin_terms([])
@@ -181,14 +198,32 @@ class ShardedScalarStepper:
         ctx = self.ctx
         w_in, w_out = self.w[self.cur], self.w[1 - self.cur]
         wp = w_in.data_ptr()
-        # 1. inverse x pass on the local columns: q = w, ux, uz (psi shared inside the kernel)
-        ctx.call("mlv_x_inverse", 3, self._srcs[self.cur], self._ops, self._dsts)
-        # 2. transpose: row block h of every field goes to rank h
-        self._exchange(0)
-        # 3. physical-space stage on the local rows
-        ctx.call("mlv_advect_z", *self._zargs)
-        # 4. transpose back: tile block h goes to rank h
-        self._exchange(1)
+        if self.world == 1 or self.p2p:
+            # 1. inverse x pass on the local columns: q = w, ux, uz (psi shared inside the
+            #    kernel); with peer memory every block lands in its consumer's buffer
+            ctx.call("mlv_x_inverse", 3, self._srcs[self.cur], self._ops, self._dsts)
+            # 2. order producers and consumers across ranks (stream-ordered, no host sync)
+            if self.world > 1:
+                dist.all_reduce(self._sync, group=self.group)
+            # 3. physical-space stage on the local rows
+            ctx.call("mlv_advect_z", *self._zargs)
+            if self.world > 1:
+                dist.all_reduce(self._sync, group=self.group)
+        else:
+            # 1.+2. one launch and one all-to-all per field: the transpose of field f (row block
+            #       h goes to rank h) travels while the x pass of field f+1 runs
+            works = []
+            for f in range(3):
+                ctx.call("mlv_x_inverse", 1, self._srcs1[self.cur], self._ops1[f], self._dsts1[f])
+                works.append(self._a2a(self.inv_recv, self.inv_send, f))
+            for wk in works:
+                wk.wait()
+            # 3. physical-space stage on the local rows
+            ctx.call("mlv_advect_z", *self._zargs)
+            # 4. transpose back: tile block h goes to rank h
+            works = [self._a2a(self.fwd_recv, self.fwd_send, f) for f in range(2)]
+            for wk in works:
+                wk.wait()
         # 5. forward x pass + RHS + AB + theta-scheme on the local columns
         d = self._xfwd
         g = d.integ

@@ -15,8 +15,11 @@ def _ngpu():
     return torch.cuda.device_count() if torch.cuda.is_available() else 0
 
 
+@pytest.mark.parametrize("mode", ["p2p", "a2a"])
 @pytest.mark.parametrize("case", ["tg64", "kh", "khlong"])
-def test_sharded_step_nccl(case):
+def test_sharded_step_nccl(case, mode):
+    """both exchange modes: stores into peer memory fused in the producer kernels, and
+    asynchronous NCCL all-to-all per field"""
     n = _ngpu()
     if n < 2:
         pytest.skip("needs at least 2 GPUs")
@@ -24,7 +27,8 @@ def test_sharded_step_nccl(case):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", "29701",
            os.path.join(ROOT, "tests", "sharded_worker.py"), "cuda", case]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900,
+                         env=dict(os.environ, MLV_EXCHANGE=mode))
     lines = [ln for ln in out.stdout.splitlines() if ln.startswith("SHARDED")]
     assert out.returncode == 0 and lines and lines[-1].endswith("OK"), out.stdout[-2000:] + out.stderr[-2000:]
 
