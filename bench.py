@@ -461,10 +461,14 @@ def sharded_arm(args, rank, world):
                             "(BASELINE configs[1]), slab-decomposed",
                 "grid": [nx, nz],
                 "parallelism": f"kz-slabs / x-slabs over {world} GPUs; exchange of the x-transformed "
-                + ("intermediates fused into the producer kernels (stores into peer memory over "
-                   "NVLink), ordered by 2 one-element all-reduces per step" if st.p2p else
-                   "intermediates by one asynchronous NCCL all-to-all per field (3 + 2 per step); "
-                   "the transfer of an inverse field overlaps the x pass of the next field"),
+                + {"p2p": "intermediates fused into the producer kernels (stores into peer memory over "
+                          "NVLink), ordered by 2 one-element all-reduces per step",
+                   "dma": "intermediates by copy-engine transfers into peer memory (one contiguous block per "
+                          "peer and field, side stream), the copies of an inverse field overlapping the x "
+                          "pass of the next field; ordered by 2 one-element all-reduces per step",
+                   "a2a": "intermediates by one asynchronous NCCL all-to-all per field (3 + 2 per step); "
+                          "the transfer of an inverse field overlaps the x pass of the next field"}[st.mode],
+                "exchange_mode": st.mode,
                 "cfl_cadence": st.cfl_cadence,
                 "tracker_cadence": st.tracker_cadence,
                 "l2": "working set per rank and step larger than the 126 MB L2; no flush",

@@ -171,6 +171,11 @@ int mlv_p2p_alloc(mlv_ctx* ctx, int64_t bytes, void** ptr, void* handle64);
 int mlv_p2p_open(mlv_ctx* ctx, const void* handle64, void** ptr);
 int mlv_p2p_close(mlv_ctx* ctx, void* ptr, int opened);
 int mlv_set_peer_buffers(mlv_ctx* ctx, int which, void* const* bufs);
+/* Alternative for large grids: the kernels write their blocks locally and the caller moves
+ * each contiguous peer block with an asynchronous device-to-device copy into the peer's
+ * (IPC-mapped) receive buffer on `cuda_stream` -- copy engines drive NVLink at full width and
+ * leave the SMs to the next x pass. */
+int mlv_p2p_copy(mlv_ctx* ctx, void* dst, const void* src, int64_t bytes, void* cuda_stream);
 const char* mlv_last_error(void);
 int mlv_abi_version(void);
 long long mlv_launch_count(void);   /* kernels launched by the library so far (process-wide) */

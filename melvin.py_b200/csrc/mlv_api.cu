@@ -617,6 +617,20 @@ int mlv_p2p_close(mlv_ctx* c, void* ptr, int opened) {
 #endif
 }
 
+int mlv_p2p_copy(mlv_ctx* c, void* dst, const void* src, int64_t bytes, void* stream) {
+    if (!c || !dst || !src || bytes < 0) { set_error("mlv_p2p_copy: bad argument"); return MLV_ERR_INVALID; }
+    if (bytes == 0) return MLV_OK;
+#ifdef MLV_EMU
+    (void)stream;
+    memcpy(dst, src, (size_t)bytes);
+    return MLV_OK;
+#else
+    // device-to-device copy (peer-mapped destination): runs on a copy engine, not on the SMs
+    return rt_check(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream),
+                    "cudaMemcpyAsync (peer)");
+#endif
+}
+
 int mlv_set_peer_buffers(mlv_ctx* c, int which, void* const* bufs) {
     if (!c || (which != 0 && which != 1)) { set_error("mlv_set_peer_buffers: bad argument"); return MLV_ERR_INVALID; }
     if (c->nranks > MLV_MAXPEER) { set_error("at most %d peers", MLV_MAXPEER); return MLV_ERR_UNSUPPORTED; }

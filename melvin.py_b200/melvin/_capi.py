@@ -18,7 +18,7 @@ KIND_REAL, KIND_CPLX, KIND_SCALAR = range(3)
 RED_SUM, RED_MAX, RED_MIN, RED_SUMSQ, RED_SUMPROD = range(5)
 
 EXPORTS = [
-    "mlv_create", "mlv_destroy", "mlv_set_stream", "mlv_get_info", "mlv_long_lines", "mlv_set_sharding", "mlv_p2p_alloc", "mlv_p2p_open",
+    "mlv_create", "mlv_destroy", "mlv_set_stream", "mlv_get_info", "mlv_long_lines", "mlv_set_sharding", "mlv_p2p_alloc", "mlv_p2p_copy", "mlv_p2p_open",
     "mlv_p2p_close", "mlv_set_peer_buffers", "mlv_last_error",
     "mlv_abi_version", "mlv_launch_count", "mlv_to_physical", "mlv_to_spectral", "mlv_x_inverse",
     "mlv_z_inverse", "mlv_z_forward", "mlv_x_forward", "mlv_advect_z", "mlv_advect_phys",
@@ -103,6 +103,7 @@ def declare(lib):
         "mlv_p2p_alloc": [vp, C.c_int64, C.POINTER(vp), vp],
         "mlv_p2p_open": [vp, vp, C.POINTER(vp)],
         "mlv_p2p_close": [vp, vp, i32],
+        "mlv_p2p_copy": [vp, vp, vp, C.c_int64, vp],
         "mlv_set_peer_buffers": [vp, i32, C.POINTER(vp)],
         "mlv_abi_version": [],
         "mlv_to_physical": [vp, vp, vp, vp],

@@ -18,16 +18,20 @@ AB + theta-scheme).  The x stencil of the conservative form is applied along the
 x lines of the forward pass, so no halo exchange exists.  Reductions (CFL max, kinetic
 energy) are 4-double all-reduces at ticker cadence.
 
-Exchange buffers are laid out [field][peer][block]; two ways to move the blocks:
+Exchange buffers are laid out [field][peer][block]; three ways to move the blocks:
   * "p2p"  -- the producer kernels store every peer's block straight into that peer's
     receive buffer (CUDA IPC mapping, NVLink); only a one-element all-reduce orders
     producers and consumers.  Lowest latency: the choice for small grids, where a step is
     a few hundred microseconds.
-  * "a2a"  -- blocks are written locally and moved by one NCCL all-to-all per field,
-    issued asynchronously so that the transfer of field f overlaps the inverse x pass of
-    field f+1.  Contiguous NVLink transfers: the choice for large grids (at 16384^2 the
-    16-byte pieces of the direct peer stores reach only ~200-300 GB/s per GPU).
-The mode is picked from the bytes a rank sends per step (MLV_EXCHANGE=p2p|a2a overrides).
+  * "dma"  -- blocks are written locally and every contiguous peer block is moved by an
+    asynchronous device-to-device copy into the peer's IPC-mapped receive buffer
+    (mlv_p2p_copy on a side stream): copy engines drive NVLink with large transfers and
+    take no SM from the kernels; the copies of field f overlap the inverse x pass of field
+    f+1.  The choice for large grids (at 16384^2 the 16-byte pieces of the direct peer
+    stores reach only ~200-300 GB/s per GPU).
+  * "a2a"  -- same, with one asynchronous NCCL all-to-all per field (also the form the CPU
+    tests run over gloo).
+The mode is picked from the bytes a rank sends per step (MLV_EXCHANGE=p2p|dma|a2a overrides).
 Collectives go through torch.distributed (NCCL on GPUs; gloo in the CPU tests of the host
 logic).
 """
@@ -71,21 +75,33 @@ class ShardedScalarStepper:
         mode = os.environ.get("MLV_EXCHANGE", "")
         if os.environ.get("MLV_NO_P2P"):
             mode = "a2a"
-        if p2p is None:
-            if mode in ("p2p", "a2a"):
-                p2p = mode == "p2p"
-            else:                                      # latency-bound steps: direct peer stores
-                p2p = self.bytes_exchanged_per_step < 256 * 1024 * 1024
-            p2p = p2p and self.world > 1 and _backend.is_cuda()
-        self.p2p = bool(p2p) and self.world > 1
+        if p2p is not None:
+            mode = "p2p" if p2p else "a2a"
+        if mode not in ("p2p", "dma", "a2a"):          # latency-bound steps: direct peer stores
+            mode = "p2p" if self.bytes_exchanged_per_step < 256 * 1024 * 1024 else "dma"
+        if self.world == 1 or not _backend.is_cuda():
+            mode = "a2a"                               # (world 1: no exchange at all)
+        self.mode = mode
+        self.p2p = mode == "p2p"
         self._ipc = []
-        if self.p2p:
+        if mode == "p2p":
             # receive buffers live in peer-mapped memory; the producer kernels of every rank
             # store straight into them over NVLink (compute + exchange in one kernel)
-            self.inv_recv_ptr = self._setup_peers(0, 3 * self.inv_stride * 16)
-            self.fwd_recv_ptr = self._setup_peers(1, 2 * self.fwd_stride * 16)
+            self.inv_recv_ptr = self._setup_peers(0, 3 * self.inv_stride * 16)[self.rank]
+            self.fwd_recv_ptr = self._setup_peers(1, 2 * self.fwd_stride * 16)[self.rank]
             self.inv_send_ptr, self.fwd_send_ptr = self.inv_recv_ptr, self.fwd_recv_ptr
             self._sync = _backend.zeros((1,), np.float64)
+        elif mode == "dma":
+            # peer-mapped receive buffers filled by copy engines from local send buffers
+            self.inv_peers = self._setup_peers(0, 3 * self.inv_stride * 16, register=False)
+            self.fwd_peers = self._setup_peers(1, 2 * self.fwd_stride * 16, register=False)
+            self.inv_recv_ptr, self.fwd_recv_ptr = self.inv_peers[self.rank], self.fwd_peers[self.rank]
+            self.inv_send = _backend.zeros((3, self.inv_stride), cplx)
+            self.fwd_send = _backend.zeros((2, self.fwd_stride), cplx)
+            self.inv_send_ptr, self.fwd_send_ptr = self.inv_send.data_ptr(), self.fwd_send.data_ptr()
+            self._sync = _backend.zeros((1,), np.float64)
+            self._copy_stream = torch.cuda.Stream()
+            self._ev = [torch.cuda.Event() for _ in range(6)]
         else:
             self.inv_send = _backend.zeros((3, self.inv_stride), cplx)
             self.fwd_send = _backend.zeros((2, self.fwd_stride), cplx)
@@ -108,8 +124,10 @@ class ShardedScalarStepper:
         self.ke_times, self.ke = [], []
         self._prebuild()
 
-    def _setup_peers(self, which, nbytes):
-        """Allocate this rank's receive buffer, exchange CUDA IPC handles, open the peers'."""
+    def _setup_peers(self, which, nbytes, register=True):
+        """Allocate this rank's receive buffer, exchange CUDA IPC handles, open the peers'.
+        Returns the list of mapped pointers (own entry = own buffer); `register` hands them to
+        the library so that its kernels store into them directly."""
         lib, h = self.ctx.lib, self.ctx.handle
         own = ctypes.c_void_p()
         handle = ctypes.create_string_buffer(64)
@@ -126,8 +144,9 @@ class ShardedScalarStepper:
                 ptrs[r] = peer.value
                 self._ipc.append((peer.value, 1))
         self._ipc.append((own.value, 0))
-        _capi.check(lib, lib.mlv_set_peer_buffers(h, which, ptrs))
-        return own.value
+        if register:
+            _capi.check(lib, lib.mlv_set_peer_buffers(h, which, ptrs))
+        return [int(ptrs[r]) for r in range(self.world)]
 
     def close(self):
         """Release peer mappings (call on every rank, after a barrier)."""
@@ -168,6 +187,30 @@ class ShardedScalarStepper:
         return dist.all_to_all_single(torch.view_as_real(recv[f]), torch.view_as_real(send[f]),
                                       group=self.group, async_op=True)
 
+    def _dma(self, which, f, ev):
+        """Copy engine exchange of field f: after the work already on the compute stream, move
+        block h of the local send buffer into slot `rank` of peer h's receive buffer."""
+        comp = torch.cuda.current_stream()
+        ev.record(comp)
+        cs = self._copy_stream
+        cs.wait_event(ev)
+        block, stride = (self.inv_field, self.inv_stride) if which == 0 else (self.fwd_field, self.fwd_stride)
+        peers, send = (self.inv_peers, self.inv_send_ptr) if which == 0 else (self.fwd_peers, self.fwd_send_ptr)
+        lib, hnd = self.ctx.lib, self.ctx.handle
+        vp = ctypes.c_void_p
+        for i in range(self.world):
+            h = (self.rank + 1 + i) % self.world       # spread the first copies over the peers
+            dst = peers[h] + 16 * (f * stride + self.rank * block)
+            src = send + 16 * (f * stride + h * block)
+            _capi.check(lib, lib.mlv_p2p_copy(hnd, vp(dst), vp(src), 16 * block, vp(cs.cuda_stream)))
+
+    def _dma_join(self, ev):
+        """Compute stream waits for this rank's outgoing copies; the all-reduce that follows
+        then tells every rank that all incoming blocks have landed."""
+        ev.record(self._copy_stream)
+        torch.cuda.current_stream().wait_event(ev)
+        dist.all_reduce(self._sync, group=self.group)
+
     def _prebuild(self):
         """ctypes argument blocks that do not change from step to step."""
         vp = ctypes.c_void_p
@@ -198,7 +241,18 @@ class ShardedScalarStepper:
         ctx = self.ctx
         w_in, w_out = self.w[self.cur], self.w[1 - self.cur]
         wp = w_in.data_ptr()
-        if self.world == 1 or self.p2p:
+        if self.mode == "dma":
+            # one launch per field; the copies of field f (row block h -> rank h) run on the copy
+            # engines while the x pass of field f+1 runs on the SMs
+            for f in range(3):
+                ctx.call("mlv_x_inverse", 1, self._srcs1[self.cur], self._ops1[f], self._dsts1[f])
+                self._dma(0, f, self._ev[f])
+            self._dma_join(self._ev[3])
+            ctx.call("mlv_advect_z", *self._zargs)
+            for f in range(2):
+                self._dma(1, f, self._ev[f])
+            self._dma_join(self._ev[4])
+        elif self.world == 1 or self.p2p:
             # 1. inverse x pass on the local columns: q = w, ux, uz (psi shared inside the
             #    kernel); with peer memory every block lands in its consumer's buffer
             ctx.call("mlv_x_inverse", 3, self._srcs[self.cur], self._ops, self._dsts)

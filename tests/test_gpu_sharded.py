@@ -15,11 +15,11 @@ def _ngpu():
     return torch.cuda.device_count() if torch.cuda.is_available() else 0
 
 
-@pytest.mark.parametrize("mode", ["p2p", "a2a"])
+@pytest.mark.parametrize("mode", ["p2p", "dma", "a2a"])
 @pytest.mark.parametrize("case", ["tg64", "kh", "khlong"])
 def test_sharded_step_nccl(case, mode):
-    """both exchange modes: stores into peer memory fused in the producer kernels, and
-    asynchronous NCCL all-to-all per field"""
+    """all exchange modes: stores into peer memory fused in the producer kernels, copy-engine
+    transfers into peer memory, asynchronous NCCL all-to-all per field"""
     n = _ngpu()
     if n < 2:
         pytest.skip("needs at least 2 GPUs")
