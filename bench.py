@@ -66,6 +66,19 @@ def byte_model(nx, nz):
     }
 
 
+def measured_traffic(nx, nz):
+    """DRAM bytes per launch from the committed ncu capture (same grid only), else None."""
+    path = os.path.join(ROOT, "profiles", "r01b_traffic.json")
+    try:
+        with open(path) as fp:
+            d = json.load(fp)
+        if list(d["grid"]) == [nx, nz]:
+            return d["bytes_per_launch"], d["source"]
+    except (OSError, ValueError, KeyError):
+        pass
+    return {}, None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -306,9 +319,11 @@ def gpu_arm(args, rank, world):
     dw._pending = None
     dominant = max(kern, key=kern.get)
     achieved = bm[dominant] / (kern[dominant] * 1e-3) / 1e9
+    traffic, traffic_src = measured_traffic(nx, nz)
     roofline = {
         "bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "frac": achieved / peak, "traffic": traffic.get(dominant), "traffic_source": traffic_src,
+        "peak_source": peak_src,
         "algorithmic_bytes_per_launch": bm[dominant], "ms_per_launch": kern[dominant],
         "kernels": {k: {"ms": v, "algorithmic_bytes": bm[k], "GBps": bm[k] / (v * 1e-3) / 1e9,
                         "frac": bm[k] / (v * 1e-3) / 1e9 / peak} for k, v in kern.items()},

@@ -159,6 +159,12 @@ int mlv_long_lines(const mlv_ctx* ctx);
  * per direction (NCCL) between those calls.  inv_fields / fwd_fields = fields batched
  * per exchange (block strides).  mlv_get_info then reports the local shapes. */
 int mlv_set_sharding(mlv_ctx* ctx, int rank, int nranks, int inv_fields, int fwd_fields);
+/* Cuts the forward exchange buffers into row blocks of `rows_per_block` local rows (a power
+ * of two dividing nx/nranks; default: one block per rank): receive side
+ * [global row block][field][tile][rows][CT], send side [peer][local row block][...].  A caller
+ * that runs mlv_advect_z_rows block by block can ship every finished block while the next
+ * one is computed.  Reset by mlv_set_sharding. */
+int mlv_set_forward_blocks(mlv_ctx* ctx, int rows_per_block);
 /* Compute + collective in one kernel: receive buffers allocated with mlv_p2p_alloc are
  * exported to the peer processes (64-byte CUDA IPC handle), opened there with
  * mlv_p2p_open and registered with mlv_set_peer_buffers (which = 0: inverse exchange,
@@ -199,6 +205,10 @@ int mlv_x_forward(mlv_ctx* ctx, const mlv_xfwd* d);                /* I -> S + e
  *   sum ux^2, sum uz^2 (Integrator.py:35-44, utility.py:42-59). */
 int mlv_advect_z(mlv_ctx* ctx, const void* iux, const void* iuz, const void* iq,
                  void* ia, void* ib, double* red4);
+/* same on the local rows [row0, row0 + nrows) only (both even); red4, if given, reduces the
+ * partials of all rows below row0 + nrows (pass it with the last range) */
+int mlv_advect_z_rows(mlv_ctx* ctx, const void* iux, const void* iuz, const void* iq,
+                      void* ia, void* ib, int row0, int nrows, double* red4);
 /* materialised physical operands: out = pddx(ux*q) + pddz(uz*q) */
 int mlv_advect_phys(mlv_ctx* ctx, const double* ux, const double* uz, const double* q,
                     double* out);

@@ -55,6 +55,7 @@ struct mlv_ctx {
     int nm_loc = 0;             // valid local columns
     int nxl = 0;                // local rows
     int inv_fields = 1, fwd_fields = 1;
+    int fwd_rows = 0;           // rows per block of the forward exchange buffers (divides nxl)
     mlv::Shard sh{};
     // peer-mapped receive buffers (mlv_set_peer_buffers); null = exchange by all-to-all
     mlv::cplx* peer_inv[MLV_MAXPEER] = {};
@@ -215,7 +216,12 @@ static void configure_shard(mlv_ctx* c, int rank, int nranks, int inv_fields, in
     c->sh.rpc_shift = shift;
     c->sh.tpr = tpr;
     c->sh.inv_chunk = nranks == 1 ? 0 : (long long)inv_fields * c->nxl * c->nml;
-    c->sh.fwd_chunk = nranks == 1 ? 0 : (long long)fwd_fields * tpr * c->nxl * ct;
+    if (c->fwd_rows <= 0 || c->fwd_rows > c->nxl || nranks == 1) c->fwd_rows = c->nxl;
+    int fshift = 0;
+    while ((1 << fshift) < c->fwd_rows) ++fshift;
+    c->sh.fwd_rshift = fshift;
+    c->sh.fwd_chunk = nranks == 1 ? 0 : (long long)fwd_fields * tpr * c->fwd_rows * ct;
+    c->sh.fwd_peer = c->sh.fwd_chunk * (c->nxl / c->fwd_rows);
     c->spec_cols = c->p.fdm_z ? c->p.nz : (nranks == 1 ? c->nm : c->nml);
 }
 
@@ -353,11 +359,11 @@ static int launch_zadv_real(mlv_ctx* c, ZAdvArgs& a, unsigned& grid_out) {
     typedef FftCfg<L> F;
     auto kfn = k_zr_advect<L>;
     const size_t smem = F::XSLOTS * sizeof(double) + (size_t)F::N * sizeof(cplx) + (size_t)4 * F::T * sizeof(double);
-    const unsigned grid = (unsigned)a.nx;
+    const unsigned grid = (unsigned)a.nrows;
     grid_out = grid;
-    int rc = ensure_red(c, (size_t)grid * 4);
+    int rc = ensure_red(c, (size_t)(a.nx / a.nrows) * grid * 4);
     if (rc) return rc;
-    a.red = c->red;
+    a.red = c->red + (size_t)(a.row0 / a.nrows) * grid * 4;
     a.wave = 148;
     MLV_LAUNCH(kfn, grid, (unsigned)F::T, smem, c->stream, a);
     return 0;
@@ -404,11 +410,12 @@ static int launch_zadv(mlv_ctx* c, ZAdvArgs& a, unsigned& grid_out) {
     auto kfn = k_z_advect<L, LPC>;
     const size_t smem = (size_t)LPC * (F::XSLOTS * sizeof(double) + (size_t)F::N * sizeof(cplx)) +
                         (size_t)4 * LPC * F::T * sizeof(double);
-    const unsigned grid = (unsigned)((a.nx / 2 + LPC - 1) / LPC);
+    const unsigned grid = (unsigned)((a.nrows / 2 + LPC - 1) / LPC);
     grid_out = grid;
-    int rc = ensure_red(c, (size_t)grid * 4);
+    // per-CTA partials: the launch over rows [row0, row0 + nrows) owns slots [k grid, (k+1) grid), k = row0 / nrows
+    int rc = ensure_red(c, (size_t)(a.nx / a.nrows) * grid * 4);
     if (rc) return rc;
-    a.red = c->red;
+    a.red = c->red + (size_t)(a.row0 / a.nrows) * grid * 4;
     a.wave = 148 * (smem > 113 * 1024 ? 1 : 2);
 
     MLV_LAUNCH(kfn, grid, (unsigned)(LPC * F::T), smem, c->stream, a);
@@ -578,7 +585,22 @@ int mlv_set_sharding(mlv_ctx* c, int rank, int nranks, int inv_fields, int fwd_f
         set_error("mlv_set_sharding: need a power-of-two rank count dividing nx/2 and field counts >= 1");
         return MLV_ERR_INVALID;
     }
+    c->fwd_rows = 0;
     configure_shard(c, rank, nranks, inv_fields, fwd_fields);
+    return MLV_OK;
+}
+
+int mlv_set_forward_blocks(mlv_ctx* c, int rows_per_block) {
+    if (!c) { set_error("null context"); return MLV_ERR_INVALID; }
+    if (int rc = need_2d(c, "mlv_set_forward_blocks")) return rc;
+    if (rows_per_block < 2 || rows_per_block > c->nxl || (rows_per_block & (rows_per_block - 1)) ||
+        c->nxl % rows_per_block) {
+        set_error("mlv_set_forward_blocks: need a power of two >= 2 dividing the %d local rows", c->nxl);
+        return MLV_ERR_INVALID;
+    }
+    if (c->nranks == 1) return MLV_OK;                 // unsharded: one block
+    c->fwd_rows = rows_per_block;
+    configure_shard(c, c->rank, c->nranks, c->inv_fields, c->fwd_fields);
     return MLV_OK;
 }
 
@@ -821,19 +843,30 @@ int mlv_to_spectral(mlv_ctx* c, const double* phys, void* iscratch, void* spec) 
 // ------------------------------------------------------------ nonlinear term
 int mlv_advect_z(mlv_ctx* c, const void* iux, const void* iuz, const void* iq, void* ia, void* ib,
                  double* red4) {
+    if (!c) { set_error("mlv_advect_z: null argument"); return MLV_ERR_INVALID; }
+    return mlv_advect_z_rows(c, iux, iuz, iq, ia, ib, 0, c->nxl, red4);
+}
+
+int mlv_advect_z_rows(mlv_ctx* c, const void* iux, const void* iuz, const void* iq, void* ia, void* ib,
+                      int row0, int nrows, double* red4) {
     if (!c || !iux || !iuz || !iq || !ia || !ib) { set_error("mlv_advect_z: null argument"); return MLV_ERR_INVALID; }
     if (int rc = need_2d(c, "mlv_advect_z")) return rc;
+    if (row0 < 0 || nrows < 2 || (nrows & 1) || row0 % nrows || row0 + nrows > c->nxl || c->nxl % nrows) {
+        set_error("mlv_advect_z_rows: need equal even row ranges tiling the %d local rows", c->nxl);
+        return MLV_ERR_INVALID;
+    }
     ZAdvArgs a{};
+    a.row0 = row0; a.nrows = nrows;
     a.nx = c->nxl; a.nm = c->nm; a.ipitch = c->nml; a.ct = c->ct; a.sh = c->sh;
     a.Iux = (const cplx*)iux; a.Iuz = (const cplx*)iuz; a.Iq = (const cplx*)iq;
     a.IA = (cplx*)ia; a.IB = (cplx*)ib; a.tw = c->planz.tw;
     a.outoff[0] = 0; a.outoff[1] = (cplx*)ib - (cplx*)ia;
     for (int h = 0; h < c->nranks; ++h) {
         if (c->p2p_fwd) {
-            a.out.blk[h] = c->peer_fwd[h] + (size_t)c->rank * c->sh.fwd_chunk +
+            a.out.blk[h] = c->peer_fwd[h] + (size_t)c->rank * c->sh.fwd_peer +
                            ((cplx*)ia - c->peer_fwd[c->rank]);
         } else {
-            a.out.blk[h] = (cplx*)ia + (size_t)h * c->sh.fwd_chunk;
+            a.out.blk[h] = (cplx*)ia + (size_t)h * c->sh.fwd_peer;
         }
     }
     unsigned grid = 0;
@@ -849,9 +882,10 @@ int mlv_advect_z(mlv_ctx* c, const void* iux, const void* iuz, const void* iq, v
 #undef MLV_GO
     }
     if (rc) return rc;
-    if (red4) {
+    if (red4) {     // per-CTA partials of the rows [0, row0 + nrows) launched so far -> 4 doubles
+        const int ncta = (int)((long long)grid * (row0 + nrows) / nrows);
         auto kfn = k_reduce_final4;
-        MLV_LAUNCH(kfn, 4u, 256u, 256 * sizeof(double), c->stream, (const double*)c->red, (int)grid, red4);
+        MLV_LAUNCH(kfn, 4u, 256u, 256 * sizeof(double), c->stream, (const double*)c->red, ncta, red4);
     }
     return MLV_OK;
 }

@@ -104,7 +104,7 @@ MLV_DEV bool xrow_static(int j, int k, int nn, int& r, int& n) {
 //   physical side  : x-slabs,  rank g owns rows    [g*nxl, (g+1)*nxl)
 // Exchange buffers are laid out so that the block for every peer is contiguous:
 //   inverse (x pass -> z stage): [peer h][field][nxl rows of h][nml cols]  (row layout)
-//   forward (z stage -> x pass): [peer h][field][tpr tiles of h][nxl rows][CT]  (tile layout)
+//   forward (z stage -> x pass): [peer h][row block][field][tpr tiles of h][RB rows][CT]  (tile layout)
 struct Shard {
     int m_off;            // global index of local column 0
     int nm_glob;          // global number of retained columns (nm)
@@ -112,7 +112,12 @@ struct Shard {
     int rpc_shift;        // log2(rows per rank)
     int tpr;              // column tiles per rank
     long long inv_chunk;  // elements between the blocks of consecutive peers, inverse buffers
-    long long fwd_chunk;  // same, forward buffers
+    // forward buffers: row blocks of RB = 2^fwd_rshift rows (RB divides the rows of a rank; one
+    // block per rank by default, several when the caller pipelines the exchange by row ranges).
+    // Receive side: [global row block][tile][RB][CT];  send side: [dest peer][local row block][tile][RB][CT]
+    long long fwd_chunk;  // elements between consecutive row blocks (0 when unsharded)
+    long long fwd_peer;   // elements between the send regions of consecutive destination peers
+    int fwd_rshift;       // log2(RB)
 };
 
 // Where the producer kernels store the block destined for peer h.  Without peer
@@ -124,11 +129,18 @@ struct PeerBlocks {
     cplx* blk[MLV_MAXPEER];
 };
 
+// element (local row xl, tile tl of its owner, column cc of the tile) inside the send region of
+// the tile owner
+MLV_DEV size_t fwd_store_off(int xl, int tl, int cc, int ct, const Shard& sh) {
+    const int rbm = (1 << sh.fwd_rshift) - 1;
+    return (size_t)(xl >> sh.fwd_rshift) * sh.fwd_chunk +
+           ((((size_t)tl) << sh.fwd_rshift) + (size_t)(xl & rbm)) * ct + cc;
+}
 // element (local row xl, global column m) of a forward intermediate, tile layout
-MLV_DEV size_t fwd_off(int xl, int m, int nxl, int ct, const Shard& sh) {
+MLV_DEV size_t fwd_off(int xl, int m, int ct, const Shard& sh) {
     const int t = m / ct;
     const int h = t / sh.tpr, tl = t - h * sh.tpr;
-    return (size_t)h * sh.fwd_chunk + ((size_t)tl * nxl + xl) * ct + (m % ct);
+    return (size_t)h * sh.fwd_peer + fwd_store_off(xl, tl, m % ct, ct, sh);
 }
 // element m (global column) of a row of an inverse intermediate whose chunk-0 part starts at `row`
 MLV_DEV size_t inv_col_off(int m, const Shard& sh) {
@@ -409,7 +421,7 @@ k_xfwd(const XFwdArgs a) {
     xc.buf = reinterpret_cast<cplx*>(MLV_SMEM_BASE());
     xc.c = c;
     const double sz = a.symz[m + a.sh.m_off];
-    const int rpc = 1 << a.sh.rpc_shift;              // rows per peer block
+    const int rpc = 1 << a.sh.fwd_rshift;             // rows per block of the forward buffers
     {   // L2 prefetch: the other fields' blocks, the next CTA's first block, and the
         // state / history columns the epilogue will read
         constexpr unsigned CHUNK = 16384;
@@ -446,7 +458,7 @@ k_xfwd(const XFwdArgs a) {
             const int sym = a.sym[f];
             const double cf = a.coef[f];
             // element x (global row, periodic) of this thread's column: block of the row owner
-            const int rshift = a.sh.rpc_shift;
+            const int rshift = a.sh.fwd_rshift;
             const size_t chunk = (size_t)a.sh.fwd_chunk;
             auto at = [=](int x) -> cplx {
                 x &= NF - 1;
@@ -701,7 +713,7 @@ k_z_r2c(const ZArgs a) {
                 const cplx P = (kk == 0) ? v[j] : pbuf[kk];
                 cplx A, B;
                 zpair_unpack(v[j], P, A, B);
-                cplx* o = a.Iout + fwd_off(2 * rp, kk, a.nx, a.ct, a.sh);
+                cplx* o = a.Iout + fwd_off(2 * rp, kk, a.ct, a.sh);
                 o[0] = A;
                 o[a.ct] = B;                                   // row 2rp+1
             }
@@ -815,6 +827,7 @@ k_x1d_r2c(const X1dArgs a) {
 // of ux, uz; utility.py:42-59 sum ux^2, uz^2) as per-CTA partials.
 struct ZAdvArgs {
     int nx, nm, ipitch, ct;        // nx = local rows, nm = global retained columns
+    int row0, nrows;               // this launch covers local rows [row0, row0 + nrows) (both even)
     Shard sh;
     int wave;                      // CTAs resident at once (prefetch distance)
     const cplx* Iux;
@@ -835,9 +848,9 @@ k_z_advect(const ZAdvArgs a) {
     typedef FftCfg<LOG2N> F;
     constexpr int NT = LPC * F::T;
     const int l = threadIdx.x / F::T, tau = threadIdx.x % F::T;
-    const int rpreal = blockIdx.x * LPC + l;
-    const bool valid = 2 * rpreal < a.nx;
-    const int rp = valid ? rpreal : 0;               // clamp: loads stay unpredicated
+    const int rplocal = blockIdx.x * LPC + l;
+    const bool valid = 2 * rplocal < a.nrows;
+    const int rp = a.row0 / 2 + (valid ? rplocal : 0);   // clamp: loads stay unpredicated
     // shared memory: [ LPC*XSLOTS doubles exchange | LPC*N cplx thread-private stash | 4*NT doubles ]
     unsigned char* base = MLV_SMEM_BASE();
     XchgSplit xc;
@@ -916,7 +929,7 @@ k_z_advect(const ZAdvArgs a) {
                         const int t = kk >> cts;
                         int h = 0, tl = t;                                       // tile owner
                         if (sharded) { h = t / a.sh.tpr; tl = t - h * a.sh.tpr; }
-                        cplx* o = a.out.blk[h] + foff + ((size_t)tl * a.nx + 2 * rp) * a.ct + (kk & (a.ct - 1));
+                        cplx* o = a.out.blk[h] + foff + fwd_store_off(2 * rp, tl, kk & (a.ct - 1), a.ct, a.sh);
                         o[0] = A;
                         o[a.ct] = B;                               // row 2rp+1
                     }

@@ -238,7 +238,7 @@ k_zr_r2c(const ZRealArgs a) {
         const int t = k >> cts;
         int h = 0, tl = t;
         if (sharded) { h = t / a.sh.tpr; tl = t - h * a.sh.tpr; }
-        a.Iout[(size_t)h * a.sh.fwd_chunk + ((size_t)tl * a.nx + x) * a.ct + (k & (a.ct - 1))] = X;
+        a.Iout[(size_t)h * a.sh.fwd_peer + fwd_store_off(x, tl, k & (a.ct - 1), a.ct, a.sh)] = X;
     });
 }
 
@@ -250,7 +250,7 @@ k_zr_advect(const ZAdvArgs a) {
     typedef FftCfg<LOG2H> F;
     constexpr int NT = F::T;
     const int tau = threadIdx.x;
-    const int x = blockIdx.x;
+    const int x = a.row0 + blockIdx.x;
     unsigned char* base = MLV_SMEM_BASE();
     XchgSplit xc;
     xc.buf = reinterpret_cast<double*>(base);
@@ -287,7 +287,7 @@ k_zr_advect(const ZAdvArgs a) {
             const int t = k >> cts;
             int h = 0, tl = t;
             if (sharded) { h = t / a.sh.tpr; tl = t - h * a.sh.tpr; }
-            a.out.blk[h][foff + ((size_t)tl * a.nx + x) * a.ct + (k & (a.ct - 1))] = X;
+            a.out.blk[h][foff + fwd_store_off(x, tl, k & (a.ct - 1), a.ct, a.sh)] = X;
         });
     }
     // ---- reductions: per-CTA partials (deterministic two-stage reduction)

@@ -18,10 +18,10 @@ KIND_REAL, KIND_CPLX, KIND_SCALAR = range(3)
 RED_SUM, RED_MAX, RED_MIN, RED_SUMSQ, RED_SUMPROD = range(5)
 
 EXPORTS = [
-    "mlv_create", "mlv_destroy", "mlv_set_stream", "mlv_get_info", "mlv_long_lines", "mlv_set_sharding", "mlv_p2p_alloc", "mlv_p2p_copy", "mlv_p2p_open",
+    "mlv_create", "mlv_destroy", "mlv_set_stream", "mlv_get_info", "mlv_long_lines", "mlv_set_sharding", "mlv_set_forward_blocks", "mlv_p2p_alloc", "mlv_p2p_copy", "mlv_p2p_open",
     "mlv_p2p_close", "mlv_set_peer_buffers", "mlv_last_error",
     "mlv_abi_version", "mlv_launch_count", "mlv_to_physical", "mlv_to_spectral", "mlv_x_inverse",
-    "mlv_z_inverse", "mlv_z_forward", "mlv_x_forward", "mlv_advect_z", "mlv_advect_phys",
+    "mlv_z_inverse", "mlv_z_forward", "mlv_x_forward", "mlv_advect_z", "mlv_advect_z_rows", "mlv_advect_phys",
     "mlv_spec_lincomb", "mlv_lap_array", "mlv_stencil", "mlv_solve_fdm", "mlv_integrate",
     "mlv_elementwise", "mlv_reduce",
 ]
@@ -100,6 +100,7 @@ def declare(lib):
         "mlv_get_info": [vp, C.POINTER(Info)],
         "mlv_long_lines": [vp],
         "mlv_set_sharding": [vp, i32, i32, i32, i32],
+        "mlv_set_forward_blocks": [vp, i32],
         "mlv_p2p_alloc": [vp, C.c_int64, C.POINTER(vp), vp],
         "mlv_p2p_open": [vp, vp, C.POINTER(vp)],
         "mlv_p2p_close": [vp, vp, i32],
@@ -113,6 +114,7 @@ def declare(lib):
         "mlv_z_forward": [vp, vp, vp],
         "mlv_x_forward": [vp, C.POINTER(XFwd)],
         "mlv_advect_z": [vp, vp, vp, vp, vp, vp, vp],
+        "mlv_advect_z_rows": [vp, vp, vp, vp, vp, vp, i32, i32, vp],
         "mlv_advect_phys": [vp, vp, vp, vp, vp],
         "mlv_spec_lincomb": [vp, C.POINTER(LinTerms), vp],
         "mlv_lap_array": [vp, f64, vp],

@@ -100,8 +100,11 @@ class ShardedScalarStepper:
             self.fwd_send = _backend.zeros((2, self.fwd_stride), cplx)
             self.inv_send_ptr, self.fwd_send_ptr = self.inv_send.data_ptr(), self.fwd_send.data_ptr()
             self._sync = _backend.zeros((1,), np.float64)
-            self._copy_stream = torch.cuda.Stream()
+            # several copy streams: copies to different peers run on different copy engines
+            ncs = int(os.environ.get("MLV_COPY_STREAMS", "4"))
+            self._copy_streams = [torch.cuda.Stream() for _ in range(max(1, min(ncs, self.world)))]
             self._ev = [torch.cuda.Event() for _ in range(6)]
+            self._join_ev = [torch.cuda.Event() for _ in self._copy_streams]
         else:
             self.inv_send = _backend.zeros((3, self.inv_stride), cplx)
             self.fwd_send = _backend.zeros((2, self.fwd_stride), cplx)
@@ -112,6 +115,17 @@ class ShardedScalarStepper:
                 self.inv_recv, self.fwd_recv = self.inv_send, self.fwd_send
             self.inv_send_ptr, self.inv_recv_ptr = self.inv_send.data_ptr(), self.inv_recv.data_ptr()
             self.fwd_send_ptr, self.fwd_recv_ptr = self.fwd_send.data_ptr(), self.fwd_recv.data_ptr()
+        # forward exchange pipelined by row blocks: the z stage runs block by block and every
+        # finished block is shipped while the next one is computed (dma mode; a2a keeps one
+        # transfer per field but uses the same block layout when asked to, for the CPU tests)
+        nch = int(os.environ.get("MLV_FWD_CHUNKS", "4" if mode == "dma" else "1"))
+        while nch > 1 and (self.nxl % nch or (self.nxl // nch) % 2 or self.nxl // nch < 2):
+            nch //= 2
+        self.nchunks = max(1, nch) if self.world > 1 else 1
+        self.chunk_rows = self.nxl // self.nchunks
+        if self.nchunks > 1:
+            self.ctx.call("mlv_set_forward_blocks", self.chunk_rows, count=False)
+        self.fwd_block = self.fwd_field // self.nchunks      # one row block of one peer and field
         self.w = [_backend.zeros((self.rows, self.nml), cplx), _backend.zeros((self.rows, self.nml), cplx)]
         self.cur = 0
         self.hist = _backend.zeros((self.order, self.rows, self.nml), cplx)
@@ -187,28 +201,34 @@ class ShardedScalarStepper:
         return dist.all_to_all_single(torch.view_as_real(recv[f]), torch.view_as_real(send[f]),
                                       group=self.group, async_op=True)
 
-    def _dma(self, which, f, ev):
+    def _dma(self, which, f, ev, chunk=None):
         """Copy engine exchange of field f: after the work already on the compute stream, move
-        block h of the local send buffer into slot `rank` of peer h's receive buffer."""
+        block h of the local send buffer into slot `rank` of peer h's receive buffer (forward
+        buffers: optionally only row block `chunk` of it)."""
         comp = torch.cuda.current_stream()
         ev.record(comp)
-        cs = self._copy_stream
-        cs.wait_event(ev)
+        streams = self._copy_streams
+        for cs in streams:
+            cs.wait_event(ev)
         block, stride = (self.inv_field, self.inv_stride) if which == 0 else (self.fwd_field, self.fwd_stride)
         peers, send = (self.inv_peers, self.inv_send_ptr) if which == 0 else (self.fwd_peers, self.fwd_send_ptr)
+        sub, n = (0, block) if chunk is None else (chunk * self.fwd_block, self.fwd_block)
         lib, hnd = self.ctx.lib, self.ctx.handle
         vp = ctypes.c_void_p
         for i in range(self.world):
             h = (self.rank + 1 + i) % self.world       # spread the first copies over the peers
-            dst = peers[h] + 16 * (f * stride + self.rank * block)
-            src = send + 16 * (f * stride + h * block)
-            _capi.check(lib, lib.mlv_p2p_copy(hnd, vp(dst), vp(src), 16 * block, vp(cs.cuda_stream)))
+            dst = peers[h] + 16 * (f * stride + self.rank * block + sub)
+            src = send + 16 * (f * stride + h * block + sub)
+            cs = streams[i % len(streams)]
+            _capi.check(lib, lib.mlv_p2p_copy(hnd, vp(dst), vp(src), 16 * n, vp(cs.cuda_stream)))
 
     def _dma_join(self, ev):
         """Compute stream waits for this rank's outgoing copies; the all-reduce that follows
         then tells every rank that all incoming blocks have landed."""
-        ev.record(self._copy_stream)
-        torch.cuda.current_stream().wait_event(ev)
+        comp = torch.cuda.current_stream()
+        for cs, e in zip(self._copy_streams, self._join_ev):
+            e.record(cs)
+            comp.wait_event(e)
         dist.all_reduce(self._sync, group=self.group)
 
     def _prebuild(self):
@@ -225,6 +245,9 @@ class ShardedScalarStepper:
         ir, fs = self.inv_recv_ptr, self.fwd_send_ptr
         self._zargs = (vp(ir + 16 * self.inv_stride), vp(ir + 32 * self.inv_stride), vp(ir),
                        vp(fs), vp(fs + 16 * self.fwd_stride), vp(self.red4.data_ptr()))
+        self._zrows = [self._zargs[:5] + (c * self.chunk_rows, self.chunk_rows,
+                                          self._zargs[5] if c == self.nchunks - 1 else None)
+                       for c in range(self.nchunks)]
         d = _capi.XFwd()
         d.nf, d.mode = 2, 1
         d.src[0] = self.fwd_recv_ptr
@@ -248,9 +271,12 @@ class ShardedScalarStepper:
                 ctx.call("mlv_x_inverse", 1, self._srcs1[self.cur], self._ops1[f], self._dsts1[f])
                 self._dma(0, f, self._ev[f])
             self._dma_join(self._ev[3])
-            ctx.call("mlv_advect_z", *self._zargs)
-            for f in range(2):
-                self._dma(1, f, self._ev[f])
+            # z stage block by block; the two fields of a finished row block leave while the
+            # next block is computed
+            for c in range(self.nchunks):
+                ctx.call("mlv_advect_z_rows", *self._zrows[c])
+                for f in range(2):
+                    self._dma(1, f, self._ev[c % 3], chunk=c if self.nchunks > 1 else None)
             self._dma_join(self._ev[4])
         elif self.world == 1 or self.p2p:
             # 1. inverse x pass on the local columns: q = w, ux, uz (psi shared inside the
@@ -273,7 +299,8 @@ class ShardedScalarStepper:
             for wk in works:
                 wk.wait()
             # 3. physical-space stage on the local rows
-            ctx.call("mlv_advect_z", *self._zargs)
+            for c in range(self.nchunks):
+                ctx.call("mlv_advect_z_rows", *self._zrows[c])
             # 4. transpose back: tile block h goes to rank h
             works = [self._a2a(self.fwd_recv, self.fwd_send, f) for f in range(2)]
             for wk in works:

@@ -14,11 +14,11 @@ if shutil.which("g++") is None:  # pragma: no cover
     pytest.skip("g++ not available for the emulation build", allow_module_level=True)
 
 
-def run_world(n, case, port):
+def run_world(n, case, port, **extra_env):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
            "--master-addr", "127.0.0.1", "--master-port", str(port),
            os.path.join(ROOT, "tests", "sharded_worker.py"), "emu", case]
-    env = dict(os.environ, OMP_NUM_THREADS="1")
+    env = dict(os.environ, OMP_NUM_THREADS="1", **extra_env)
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
     lines = [ln for ln in out.stdout.splitlines() if ln.startswith("SHARDED")]
     assert out.returncode == 0 and lines and lines[-1].endswith("OK"), out.stdout[-2000:] + out.stderr[-2000:]
@@ -38,3 +38,10 @@ def test_kelvin_helmholtz_sharded_uneven_split():
 def test_long_line_kernels_sharded():
     """split x passes + real-row z stage under the slab decomposition (world 2)"""
     run_world(2, "khlong", 29612)
+
+
+@pytest.mark.parametrize("case", ["kh", "khlong"])
+def test_forward_exchange_in_row_blocks(case):
+    """forward buffers cut into row blocks, z stage launched block by block (the layout the
+    copy-engine exchange pipelines on GPUs)"""
+    run_world(2, case, 29613, MLV_FWD_CHUNKS="4")
