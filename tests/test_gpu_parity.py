@@ -280,6 +280,48 @@ def test_steps_with_16384_point_lines(nx, nz):
     np.testing.assert_allclose(out["ke"], run.ke, rtol=SERIES_TOL)
 
 
+@pytest.mark.parametrize("nx,nz", [(8192, 64), (64, 8192)])
+def test_double_diffusive_with_config4_line_length(nx, nz):
+    """BASELINE config 4 line length (8192 points: long-line kernels) through the public API:
+    three fields, coupling terms, column fix-ups; 4 steps vs the oracle."""
+    lx, lz = 83.75, 9 * 83.75 / 16
+    Pr, R0, tau, dt = 7.0, 1.1, 1.0 / 3.0, 1e-3
+    g = mo.Grid(nx, nz, lx, lz)
+    run = mo.Run(g, dt, tracker_cadence=1)
+    noise = mo.ic_noise(g)
+    state = tuple(mo.to_spectral(g, noise) for _ in range(3))
+    hists = tuple(mo.History(g) for _ in range(3))
+    for _ in range(4):
+        state = mo.step_double_diffusive(g, run, state, hists, Pr, R0, tau)
+    with pc.scratch_cwd():
+        out = pc.run_ddc(nx, nz, lx, lz, dt, 4, Pr, R0, tau, snaps=(4,))
+    for nm, arr in zip(("w", "tmp", "xi"), state):
+        assert rel_l2(out[f"{nm}_step4"], arr) < FIELD_TOL, nm
+    np.testing.assert_allclose(out["ke"], run.ke, rtol=SERIES_TOL)
+    np.testing.assert_allclose(out["nu"] - 1, np.array(run.extra) - 1, rtol=1e-6, atol=1e-17)
+
+
+@pytest.mark.parametrize("nx,nz", [(16384, 64), (64, 16384)])
+def test_tearing_with_config5_line_length(nx, nz):
+    """BASELINE config 5 line length (16384 points) through the public API: vorticity and
+    current with the updated-vorticity ordering of the reference loop; 3 steps vs the oracle."""
+    lx, lz, Re, S = 16.0 / 9.0, 1.0, 1e6, 1e6
+    g = mo.Grid(nx, nz, lx, lz)
+    j0 = mo.ic_tearing_current(g)
+    dt = 0.05 * min(lx / nx, lz / nz) * 0.01
+    run = mo.Run(g, dt, tracker_cadence=1)
+    state = (np.zeros(g.spectral_shape, complex), mo.to_spectral(g, j0))
+    hists = (mo.History(g), mo.History(g))
+    for _ in range(3):
+        state = mo.step_tearing(g, run, state, hists, Re, S)
+    with pc.scratch_cwd():
+        out = pc.run_tearing(nx, nz, lx, lz, dt, 3, Re, S, j0, snaps=(3,))
+    assert rel_l2(out["j_step3"], state[1]) < FIELD_TOL
+    # w starts from exactly zero and is the small residue of cancelling O(1) terms
+    assert rel_l2(out["w_step3"], state[0]) < 1e-6
+    np.testing.assert_allclose(out["ke"], run.ke, rtol=1e-4, atol=1e-300)
+
+
 # --------------------------------------------------------------- edge cases
 def test_edge_cases_and_errors():
     from melvin import Parameters, Simulation
