@@ -297,10 +297,31 @@ static int launch_xinv(mlv_ctx* c, XInvArgs& a) {
     constexpr int C = xcols(L);
     typedef FftCfg<L> F;
     auto kfn = k_xinv<L, C>;
-    const size_t smem = ((size_t)F::XSLOTS + (size_t)(2 * a.nn + 1)) * C * sizeof(cplx);
+    const int rows = 2 * a.nn + 1;
+    size_t smem = ((size_t)F::XSLOTS + (size_t)rows) * C * sizeof(cplx) + 16;     // + mbarrier
     const unsigned grid = (unsigned)((a.nm + C - 1) / C);
-    a.wave = 148 * (smem > 113 * 1024 ? 1 : 2);
     a.use_tma = 0;
+    a.load_tma = 0; a.ld_rows = rows; a.ld_boxes = 1;
+#ifndef MLV_EMU
+    if (rt_tma_enabled()) {
+        // source tiles through tensor loads: boxes of ld_rows rows; the stash is rounded up to whole
+        // boxes, so pick the largest box height whose padding still fits the shared memory
+        for (int lr = 256; lr >= 16 && !a.load_tma; lr >>= 1) {
+            const int h = rows < lr ? rows : lr, nb = (rows + h - 1) / h;
+            const size_t need = ((size_t)F::XSLOTS + (size_t)h * nb) * C * sizeof(cplx) + 16;
+            if (need > rt_max_smem()) continue;
+            if (smem <= 113 * 1024 && need > 113 * 1024) continue;     // keep two CTAs per SM
+            a.load_tma = 1; a.ld_rows = h; a.ld_boxes = nb;
+            for (int f = 0; f < a.nf && a.load_tma; ++f)
+                if (!rt_make_tmap(&a.smap[f], const_cast<cplx*>(a.src[f]), 2ull * a.spitch, (unsigned long long)rows,
+                                  16ull * a.spitch, 2u * C, (unsigned)h))
+                    a.load_tma = 0;
+            if (a.load_tma) smem = need;
+            else { a.ld_rows = rows; a.ld_boxes = 1; break; }
+        }
+    }
+#endif
+    a.wave = 148 * (smem > 113 * 1024 ? 1 : 2);
 #ifndef MLV_EMU
     if (c->nranks == 1 && rt_tma_enabled()) {
         // column tiles leave through tensor stores: one (rows x 2C doubles) box per 256 rows
@@ -333,7 +354,8 @@ static int launch_xfwd_split(mlv_ctx* c, XFwdArgs& a) {
     constexpr int C = xcols(L);
     typedef FftCfg<L> F;
     auto kfn = k_xfwd<L, C, 2>;
-    const size_t smem = (size_t)F::XSLOTS * C * sizeof(cplx);
+    a.stage = 0;
+    const size_t smem = (size_t)F::XSLOTS * C * sizeof(cplx) + 16;
     const unsigned grid = (unsigned)((a.nm + C - 1) / C);
     a.wave = 148 * (smem > 113 * 1024 ? 1 : 2);
     MLV_LAUNCH(kfn, grid, (unsigned)(C * F::T), smem, c->stream, a);
@@ -374,9 +396,17 @@ static int launch_xfwd(mlv_ctx* c, XFwdArgs& a) {
     constexpr int C = xcols(L);
     typedef FftCfg<L> F;
     auto kfn = k_xfwd<L, C, 1>;
-    const size_t smem = (size_t)F::XSLOTS * C * sizeof(cplx);
+    const size_t smem = (size_t)F::XSLOTS * C * sizeof(cplx) + 16;       // + mbarrier
     const unsigned grid = (unsigned)((a.nm + C - 1) / C);
     a.wave = 148 * (smem > 113 * 1024 ? 1 : 2);
+    a.stage = 0;
+#ifndef MLV_EMU
+    // operand pair of an advected scalar (d/dx by the order-2 stencil, d/dz by its symbol):
+    // stage the stencil operand in shared memory with bulk copies
+    if (rt_tma_enabled() && a.nf >= 2 && a.sym[0] == XSYM_FDX && a.sym[1] == XSYM_FDZ && a.order == 2 &&
+        ((1u << a.sh.fwd_rshift) * C * sizeof(cplx)) % 16 == 0)
+        a.stage = 1;
+#endif
     MLV_LAUNCH(kfn, grid, (unsigned)(C * F::T), smem, c->stream, a);
     return 0;
 }

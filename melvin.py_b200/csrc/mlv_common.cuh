@@ -181,6 +181,63 @@ MLV_DEV void tma_wait_read() {         // the shared-memory source of every comm
 #endif
 }
 
+// ---- asynchronous global -> shared copies completing on an mbarrier (TMA loads): the copy
+// engine fetches a whole tile while the threads do something else; consumers wait on the
+// barrier's phase parity.
+MLV_DEV void mbar_init(unsigned long long* bar, int count) {
+#ifndef MLV_EMU
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#else
+    (void)bar; (void)count;
+#endif
+}
+MLV_DEV void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+#ifndef MLV_EMU
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+#else
+    (void)bar; (void)bytes;
+#endif
+}
+MLV_DEV void mbar_wait(unsigned long long* bar, unsigned parity) {
+#ifndef MLV_EMU
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "MLV_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n\t"
+        "@p bra MLV_DONE_%=;\n\t"
+        "bra MLV_WAIT_%=;\n\t"
+        "MLV_DONE_%=:\n\t}" ::"r"(a), "r"(parity) : "memory");
+#else
+    (void)bar; (void)parity;
+#endif
+}
+// contiguous global -> shared (multiple of 16 bytes, 16-byte aligned on both sides)
+MLV_DEV void bulk_load(void* smem, const void* gmem, unsigned bytes, unsigned long long* bar) {
+#ifndef MLV_EMU
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(s), "l"(gmem), "r"(bytes), "r"(b) : "memory");
+#else
+    (void)smem; (void)gmem; (void)bytes; (void)bar;
+#endif
+}
+// one box of a 2-D tensor map, global -> shared
+MLV_DEV void tma_load_2d(void* smem, const CUtensorMap* map, int c0, int c1, unsigned long long* bar) {
+#ifndef MLV_EMU
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(s), "l"((unsigned long long)map), "r"(b), "r"(c0), "r"(c1) : "memory");
+#else
+    (void)smem; (void)map; (void)c0; (void)c1; (void)bar;
+#endif
+}
+
 // Reciprocal to ~1 ulp without the branchy IEEE division sequence: 20-bit hardware
 // seed + two Newton steps (operands here are O(1)..O(1e9), never denormal or zero).
 MLV_DEV double fast_rcp(double x) {

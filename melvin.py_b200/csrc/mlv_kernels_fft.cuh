@@ -246,6 +246,9 @@ struct XInvArgs {
     int use_tma;                 // 1: column tiles leave through TMA tensor stores (unsharded, GPU build)
     int tma_rows;                // rows per tensor-store box (<= 256)
     CUtensorMap tmap[MLV_XMAXF]; // per destination: (nx, 2*ipitch) float64, box (tma_rows, 2*C)
+    int load_tma;                // 1: source column tiles arrive in the stash through TMA tensor loads
+    int ld_rows, ld_boxes;       // rows per load box, boxes per column tile (stash holds ld_rows*ld_boxes rows)
+    CUtensorMap smap[MLV_XMAXF]; // per source: (2nn+1, 2*spitch) float64, box (ld_rows, 2*C)
 };
 
 // spectral (2nn+1, nm) -> I (nx, ipitch); nf fields, each with its own prologue.
@@ -265,6 +268,22 @@ k_xinv(const __grid_constant__ XInvArgs a) {
     xc.buf = reinterpret_cast<cplx*>(MLV_SMEM_BASE());
     xc.c = c;
     cplx* stash = xc.buf + (size_t)F::XSLOTS * C;
+    // source column tiles (C*16-byte pieces of 2nn+1 rows) are gathered by the copy engine into
+    // the stash: one tensor load per ld_rows rows instead of a scattered load per row and warp
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(stash + (size_t)a.ld_rows * a.ld_boxes * C);
+    unsigned ld_phase = 0;
+    auto stash_fetch = [&](int f) {
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(bar, (unsigned)((size_t)a.ld_rows * a.ld_boxes * C * sizeof(cplx)));
+            for (int b = 0; b < a.ld_boxes; ++b)
+                tma_load_2d(stash + (size_t)b * a.ld_rows * C, &a.smap[f], 2 * C * (int)blockIdx.x, b * a.ld_rows, bar);
+        }
+    };
+    if (a.load_tma) {
+        if (threadIdx.x == 0) mbar_init(bar, 1);
+        __syncthreads();
+        stash_fetch(0);                              // flies during the prefetch announcements below
+    }
     // announce the columns of the CTA that follows this one on the SM
     if ((int)(blockIdx.x + a.wave) < (int)gridDim.x) {
         const int rows = 2 * a.nn + 1;
@@ -287,7 +306,16 @@ k_xinv(const __grid_constant__ XInvArgs a) {
         const int opn = keep ? a.op[f + 1] : -1;
         const bool next_wants_psi = (opn == XOP_PSI || opn == XOP_UX || opn == XOP_UZ);
         // branch-free loads (all issued before the first is consumed); truncated rows read 0
-        if (reuse) {
+        const bool via_tma = !reuse && a.load_tma;
+        if (via_tma) {
+            if (f > 0) {                             // the stash still held the previous source
+                __syncthreads();
+                stash_fetch(f);
+            }
+            mbar_wait(bar, ld_phase);
+            ld_phase ^= 1;
+        }
+        if (reuse || via_tma) {
             MLV_UNROLL
             for (int j = 0; j < 16; ++j) {
                 if (MLV_MID(j)) { v[j] = mk(0.0, 0.0); continue; }
@@ -305,7 +333,7 @@ k_xinv(const __grid_constant__ XInvArgs a) {
                 v[j] = ldg_pred(src + (size_t)(ok ? r : 0) * a.spitch + m, ok);
             }
         }
-        if (keep && !reuse && !(wants_psi && next_wants_psi)) {      // park the raw column
+        if (keep && !reuse && !via_tma && !(wants_psi && next_wants_psi)) {      // park the raw column
             MLV_UNROLL
             for (int j = 0; j < 16; ++j) {
                 if (MLV_MID(j)) continue;
@@ -396,6 +424,7 @@ struct XFwdArgs {
     SpecConsts k;
     FftTw tw;
     const cplx* tws;             // SPLIT = 2: e^{-2 pi i p/nx}, p < nx/2
+    int stage;                   // 1: the block of operand 0 is staged in shared memory by bulk copies
 };
 
 // I (tile layout) x nf -> spectral: value = scale * FFT_x( sum_f coef_f * D_f[src_f] ), rows
@@ -448,6 +477,21 @@ k_xfwd(const XFwdArgs a) {
     }
     const size_t blk0 = (size_t)blockIdx.x * rpc * C + c;
     const int mg = m + a.sh.m_off;
+    // the x stencil reads every element of operand 0 twice (rows x-1, x+1): its block of this
+    // column tile is brought into the (still idle) exchange buffer by the copy engine -- one
+    // request for the whole block instead of four dependent groups of loads per thread
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(xc.buf + (size_t)F::XSLOTS * C);
+    if (SPLIT == 1 && a.stage) {
+        if (threadIdx.x == 0) mbar_init(bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(bar, (unsigned)(NF * C * sizeof(cplx)));
+            for (int x0 = 0; x0 < NF; x0 += rpc)
+                bulk_load(xc.buf + (size_t)x0 * C,
+                          a.src[0] + (size_t)(x0 >> a.sh.fwd_rshift) * a.sh.fwd_chunk + (size_t)blockIdx.x * rpc * C,
+                          (unsigned)(rpc * C * sizeof(cplx)), bar);
+        }
+    }
     for (int s = 0; s < SPLIT; ++s) {
         cplx v[16];
         MLV_UNROLL
@@ -481,6 +525,26 @@ k_xfwd(const XFwdArgs a) {
             if (SPLIT == 1 && sym == XSYM_FDX && a.order == 2 && f + 1 < a.nf && a.sym[f + 1] == XSYM_FDZ) {
                 const cplx* __restrict__ srcb = a.src[f + 1];
                 const double ci = sz * a.coef[f + 1], cw = cf * w1;
+                if (SPLIT == 1 && a.stage && f == 0) {
+                    // second operand straight from global memory (16 loads in flight per thread)
+                    // while the staged block arrives
+                    MLV_UNROLL
+                    for (int j = 0; j < 16; ++j) {
+                        const int x = tau + F::T * j;
+                        const cplx b = srcb[(size_t)(x >> rshift) * chunk + blk0 + (size_t)(x & (rpc - 1)) * C];
+                        v[j] = mk(fma(-ci, b.y, v[j].x), fma(ci, b.x, v[j].y));
+                    }
+                    mbar_wait(bar, 0);
+                    MLV_UNROLL
+                    for (int j = 0; j < 16; ++j) {
+                        const int x = tau + F::T * j;
+                        const cplx p = xc.buf[(size_t)((x + 1) & (NF - 1)) * C + c];
+                        const cplx q = xc.buf[(size_t)((x - 1) & (NF - 1)) * C + c];
+                        v[j] = mk(fma(cw, p.x - q.x, v[j].x), fma(cw, p.y - q.y, v[j].y));
+                    }
+                    ++f;
+                    continue;
+                }
                 MLV_UNROLL
                 for (int j0 = 0; j0 < 16; j0 += 4) {
                     MLV_SCHED_FENCE();
