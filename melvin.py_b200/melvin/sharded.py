@@ -46,6 +46,10 @@ from . import _backend, _capi
 
 
 class ShardedScalarStepper:
+    # exchange-buffer slots (fields) per direction, and fields actually moved per step
+    N_INV, N_FWD = 3, 2
+    MOVED_INV, MOVED_FWD = 3, 2
+
     def __init__(self, nx, nz, lx, lz, coef, dt, fd_order=2, ab_order=2, alpha=0.51,
                  cfl_cutoff=0.5, cfl_cadence=10, tracker_cadence=100, group=None, p2p=None):
         self.group = group
@@ -71,7 +75,7 @@ class ShardedScalarStepper:
         self.fwd_stride = self.world * self.fwd_field
         cplx = np.complex128
         # bytes this rank sends to its peers per step (3 inverse + 2 forward fields)
-        self.bytes_exchanged_per_step = 16 * (3 * self.inv_field + 2 * self.fwd_field) * (self.world - 1)
+        self.bytes_exchanged_per_step = 16 * (self.MOVED_INV * self.inv_field + self.MOVED_FWD * self.fwd_field) * (self.world - 1)
         mode = os.environ.get("MLV_EXCHANGE", "")
         if os.environ.get("MLV_NO_P2P"):
             mode = "a2a"
@@ -87,17 +91,17 @@ class ShardedScalarStepper:
         if mode == "p2p":
             # receive buffers live in peer-mapped memory; the producer kernels of every rank
             # store straight into them over NVLink (compute + exchange in one kernel)
-            self.inv_recv_ptr = self._setup_peers(0, 3 * self.inv_stride * 16)[self.rank]
-            self.fwd_recv_ptr = self._setup_peers(1, 2 * self.fwd_stride * 16)[self.rank]
+            self.inv_recv_ptr = self._setup_peers(0, self.N_INV * self.inv_stride * 16)[self.rank]
+            self.fwd_recv_ptr = self._setup_peers(1, self.N_FWD * self.fwd_stride * 16)[self.rank]
             self.inv_send_ptr, self.fwd_send_ptr = self.inv_recv_ptr, self.fwd_recv_ptr
             self._sync = _backend.zeros((1,), np.float64)
         elif mode == "dma":
             # peer-mapped receive buffers filled by copy engines from local send buffers
-            self.inv_peers = self._setup_peers(0, 3 * self.inv_stride * 16, register=False)
-            self.fwd_peers = self._setup_peers(1, 2 * self.fwd_stride * 16, register=False)
+            self.inv_peers = self._setup_peers(0, self.N_INV * self.inv_stride * 16, register=False)
+            self.fwd_peers = self._setup_peers(1, self.N_FWD * self.fwd_stride * 16, register=False)
             self.inv_recv_ptr, self.fwd_recv_ptr = self.inv_peers[self.rank], self.fwd_peers[self.rank]
-            self.inv_send = _backend.zeros((3, self.inv_stride), cplx)
-            self.fwd_send = _backend.zeros((2, self.fwd_stride), cplx)
+            self.inv_send = _backend.zeros((self.N_INV, self.inv_stride), cplx)
+            self.fwd_send = _backend.zeros((self.N_FWD, self.fwd_stride), cplx)
             self.inv_send_ptr, self.fwd_send_ptr = self.inv_send.data_ptr(), self.fwd_send.data_ptr()
             self._sync = _backend.zeros((1,), np.float64)
             # several copy streams: copies to different peers run on different copy engines
@@ -106,11 +110,11 @@ class ShardedScalarStepper:
             self._ev = [torch.cuda.Event() for _ in range(6)]
             self._join_ev = [torch.cuda.Event() for _ in self._copy_streams]
         else:
-            self.inv_send = _backend.zeros((3, self.inv_stride), cplx)
-            self.fwd_send = _backend.zeros((2, self.fwd_stride), cplx)
+            self.inv_send = _backend.zeros((self.N_INV, self.inv_stride), cplx)
+            self.fwd_send = _backend.zeros((self.N_FWD, self.fwd_stride), cplx)
             if self.world > 1:
-                self.inv_recv = _backend.zeros((3, self.inv_stride), cplx)
-                self.fwd_recv = _backend.zeros((2, self.fwd_stride), cplx)
+                self.inv_recv = _backend.zeros((self.N_INV, self.inv_stride), cplx)
+                self.fwd_recv = _backend.zeros((self.N_FWD, self.fwd_stride), cplx)
             else:
                 self.inv_recv, self.fwd_recv = self.inv_send, self.fwd_send
             self.inv_send_ptr, self.inv_recv_ptr = self.inv_send.data_ptr(), self.inv_recv.data_ptr()
@@ -126,17 +130,21 @@ class ShardedScalarStepper:
         if self.nchunks > 1:
             self.ctx.call("mlv_set_forward_blocks", self.chunk_rows, count=False)
         self.fwd_block = self.fwd_field // self.nchunks      # one row block of one peer and field
-        self.w = [_backend.zeros((self.rows, self.nml), cplx), _backend.zeros((self.rows, self.nml), cplx)]
         self.cur = 0
-        self.hist = _backend.zeros((self.order, self.rows, self.nml), cplx)
         self.hidx = 0
         self.red4 = _backend.zeros((4,), np.float64)
+        self._alloc_state()
         self.t = 0.0
         self.loop = 0
         self._cfl_counter = 0
         self._trk_counter = 0
         self.ke_times, self.ke = [], []
         self._prebuild()
+
+    def _alloc_state(self):
+        cplx = np.complex128
+        self.w = [_backend.zeros((self.rows, self.nml), cplx), _backend.zeros((self.rows, self.nml), cplx)]
+        self.hist = _backend.zeros((self.order, self.rows, self.nml), cplx)
 
     def _setup_peers(self, which, nbytes, register=True):
         """Allocate this rank's receive buffer, exchange CUDA IPC handles, open the peers'.
@@ -175,24 +183,13 @@ class ShardedScalarStepper:
     # ------------------------------------------------------------------ state
     def load_spectral(self, w_full):
         """Keep this rank's column slab of a full (2nn+1, nm) spectral array (host)."""
-        w_full = np.asarray(w_full)
-        slab = np.zeros((self.rows, self.nml), dtype=np.complex128)
-        n = self.nm_local
-        if n > 0:
-            slab[:, :n] = w_full[:, self.m_off:self.m_off + n]
-        self.w[self.cur].copy_(_backend.from_host(slab))
+        self.w[self.cur].copy_(self._slab_local(w_full))
         self.hist.zero_()
         self.hidx = 0
 
     def gather_spectral(self):
         """Full (2nn+1, nm) spectral state on the host of every rank."""
-        local = self.w[self.cur]
-        if self.world == 1:
-            return _backend.to_host(local)[:, : self.nm]
-        parts = [torch.empty_like(local) for _ in range(self.world)]
-        dist.all_gather([torch.view_as_real(p) for p in parts], torch.view_as_real(local), group=self.group)
-        full = np.concatenate([_backend.to_host(p) for p in parts], axis=1)
-        return full[:, : self.nm]
+        return self._gather(self.w[self.cur])
 
     # ------------------------------------------------------------------- step
     def _a2a(self, recv, send, f):
@@ -230,6 +227,103 @@ class ShardedScalarStepper:
             e.record(cs)
             comp.wait_event(e)
         dist.all_reduce(self._sync, group=self.group)
+
+    # ------------------------------------------------ generic exchange rounds (multi-field steppers)
+    def _slot(self, which, recv, slot):
+        base = {(0, 0): self.inv_send_ptr, (0, 1): self.inv_recv_ptr,
+                (1, 0): self.fwd_send_ptr, (1, 1): self.fwd_recv_ptr}[(which, int(recv))]
+        return base + 16 * slot * (self.inv_stride if which == 0 else self.fwd_stride)
+
+    def _slab_local(self, full):
+        """This rank's column slab of a full (2nn+1, nm) spectral array (host) as a device array."""
+        full = np.asarray(full)
+        slab = np.zeros((self.rows, self.nml), dtype=np.complex128)
+        if self.nm_local > 0:
+            slab[:, :self.nm_local] = full[:, self.m_off:self.m_off + self.nm_local]
+        return _backend.from_host(slab)
+
+    def _gather(self, local):
+        if self.world == 1:
+            return _backend.to_host(local)[:, : self.nm]
+        parts = [torch.empty_like(local) for _ in range(self.world)]
+        dist.all_gather([torch.view_as_real(p) for p in parts], torch.view_as_real(local), group=self.group)
+        return np.concatenate([_backend.to_host(p) for p in parts], axis=1)[:, : self.nm]
+
+    def _inverse_round(self, fields):
+        """fields: [(source spectral tensor, MLV_OP_*, inverse slot)].  Inverse x pass of every
+        field on the local columns, then row block h of every field at rank h."""
+        ctx, vp = self.ctx, ctypes.c_void_p
+        if self.mode == "dma" or not (self.world == 1 or self.p2p):
+            works = []
+            for i, (src, op, slot) in enumerate(fields):
+                ctx.call("mlv_x_inverse", 1, (vp * 1)(src.data_ptr()), (ctypes.c_int32 * 1)(op),
+                         (vp * 1)(self._slot(0, False, slot)))
+                if self.mode == "dma":
+                    self._dma(0, slot, self._ev[i % 3])
+                else:
+                    works.append(self._a2a(self.inv_recv, self.inv_send, slot))
+            if self.mode == "dma":
+                self._dma_join(self._ev[3])
+            for wk in works:
+                wk.wait()
+            return
+        # world 1 / peer stores: batches of up to 4 fields share the column stash of their source
+        for b in range(0, len(fields), 4):
+            grp = fields[b:b + 4]
+            n = len(grp)
+            ctx.call("mlv_x_inverse", n, (vp * n)(*[g[0].data_ptr() for g in grp]),
+                     (ctypes.c_int32 * n)(*[g[1] for g in grp]),
+                     (vp * n)(*[self._slot(0, False, g[2]) for g in grp]))
+        if self.world > 1:
+            dist.all_reduce(self._sync, group=self.group)
+
+    def _advect_round(self, jobs):
+        """jobs: [(inverse slots ux, uz, q, forward slots a, b, red4 tensor or None)].  Fused z
+        stage on the local rows, then tile block h of every forward field at rank h."""
+        ctx, vp = self.ctx, ctypes.c_void_p
+        chunked = self.mode == "dma" or not (self.world == 1 or self.p2p)
+        works = []
+        for (sux, suz, sq, fa, fb, red) in jobs:
+            args = (vp(self._slot(0, True, sux)), vp(self._slot(0, True, suz)), vp(self._slot(0, True, sq)),
+                    vp(self._slot(1, False, fa)), vp(self._slot(1, False, fb)))
+            redp = vp(red.data_ptr()) if red is not None else None
+            if not chunked:
+                ctx.call("mlv_advect_z", *args, redp)
+                continue
+            for c in range(self.nchunks):
+                ctx.call("mlv_advect_z_rows", *args, c * self.chunk_rows, self.chunk_rows,
+                         redp if c == self.nchunks - 1 else None)
+                if self.mode == "dma":
+                    for f in (fa, fb):
+                        self._dma(1, f, self._ev[c % 3], chunk=c if self.nchunks > 1 else None)
+            if self.mode != "dma":
+                works += [self._a2a(self.fwd_recv, self.fwd_send, f) for f in (fa, fb)]
+        if self.mode == "dma":
+            self._dma_join(self._ev[4])
+        elif not chunked and self.world > 1:
+            dist.all_reduce(self._sync, group=self.group)
+        for wk in works:
+            wk.wait()
+
+    def _forward(self, slots, coefs, lin, lcoef, q_in, q_out, hist, hidx):
+        """Forward x pass of the operand pairs in `slots` (d/dx, d/dz alternating) with the fused
+        right-hand side (lin = [(coef, MLV_OP_*, tensor)]), AB predictor and theta-scheme."""
+        d = _capi.XFwd()
+        d.nf, d.mode = len(slots), 1
+        for i, (sl, cf) in enumerate(zip(slots, coefs)):
+            d.src[i] = self._slot(1, True, sl)
+            d.sym[i] = _capi.SYM_FDX if i % 2 == 0 else _capi.SYM_FDZ
+            d.coef[i] = cf
+        d.lin = _capi.make_lin_terms([(c, op, t.data_ptr()) for (c, op, t) in lin])
+        g = d.integ
+        g.ab_order, g.scheme = self.order, _capi.SCHEME_SI_LAP
+        g.alpha, g.lcoef, g.dt = self.alpha, lcoef, self.dt
+        g.q_in, g.q_out = q_in.data_ptr(), q_out.data_ptr()
+        lv = [hist[(hidx - k) % self.order].data_ptr() for k in range(self.order)]
+        g.f0, g.fm1 = lv[0], lv[1]
+        if self.order == 4:
+            g.fm2, g.fm3 = lv[2], lv[3]
+        self.ctx.call("mlv_x_forward", ctypes.byref(d))
 
     def _prebuild(self):
         """ctypes argument blocks that do not change from step to step."""
@@ -348,4 +442,131 @@ class ShardedScalarStepper:
         if need_trk:                                   # calc_kinetic_energy (utility.py:42-59)
             self.ke_times.append(self.t)
             self.ke.append(0.5 * (sz + sx) / (self.nx * self.nz))
+            self._extra_trackers()
             self._trk_counter += self.tracker_cadence
+
+    def _extra_trackers(self):
+        pass
+
+
+class ShardedDoubleDiffusiveStepper(ShardedScalarStepper):
+    """Slab-decomposed form of the double-diffusive loop (BASELINE config 4;
+    examples/double_diffusive_convection.py:100-126): vorticity w, temperature tmp and
+    composition xi advected by the velocity of the *old* vorticity, coupling terms
+    Pr*(ddx xi - ddx tmp), -uz and -uz/R0 assembled in the epilogue of the forward x pass, the
+    script's fix-up `tmp[:, 0] = 0; xi[:, 0] = 0`, kinetic-energy and Nusselt trackers.
+    One exchange round per direction and step: 5 inverse fields, 6 forward fields."""
+    N_INV, N_FWD = 5, 6
+    MOVED_INV, MOVED_FWD = 5, 6
+
+    def __init__(self, nx, nz, lx, lz, Pr, R0, tau, dt, **kw):
+        self.Pr, self.R0, self.tau = float(Pr), float(R0), float(tau)
+        super().__init__(nx, nz, lx, lz, Pr, dt, **kw)
+
+    def _alloc_state(self):
+        cplx = np.complex128
+        mk = lambda: [_backend.zeros((self.rows, self.nml), cplx) for _ in range(2)]   # noqa: E731
+        self.q = {"w": mk(), "tmp": mk(), "xi": mk()}
+        self.h = {k: _backend.zeros((self.order, self.rows, self.nml), cplx) for k in self.q}
+        self.w = self.q["w"]
+        self.hist = self.h["w"]
+        self.nu, self._phys = [], None
+
+    def _prebuild(self):
+        pass
+
+    def load_spectral(self, w_full, tmp_full, xi_full):
+        for k, full in (("w", w_full), ("tmp", tmp_full), ("xi", xi_full)):
+            self.q[k][self.cur].copy_(self._slab_local(full))
+            self.h[k].zero_()
+        self.hidx = 0
+
+    def gather_spectral(self):
+        return tuple(self._gather(self.q[k][self.cur]) for k in ("w", "tmp", "xi"))
+
+    def step(self):
+        c, n = self.cur, 1 - self.cur
+        w, tmp, xi = (self.q[k][c] for k in ("w", "tmp", "xi"))
+        OP = _capi
+        # inverse slots: 0 w, 1 ux, 2 uz (all from the old vorticity), 3 tmp, 4 xi
+        self._inverse_round([(w, OP.OP_IDENT, 0), (w, OP.OP_UX, 1), (w, OP.OP_UZ, 2),
+                             (tmp, OP.OP_IDENT, 3), (xi, OP.OP_IDENT, 4)])
+        self._advect_round([(1, 2, 0, 0, 1, self.red4), (1, 2, 3, 2, 3, None), (1, 2, 4, 4, 5, None)])
+        Pr, R0, tau = self.Pr, self.R0, self.tau
+        self._forward((0, 1), (-1.0, -1.0), [(Pr, OP.OP_DDX, xi), (-Pr, OP.OP_DDX, tmp)], Pr,
+                      w, self.q["w"][n], self.h["w"], self.hidx)
+        self._forward((2, 3), (-1.0, -1.0), [(-1.0, OP.OP_UZ, w)], 1.0,
+                      tmp, self.q["tmp"][n], self.h["tmp"], self.hidx)
+        self._forward((4, 5), (-1.0, -1.0), [(-1.0 / R0, OP.OP_UZ, w)], tau,
+                      xi, self.q["xi"][n], self.h["xi"], self.hidx)
+        if self.m_off == 0 and self.nm_local > 0:      # the rank that owns the m = 0 column
+            self.q["tmp"][n][:, 0] = 0.0
+            self.q["xi"][n][:, 0] = 0.0
+        self.cur = n
+        self.hidx = (self.hidx + 1) % self.order
+        self.end_loop()
+
+    def _extra_trackers(self):
+        """Nusselt number 1 - mean(T_p uz_p) on this loop's (pre-update) fields
+        (examples/double_diffusive_convection.py:20-23): inverse z pass of the local rows."""
+        vp = ctypes.c_void_p
+        if self._phys is None:
+            self._phys = [_backend.zeros((self.nxl, self.nz), np.float64) for _ in range(2)]
+        for slot, out in ((3, self._phys[0]), (2, self._phys[1])):
+            self.ctx.call("mlv_z_inverse", vp(self._slot(0, True, slot)), vp(out.data_ptr()))
+        sm = (self._phys[0] * self._phys[1]).sum().reshape(1)
+        if self.world > 1:
+            dist.all_reduce(sm, group=self.group)
+        self.nu.append(1.0 - float(_backend.to_host(sm)[0]) / (self.nx * self.nz))
+
+
+class ShardedTearingStepper(ShardedScalarStepper):
+    """Slab-decomposed form of the resistive-tearing (MHD) loop (BASELINE config 5;
+    examples/resistive_tearing_instability.py:125-148): vorticity w and current j, velocity
+    from w and magnetic field from j, and the reference's ordering -- the j equation advects
+    the *updated* vorticity with the magnetic field.  Two exchange rounds per direction and
+    step: 6 + 1 inverse fields, 6 + 2 forward fields."""
+    N_INV, N_FWD = 7, 8
+    MOVED_INV, MOVED_FWD = 7, 8
+
+    def __init__(self, nx, nz, lx, lz, Re, S, dt, **kw):
+        self.Re, self.S = float(Re), float(S)
+        super().__init__(nx, nz, lx, lz, 1.0 / Re, dt, **kw)
+
+    def _alloc_state(self):
+        cplx = np.complex128
+        mk = lambda: [_backend.zeros((self.rows, self.nml), cplx) for _ in range(2)]   # noqa: E731
+        self.q = {"w": mk(), "j": mk()}
+        self.h = {k: _backend.zeros((self.order, self.rows, self.nml), cplx) for k in self.q}
+        self.w = self.q["w"]
+        self.hist = self.h["w"]
+
+    def _prebuild(self):
+        pass
+
+    def load_spectral(self, w_full, j_full):
+        for k, full in (("w", w_full), ("j", j_full)):
+            self.q[k][self.cur].copy_(self._slab_local(full))
+            self.h[k].zero_()
+        self.hidx = 0
+
+    def gather_spectral(self):
+        return tuple(self._gather(self.q[k][self.cur]) for k in ("w", "j"))
+
+    def step(self):
+        c, n = self.cur, 1 - self.cur
+        w, j = self.q["w"][c], self.q["j"][c]
+        w_new, j_new = self.q["w"][n], self.q["j"][n]
+        OP = _capi
+        # inverse slots: 0 w, 1 ux, 2 uz, 3 j, 4 bx, 5 bz, 6 updated w
+        self._inverse_round([(w, OP.OP_IDENT, 0), (w, OP.OP_UX, 1), (w, OP.OP_UZ, 2),
+                             (j, OP.OP_IDENT, 3), (j, OP.OP_UX, 4), (j, OP.OP_UZ, 5)])
+        # forward slots: (0,1) u.grad w, (2,3) b.grad j, (4,5) u.grad j, (6,7) b.grad w_new
+        self._advect_round([(1, 2, 0, 0, 1, self.red4), (4, 5, 3, 2, 3, None), (1, 2, 3, 4, 5, None)])
+        self._forward((0, 1, 2, 3), (-1.0, -1.0, 1.0, 1.0), [], 1.0 / self.Re, w, w_new, self.h["w"], self.hidx)
+        self._inverse_round([(w_new, OP.OP_IDENT, 6)])
+        self._advect_round([(4, 5, 6, 6, 7, None)])
+        self._forward((4, 5, 6, 7), (-1.0, -1.0, 1.0, 1.0), [], 1.0 / self.S, j, j_new, self.h["j"], self.hidx)
+        self.cur = n
+        self.hidx = (self.hidx + 1) % self.order
+        self.end_loop()

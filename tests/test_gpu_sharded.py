@@ -33,6 +33,22 @@ def test_sharded_step_nccl(case, mode):
     assert out.returncode == 0 and lines and lines[-1].endswith("OK"), out.stdout[-2000:] + out.stderr[-2000:]
 
 
+@pytest.mark.parametrize("mode", ["p2p", "dma", "a2a"])
+@pytest.mark.parametrize("case", ["ddc", "tearing"])
+def test_multi_field_steppers_nccl(case, mode):
+    """double-diffusive and MHD tearing loops slab-decomposed over 2 GPUs, every exchange mode,
+    vs the goldens of the unmodified reference"""
+    if _ngpu() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29702",
+           os.path.join(ROOT, "tests", "sharded_worker.py"), "cuda", case]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900,
+                         env=dict(os.environ, MLV_EXCHANGE=mode))
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("SHARDED")]
+    assert out.returncode == 0 and lines and lines[-1].endswith("OK"), out.stdout[-2000:] + out.stderr[-2000:]
+
+
 def test_single_rank_stepper_matches_python_api_path():
     """The rank-local stepper (world 1) against the golden: same kernels as the public API."""
     import numpy as np

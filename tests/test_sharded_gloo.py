@@ -40,8 +40,15 @@ def test_long_line_kernels_sharded():
     run_world(2, "khlong", 29612)
 
 
-@pytest.mark.parametrize("case", ["kh", "khlong"])
+@pytest.mark.parametrize("case", ["kh", "khlong", "tearing"])
 def test_forward_exchange_in_row_blocks(case):
     """forward buffers cut into row blocks, z stage launched block by block (the layout the
     copy-engine exchange pipelines on GPUs)"""
     run_world(2, case, 29613, MLV_FWD_CHUNKS="4")
+
+
+@pytest.mark.parametrize("case,world", [("ddc", 1), ("ddc", 2), ("tearing", 2), ("tearing", 4)])
+def test_multi_field_steppers(case, world):
+    """double-diffusive (3 coupled scalars) and MHD tearing (2 exchange rounds per step)
+    slab-decomposed, vs the goldens of the unmodified reference"""
+    run_world(world, case, 29620 + world)
