@@ -68,7 +68,7 @@ def byte_model(nx, nz):
 
 def measured_traffic(nx, nz):
     """DRAM bytes per launch from the committed ncu capture (same grid only), else None."""
-    path = os.path.join(ROOT, "profiles", "r01b_traffic.json")
+    path = os.path.join(ROOT, "profiles", "r01c_traffic.json")
     try:
         with open(path) as fp:
             d = json.load(fp)
