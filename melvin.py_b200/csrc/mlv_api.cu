@@ -43,7 +43,6 @@ struct mlv_ctx {
     double dx, dz;
     mlv::SpecConsts k;
     mlv::Plan planx, planz;
-    double* symx = nullptr;     // [nx]
     double* symz = nullptr;     // [nm]
     double* tri_cp = nullptr;   // FDM-z: (nn, nz)
     double* tri_inv = nullptr;
@@ -540,15 +539,6 @@ int mlv_create(const mlv_params* p, mlv_ctx** out) {
     if (!rc && !p->fdm_z) rc = make_plan(c->planz, c->planlz, c->stream);
     if (!rc && xsplit) rc = make_split_table(&c->tws_x, p->nx, c->stream);
     if (!rc && zreal) rc = make_split_table(&c->tws_z, p->nz, c->stream);
-    if (!rc) {
-        std::vector<double> sx(p->nx);
-        for (int kk = 0; kk < p->nx; ++kk) {
-            const long long n = kk <= p->nx / 2 ? kk : kk - p->nx;
-            sx[kk] = stencil_symbol(p->fd_order, n, p->nx, c->dx);
-        }
-        rc = rt_malloc((void**)&c->symx, sx.size() * sizeof(double));
-        if (!rc) rc = rt_h2d(c->symx, sx.data(), sx.size() * sizeof(double), c->stream);
-    }
     if (!rc && !p->fdm_z) {
         std::vector<double> sz(c->nm > 0 ? c->nm : 1);
         for (int m = 0; m < c->nm; ++m) sz[m] = stencil_symbol(p->fd_order, m, p->nz, c->dz);
@@ -592,7 +582,6 @@ int mlv_destroy(mlv_ctx* c) {
     if (c->planz.dev) rt_free(c->planz.dev);
     if (c->tws_x) rt_free(c->tws_x);
     if (c->tws_z) rt_free(c->tws_z);
-    if (c->symx) rt_free(c->symx);
     if (c->symz) rt_free(c->symz);
     if (c->tri_cp) rt_free(c->tri_cp);
     if (c->tri_inv) rt_free(c->tri_inv);

@@ -41,7 +41,7 @@ enum {
 // Multiplier symbols of the forward x pass epilogue.
 enum {
     XSYM_ONE = 0,
-    XSYM_FDX = 1,  // Fourier symbol of the central x stencil (order 2/4), table symx[k]
+    XSYM_FDX = 1,  // central x stencil (order 2/4), applied along the line before the transform
     XSYM_FDZ = 2,  // Fourier symbol of the central z stencil, table symz[m]
 };
 
