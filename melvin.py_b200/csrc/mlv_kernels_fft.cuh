@@ -658,6 +658,9 @@ k_xfwd(const XFwdArgs a) {
     }
 }
 
+// NaN-propagating maximum (numpy.max semantics)
+MLV_DEV double nan_max(double x, double y) { return (x != x || y != y) ? NAN : fmax(x, y); }
+
 // ===================================================================== z passes
 // Packed-pair element idx of the Hermitian-extended spectrum of two real rows
 // whose one-sided spectra are rowA, rowB (F4: Im of the m=0 bin is dropped):
@@ -965,7 +968,9 @@ k_z_advect(const ZAdvArgs a) {
                 const cplx q = stash[j * F::T];
                 v[j] = mk(v[j].x * q.x, v[j].y * q.y);
             }
-            rbuf[pass * NT + threadIdx.x] = valid ? mx : -INFINITY;
+            // fmax drops NaNs; the sum of squares does not: a NaN anywhere in the row makes the
+            // maximum NaN too, as numpy.max does (Integrator.py:41 tests np.isnan(cfl_dt))
+            rbuf[pass * NT + threadIdx.x] = valid ? (ss != ss ? NAN : mx) : -INFINITY;
             rbuf[(2 + pass) * NT + threadIdx.x] = valid ? ss : 0.0;
         }
         fft_line<LOG2N, false>(v, tau, a.tw, xc);
@@ -1009,14 +1014,14 @@ k_z_advect(const ZAdvArgs a) {
         const int w = threadIdx.x / G, g = threadIdx.x % G;
         if (w < 4) {
             double r = rbuf[w * NT + g];
-            for (int i = g + G; i < NT; i += G) r = (w < 2) ? fmax(r, rbuf[w * NT + i]) : r + rbuf[w * NT + i];
+            for (int i = g + G; i < NT; i += G) r = (w < 2) ? nan_max(r, rbuf[w * NT + i]) : r + rbuf[w * NT + i];
             rbuf[w * NT + g] = r;
         }
         for (int s2 = G / 2; s2 > 0; s2 >>= 1) {
             __syncthreads();
             if (w < 4 && g < s2) {
                 const double x = rbuf[w * NT + g], y = rbuf[w * NT + g + s2];
-                rbuf[w * NT + g] = (w < 2) ? fmax(x, y) : x + y;
+                rbuf[w * NT + g] = (w < 2) ? nan_max(x, y) : x + y;
             }
         }
         if (w < 4 && g == 0) a.red[(size_t)blockIdx.x * 4 + w] = rbuf[w * NT];

@@ -278,7 +278,7 @@ k_zr_advect(const ZAdvArgs a) {
                 const cplx q = stash[j * F::T];
                 v[j] = mk(v[j].x * q.x, v[j].y * q.y);
             }
-            rbuf[pass * NT + tau] = mx;
+            rbuf[pass * NT + tau] = ss != ss ? NAN : mx;      // NaN-propagating, see k_z_advect
             rbuf[(2 + pass) * NT + tau] = ss;
         }
         fft_line<LOG2H, false>(v, tau, a.tw, xc);
@@ -297,14 +297,14 @@ k_zr_advect(const ZAdvArgs a) {
         const int w = threadIdx.x / G, g = threadIdx.x % G;
         if (w < 4) {
             double r = rbuf[w * NT + g];
-            for (int i = g + G; i < NT; i += G) r = (w < 2) ? fmax(r, rbuf[w * NT + i]) : r + rbuf[w * NT + i];
+            for (int i = g + G; i < NT; i += G) r = (w < 2) ? nan_max(r, rbuf[w * NT + i]) : r + rbuf[w * NT + i];
             rbuf[w * NT + g] = r;
         }
         for (int s2 = G / 2; s2 > 0; s2 >>= 1) {
             __syncthreads();
             if (w < 4 && g < s2) {
                 const double p = rbuf[w * NT + g], q = rbuf[w * NT + g + s2];
-                rbuf[w * NT + g] = (w < 2) ? fmax(p, q) : p + q;
+                rbuf[w * NT + g] = (w < 2) ? nan_max(p, q) : p + q;
             }
         }
         if (w < 4 && g == 0) a.red[(size_t)blockIdx.x * 4 + w] = rbuf[w * NT];

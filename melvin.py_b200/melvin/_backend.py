@@ -10,6 +10,7 @@ the host *emulation* build of the kernels; product code never does that.)
 """
 import ctypes
 import os
+import weakref
 
 import numpy as np
 import torch
@@ -97,7 +98,15 @@ def empty(shape, dtype):
 
 
 def zeros(shape, dtype):
-    return torch.zeros(tuple(shape), dtype=torch_dtype(dtype), device=device())
+    """Zero-filled device buffer; the fill is the library's own kernel (mlv_elementwise)."""
+    t = empty(shape, dtype)
+    if t.numel():
+        if t.is_complex() or t.is_floating_point():
+            from . import b200
+            b200._elementwise(_capi.EW_COPY, 0.0, None, out=t)
+        else:
+            t.zero_()
+    return t
 
 
 def from_host(arr, dtype=None):
@@ -148,12 +157,19 @@ class Context:
         self._ipool = []
         self._scratch_i = None
         self._red4 = None
+        self._lazy_exprs = weakref.WeakSet()     # live deferred expressions (b200.SpecExpr)
+        self._stream = None
         self.set_stream(current_stream_handle())
 
     def set_stream(self, handle):
-        self.call("mlv_set_stream", ctypes.c_void_p(handle), count=False)
+        _capi.check(self.lib, self.lib.mlv_set_stream(self.handle, ctypes.c_void_p(handle)))
+        self._stream = handle
 
     def call(self, name, *args, count=True):
+        # kernels run on torch's *current* stream, like the allocations and copies around them
+        stream = current_stream_handle()
+        if stream != self._stream:
+            self.set_stream(stream)
         _capi.check(self.lib, getattr(self.lib, name)(self.handle, *args))
         if count:
             _state["launches"] += 1
@@ -192,9 +208,8 @@ def context_for(params):
     fdm_z = params.discretisation[1] == "fdm"
     if params.discretisation[0] == "fdm":
         raise NotImplementedError("Finite difference not implemented in x direction")
-    if getattr(params, "precision", "double") != "double":
-        raise NotImplementedError(
-            "melvin-b200 computes in float64/complex128 only (precision='double')")
+    if getattr(params, "precision", "double") not in ("double", "single"):
+        raise NotImplementedError("precision must be 'double' or 'single' (promoted to double)")
     key = (int(params.nx), int(params.nz), float(params.lx), float(params.lz), fdm_z,
            int(params.spatial_derivative_order), str(device()))
     ctx = _contexts.get(key)

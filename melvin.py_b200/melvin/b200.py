@@ -55,16 +55,25 @@ class DeviceArray:
     __array_priority__ = 1000
     __array_ufunc__ = None          # make NumPy scalars defer to our reflected operators
 
-    def __init__(self, tensor):
+    def __init__(self, tensor, base=None, idx=None):
         self._t = tensor
+        # a view keeps its parent: reads and in-place writes through the view go through the
+        # parent's hooks (deferred definitions, dependants), and the view follows the parent
+        # when a Variable re-points its state buffer (double buffering)
+        self._base = base
+        self._idx = idx
 
     # -- hooks for lazily materialised subclasses
     def _touch(self):
         """Called before the data is read or written in place."""
+        if self._base is not None:
+            self._t = self._base._touch()._t[self._idx]
         return self
 
     def _pre_write(self):
         """Called before the data is modified in place."""
+        if self._base is not None:
+            self._base._pre_write()
 
     # -- metadata
     @property
@@ -120,7 +129,8 @@ class DeviceArray:
     # -- views
     def __getitem__(self, idx):
         self._touch()
-        return DeviceArray(self._t[idx])
+        tracked = self._base is not None or type(self) is not DeviceArray
+        return DeviceArray(self._t[idx], self if tracked else None, idx if tracked else None)
 
     def __setitem__(self, idx, value):
         self._touch()
@@ -389,6 +399,28 @@ fft = _FFT()
 
 
 # ================================================================ SpecExpr
+def _frozen(a):
+    """Plain array on the buffer `a` occupies now (materialising a deferred definition)."""
+    if type(a) is DeviceArray and a._base is None:
+        return a
+    return DeviceArray(a._touch()._t)
+
+
+def _eval_terms(ctx, terms, out_t, accumulate):
+    """out (+)= sum_i c_i op_i(a_i), four operands per launch."""
+    terms = list(terms)
+    first = not accumulate
+    while terms:
+        room = 4 if first else 3
+        chunk, terms = terms[:room], terms[room:]
+        packed = [(c, op, a._touch()._t.data_ptr()) for c, op, a in chunk]
+        if not first:
+            packed.append((1.0, _capi.OP_IDENT, out_t.data_ptr()))
+        lt = _capi.make_lin_terms(packed)
+        ctx.call("mlv_spec_lincomb", ctypes.byref(lt), ctypes.c_void_p(out_t.data_ptr()))
+        first = False
+
+
 class NLTerm:
     """Handle on the z-spectra (IA, IB) of the products ux*q, uz*q produced by the
     fused physical-space stage; consumed by the forward x pass."""
@@ -411,8 +443,29 @@ class SpecExpr:
 
     def __init__(self, ctx, terms=(), nls=()):
         self.ctx = ctx
-        self.terms = list(terms)      # (complex coef, op code, DeviceArray)
+        # (complex coef, op code, DeviceArray).  Operands are captured as plain arrays on the
+        # buffer they live in *now*: the expression is registered with the context so that
+        # whoever is about to overwrite that buffer evaluates the affected terms first
+        # (the reference evaluates right-hand sides eagerly; see Variable._flush_dependants)
+        self.terms = [(c, op, _frozen(a)) for c, op, a in terms]
         self.nls = list(nls)          # (float coef, NLTerm)
+        if self.terms:
+            ctx._lazy_exprs.add(self)
+
+    def _reads(self, tensor):
+        ptr = tensor.data_ptr()
+        return any(a._t.data_ptr() == ptr for _, _, a in self.terms)
+
+    def _detach_from(self, tensor):
+        """`tensor` is about to change: evaluate the terms that read it into a private buffer."""
+        ptr = tensor.data_ptr()
+        hit = [t for t in self.terms if t[2]._t.data_ptr() == ptr]
+        if not hit:
+            return
+        tmp = _backend.empty(self.ctx.spec_shape, np.complex128)
+        _eval_terms(self.ctx, hit, tmp, False)
+        self.terms = [t for t in self.terms if t[2]._t.data_ptr() != ptr]
+        self.terms.append((1.0 + 0j, _capi.OP_IDENT, DeviceArray(tmp)))
 
     # -- metadata
     @property
@@ -503,17 +556,9 @@ class SpecExpr:
                 ctx.call("mlv_x_forward", ctypes.byref(d))
                 terms.append((1.0 + 0j, _capi.OP_IDENT, DeviceArray(tmp)))
         if not terms and first:
-            out_t.zero_()
+            out[...] = 0.0
             return out
-        while terms:
-            room = 4 if first else 3
-            chunk, terms = terms[:room], terms[room:]
-            packed = [(c, op, a._touch()._t.data_ptr()) for c, op, a in chunk]
-            if not first:
-                packed.append((1.0, _capi.OP_IDENT, out_t.data_ptr()))
-            lt = _capi.make_lin_terms(packed)
-            ctx.call("mlv_spec_lincomb", ctypes.byref(lt), ctypes.c_void_p(out_t.data_ptr()))
-            first = False
+        _eval_terms(ctx, terms, out_t, not first)
         return out
 
     # -- array-like fallbacks

@@ -22,7 +22,7 @@ import weakref
 import numpy as np
 
 from . import _backend, _capi
-from .b200 import DeviceArray, LazyLap, NLTerm, SpecExpr
+from .b200 import DeviceArray, LazyLap, NLTerm, SpecExpr, _frozen
 from .basis import BasisFunctions
 
 _I_NONE, _I_PENDING, _I_VALID = 0, 1, 2
@@ -38,14 +38,14 @@ class _SpecHandle(DeviceArray):
 
     def _touch(self):
         o = self._owner()
-        if o is not None and o._s is self:
+        if o is not None:
             o._materialize_s()
         return self
 
     def _pre_write(self):
         o = self._owner()
         if o is not None:
-            o._flush_dependants(self)
+            o._flush_dependants(self._t)
 
 
 class _PhysHandle(DeviceArray):
@@ -87,10 +87,12 @@ class Variable:
         self._fused = (not self._ctx.fdm_z
                        and basis_functions[0] is BasisFunctions.COMPLEX_EXP
                        and basis_functions[1] is BasisFunctions.COMPLEX_EXP)
+        # ONE handle per Variable for its whole life (gets() / _sdata always return it, as the
+        # reference returns the same ndarray); double buffering re-points its tensor
         self._s = _SpecHandle(_backend.zeros(params.spectral_shape, np.complex128), self)
-        self._s_spare = None                 # second state buffer (double buffering)
+        self._s_spare = None                 # second state tensor (double buffering)
         self._p = _PhysHandle(_backend.zeros(params.physical_shape, np.float64), self)
-        self._virt = None                    # (op, DeviceArray): deferred spectral definition
+        self._virt = None                    # (op, frozen DeviceArray): deferred spectral definition
         self._i = None                       # torch tensor (nx, ipitch) complex128
         self._i_state = _I_NONE
         self._i_def = None                   # (op, DeviceArray) the pending x pass reads
@@ -106,20 +108,28 @@ class Variable:
             self._ctx._lazy_vars = reg
         return reg
 
-    def _depends_on(self, handle):
-        return ((self._virt is not None and self._virt[1] is handle)
-                or (self._i_state == _I_PENDING and self._i_def[1] is handle))
+    # Pending work (deferred definitions, requested transforms, deferred right-hand sides) reads
+    # the *tensor* it was defined on.  Whoever overwrites a tensor flushes its dependants first,
+    # so every read returns what the reference's eager evaluation would have returned.
+    def _depends_on(self, tensor):
+        ptr = tensor.data_ptr()
+        return ((self._virt is not None and self._virt[1]._t.data_ptr() == ptr)
+                or (self._i_state == _I_PENDING and self._i_def[1]._t.data_ptr() == ptr))
 
-    def _flush_dependants(self, handle):
-        """`handle`'s buffer is about to change in place."""
+    def _flush_dependants(self, tensor):
+        """`tensor` is about to change in place."""
+        ptr = tensor.data_ptr()
         for v in list(self._ctx_vars()):
-            if v._i_state == _I_PENDING and v._i_def[1] is handle:
+            if v._i_state == _I_PENDING and v._i_def[1]._t.data_ptr() == ptr:
                 v._ensure_i()
-            if v._virt is not None and v._virt[1] is handle:
+            if v._virt is not None and v._virt[1]._t.data_ptr() == ptr:
                 v._materialize_s()
+        for e in list(self._ctx._lazy_exprs):
+            e._detach_from(tensor)
 
-    def _has_dependants(self, handle):
-        return any(v._depends_on(handle) for v in self._ctx_vars())
+    def _has_dependants(self, tensor, exclude=None):
+        return (any(v._depends_on(tensor) for v in self._ctx_vars())
+                or any(e is not exclude and e._reads(tensor) for e in list(self._ctx._lazy_exprs)))
 
     # ---------------------------------------------------- spectral storage
     @property
@@ -140,16 +150,16 @@ class Variable:
             return
         op, src = self._virt
         self._virt = None
-        lt = _capi.make_lin_terms([(1.0, op, src._touch()._t.data_ptr())])
+        lt = _capi.make_lin_terms([(1.0, op, src._t.data_ptr())])
         self._ctx.call("mlv_spec_lincomb", ctypes.byref(lt), ctypes.c_void_p(self._s._t.data_ptr()))
 
     def _set_virtual(self, op, src):
         """Spectral data := op(src) without writing it (fully spectral mode)."""
-        self._flush_dependants(self._s)
-        self._virt = (op, src)
+        self._flush_dependants(self._s._t)
+        self._virt = (op, _frozen(src))
 
     def _spec_def(self):
-        return self._virt if self._virt is not None else (_capi.OP_IDENT, self._s)
+        return self._virt if self._virt is not None else (_capi.OP_IDENT, DeviceArray(self._s._t))
 
     def __setitem__(self, index, value):
         self._materialize_s()
@@ -165,11 +175,11 @@ class Variable:
     def sets(self, data):
         """Setter for spectral data"""
         if isinstance(data, SpecExpr):
-            self._flush_dependants(self._s)
+            self._flush_dependants(self._s._t)
             self._virt = None
             data.materialize(out=DeviceArray(self._s._t))
             return
-        self._flush_dependants(self._s)
+        self._flush_dependants(self._s._t)
         self._virt = None
         self._s[:, :] = data[:, :]
 
@@ -227,7 +237,7 @@ class Variable:
 
     def to_spectral(self):
         """Convert physical data to spectral"""
-        self._flush_dependants(self._s)
+        self._flush_dependants(self._s._t)
         self._virt = None
         self._st.to_spectral(self._p, DeviceArray(self._s._t), self._basis_functions)
 
@@ -367,7 +377,7 @@ def _run_x_inverse(ctx, variables):
             op, src = v._i_def
             if v._i is None:
                 v._i = _backend.empty((ctx.nx, ctx.ipitch), np.complex128)
-            srcs[k] = src._touch()._t.data_ptr()
+            srcs[k] = src._t.data_ptr()
             ops[k] = op
             dsts[k] = v._i.data_ptr()
         ctx.call("mlv_x_inverse", n, srcs, ops, dsts)

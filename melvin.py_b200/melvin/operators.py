@@ -38,8 +38,13 @@ def _dev(x, dtype=None):
 
 
 def _contig(a):
+    """Contiguous tensor holding `a` (strided views are packed by mlv_elementwise)."""
     t = a._touch()._t
-    return t if t.is_contiguous() else t.contiguous()
+    if t.is_contiguous():
+        return t
+    packed = DeviceArray(_backend.empty(tuple(t.shape), a.dtype))
+    packed[...] = a
+    return packed._t
 
 
 class ArrayFactory:
@@ -390,25 +395,26 @@ class Integrator:
         is_var = isinstance(var, Variable)
         if is_var:
             var._materialize_s()
-            q_in = var._s
-            double = var._has_dependants(q_in)
+            q_in = var._s._t
+            # somebody (psi/ux/uz, a requested transform, another deferred right-hand side)
+            # still reads the old state: write the new one into the second buffer
+            double = var._has_dependants(q_in, exclude=pending)
             if double:
                 if var._s_spare is None:
-                    from .fields import _SpecHandle
-                    var._s_spare = _SpecHandle(_backend.empty(q_in.shape, np.complex128), var)
+                    var._s_spare = _backend.empty(tuple(q_in.shape), np.complex128)
                 q_out = var._s_spare
                 var._flush_dependants(q_out)
             else:
                 q_out = q_in
         else:
-            q_in = q_out = var._touch()
             double = False
             var._pre_write()
+            q_in = q_out = var._touch()._t
         g = _capi.Integ()
         g.ab_order, g.scheme = order, scheme
         g.dt, g.alpha, g.lcoef = float(self._dt), float(getattr(self, "_alpha", 0.0)), float(lcoef)
         g.larr = larr._t.data_ptr() if larr is not None else None
-        g.q_in, g.q_out = q_in._t.data_ptr(), q_out._t.data_ptr()
+        g.q_in, g.q_out = q_in.data_ptr(), q_out.data_ptr()
         g.f0, g.fm1 = f0.data_ptr(), older[0].data_ptr()
         if order == 4:
             g.fm2, g.fm3 = older[1].data_ptr(), older[2].data_ptr()
@@ -434,7 +440,7 @@ class Integrator:
             ctx.call("mlv_integrate", ctypes.byref(lt) if lin else None, ctypes.byref(g))
         del keep
         if double:
-            var._s, var._s_spare = q_out, q_in
+            var._s._t, var._s_spare = q_out, q_in       # the handle object never changes
         dvar.advance()
 
     def _explicit(self, var, dvar, diffusion_term):

@@ -205,3 +205,26 @@ def test_rbc_fdm_loop_matches_golden(order, ab):
         for nm in ("w", "tmp", "psi"):
             assert rel(out[f"{nm}_step{k}"], gl[f"{nm}_step{k}"]) < 1e-10, (nm, k)
     np.testing.assert_allclose(out["ke"], gl["ke"][:10], rtol=1e-9)
+
+
+# ---- orderings that only work if deferred work tracks the buffers it reads
+@pytest.mark.parametrize("inplace_write", [False, True])
+def test_rhs_assigned_before_its_source_changes(inplace_write):
+    import aliasing_cases as ac
+    got, want = ac.swapped_integrate_order(inplace_write=inplace_write)
+    for k in want:
+        assert rel(got[k], want[k]) < 1e-12, k
+
+
+def test_augmented_assignment_and_view_writes_flush_dependants():
+    import aliasing_cases as ac
+    got, want = ac.augmented_assignment_after_velocity()
+    for k in want:
+        assert rel(got[k], want[k]) < 1e-12, k
+
+
+def test_held_handle_stays_current():
+    import aliasing_cases as ac
+    same, rows_ok, col0 = ac.held_handle_stays_current()
+    assert all(same) and all(rows_ok)
+    assert np.all(col0 == 0.0)
