@@ -244,15 +244,18 @@ class Variable:
     def load(self, data, is_physical=False):
         if isinstance(data, str):
             raise NotImplementedError
-        data = self._dt.from_host(data)
         if is_physical:
-            self.setp(data)
+            self.setp(self._dt.from_host(data))
             self.to_spectral()
         else:
+            # the reference compares data.shape with (nn, nm), which never matches, and always
+            # takes the (complex-discarding) scaling route (Variable.py:82); here a
+            # state of the right shape is loaded as it is and any other resolution is re-sampled
+            # in spectral space, on the host for host data (one upload of the final size)
             nn, nm = self._params.nn, self._params.nm
-            if tuple(data.shape) != (nn, nm):
-                data = scale_variable(data, (nn, nm), self._xp)
-            self.sets(data)
+            if tuple(data.shape) != (2 * nn + 1, nm):
+                data = scale_variable(data, (nn, nm), np if isinstance(data, np.ndarray) else self._xp)
+            self.sets(self._dt.from_host(data))
 
     # ------------------------------------------------------ derivatives
     def pddx(self):
@@ -390,12 +393,15 @@ def scale_variable(var, outsize, xp):
     """Scale an array in spectral space from its size to `outsize` (nn, nm)
     (reference melvin/Variable.py:142-151, but complex-preserving: the reference
     allocates a real buffer here)."""
-    insize = var.shape
+    insize = var.shape                       # (2 nn_in + 1, nm_in)
     outvar = xp.zeros((2 * outsize[0] + 1, outsize[1]), dtype=np.complex128)
-    nx_min = min(insize[0], outsize[0])
+    # the reference takes insize[0] (= 2 nn_in + 1 rows) for the mode count nn_in, which mixes
+    # positive and negative modes whenever the resolutions differ; use the real count
+    nx_min = min((insize[0] - 1) // 2, outsize[0])
     nz_min = min(insize[1], outsize[1])
     outvar[: nx_min + 1, :nz_min] = var[: nx_min + 1, :nz_min]
-    outvar[-nx_min:, :nz_min] = var[-nx_min:, :nz_min]
+    if nx_min > 0:
+        outvar[-nx_min:, :nz_min] = var[-nx_min:, :nz_min]
     return outvar
 
 
@@ -471,7 +477,7 @@ class TimeDerivative:
         for i in range(self._params.integrator_order):
             level = data[i]
             if tuple(level.shape) != (2 * nn + 1, nm):
-                level = scale_variable(level, (nn, nm), self._xp)
+                level = scale_variable(level, (nn, nm), np if isinstance(level, np.ndarray) else self._xp)
             self._store[i][...] = level
 
     def get_name(self):

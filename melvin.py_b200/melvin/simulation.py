@@ -205,7 +205,7 @@ class Simulation:
         """Restart from a dump (Simulation.py:183-197; works here)."""
         arrays = np.load(self.form_dumpname(index), allow_pickle=True)
         for var in self._dump_vars:
-            var.sets(self._data_trans.from_host(arrays[var._dump_name]))
+            var.load(arrays[var._dump_name])          # re-sampled if the resolution changed
         for dvar in self._dump_dvars:
             dvar.load(arrays[dvar._dump_name])
             dvar.set_curr_idx(int(arrays["curr_idx"]))

@@ -144,6 +144,12 @@ def case_fused_advection_step(H, nx, nz, order, tol=1e-13):
     ctx.call("mlv_x_forward", ctypes.byref(d))
     assert rel(f0, f0_want) < tol
     assert rel(w_new, w_want) < tol
+    # a NaN anywhere in a velocity makes its CFL maximum NaN, as numpy.max does
+    # (Integrator.py:41 tests np.isnan(cfl_dt)); the other component is untouched
+    Iux[nx // 2 + 1, 1] = np.nan
+    ctx.call("mlv_advect_z", H.ptr(Iux), H.ptr(Iuz), H.ptr(Iq), H.ptr(IA), H.ptr(IB), H.ptr(red))
+    assert np.isnan(red[0]) and np.isnan(red[2])
+    np.testing.assert_allclose(red[1], vel["uz_p"].max(), rtol=1e-13)
     ctx.close()
 
 

@@ -228,3 +228,29 @@ def test_held_handle_stays_current():
     same, rows_ok, col0 = ac.held_handle_stays_current()
     assert all(same) and all(rows_ok)
     assert np.all(col0 == 0.0)
+
+
+# ---- restart and the Adams-Moulton formulas (a14)
+def test_restart_roundtrip_is_bit_exact():
+    import host_cases as hc
+    (lb, la), wb, wa = hc.restart_roundtrip()
+    assert lb == la and np.array_equal(wb, wa)
+
+
+@pytest.mark.parametrize("n_from,n_to", [(64, 128), (64, 32)])
+def test_restart_at_a_different_resolution(n_from, n_to):
+    import host_cases as hc
+    w_old, h_old, w_new, h_new, meta, ok = hc.restart_resolution_change(n_from, n_to)
+    nn, nm = (n_to - 1) // 3, (n_to - 1) // 3
+    assert np.array_equal(w_new, hc.expected_rescale(w_old, nn, nm))
+    for k in range(h_old.shape[0]):
+        assert np.array_equal(h_new[k], hc.expected_rescale(h_old[k], nn, nm))
+    assert meta[0] == 3 and meta[2] == meta[3] and ok
+    assert np.linalg.norm(w_new) > 0
+
+
+@pytest.mark.parametrize("order", [2, 4])
+def test_adams_moulton_corrector_formulas(order):
+    import host_cases as hc
+    got_c, want_c, got_p, want_p = hc.corrector_formulas(order)
+    assert rel(got_c, want_c) < 1e-14 and rel(got_p, want_p) < 1e-14

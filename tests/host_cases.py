@@ -1,0 +1,105 @@
+"""Host-logic cases shared by the emulation (CPU) and the GPU test modules: restart from the
+reference's dump format (same and changed resolution) and the Adams-Moulton
+corrector formulas (reference melvin/Integrator.py:20-33; dead code there)."""
+from functools import partial
+
+import numpy as np
+
+import parity_cases as pc
+from melvin import b200 as xp
+from melvin.utility import calc_kinetic_energy, calc_velocity_from_vorticity
+from oracle import melvin_oracle as mo
+
+
+def _build(n, lx, lz, order=2):
+    d = pc.base_params(n, n, lx, lz, initial_dt=1e-3, nu=0.25, integrator_order=order)
+    p, sim, (w,), (dw,), psi, ux, uz = pc.make_sim(d, ["w"], ["dw"], [pc.CE, pc.CE])
+    sim.config_dump([w], [dw])
+    sim.config_scalar_trackers({"ke": partial(calc_kinetic_energy, ux, uz, xp, p)})
+    return p, sim, w, dw, psi, ux, uz
+
+
+def _step(p, sim, w, dw, psi, ux, uz):
+    calc_velocity_from_vorticity(w, psi, ux, uz, sim.get_laplacian_solver())
+    dw[:] = -w.vec_dot_nabla(ux.getp(), uz.getp())
+    sim._integrator.integrate(w, dw, p.nu * w.lap())
+    sim.end_loop()
+
+
+def restart_roundtrip():
+    """dump after 5 steps, run 5 more; a fresh simulation loaded from the dump and stepped 5
+    times must hold bit-identical state."""
+    g = mo.Grid(64, 64, 2 * np.pi, 2 * np.pi)
+    with pc.scratch_cwd():
+        a = _build(64, g.lx, g.lz)
+        a[2].load(mo.ic_taylor_green(g) + 0.1 * mo.ic_noise(g, 1.0, 3), is_physical=True)
+        for _ in range(5):
+            _step(*a)
+        a[1].dump(a[1]._dump_ticker)
+        idx = a[1]._dump_ticker.times_fired
+        for _ in range(5):
+            _step(*a)
+        b = _build(64, g.lx, g.lz)
+        b[1].load(idx)
+        for _ in range(5):
+            _step(*b)
+        return (b[1]._loop_counter, a[1]._loop_counter), pc.host(b[2][:]), pc.host(a[2][:])
+
+
+def restart_resolution_change(n_from=64, n_to=128):
+    """A dump written at n_from^2 is loaded into a simulation at n_to^2: state and history are
+    re-sampled in spectral space (modes common to both grids are kept, signed-mode aware)."""
+    g = mo.Grid(n_from, n_from, 2 * np.pi, 2 * np.pi)
+    rng = np.random.default_rng(5)
+    with pc.scratch_cwd():
+        a = _build(n_from, g.lx, g.lz)
+        a[2].load(mo.ic_taylor_green(g) + rng.standard_normal(g.physical_shape), is_physical=True)
+        for _ in range(3):
+            _step(*a)
+        a[1].dump(a[1]._dump_ticker)
+        idx = a[1]._dump_ticker.times_fired
+        w_old, h_old = pc.host(a[2][:]), pc.host(a[3].get_all())
+        b = _build(n_to, g.lx, g.lz)
+        b[1].load(idx)
+        w_new, h_new = pc.host(b[2][:]), pc.host(b[3].get_all())
+        meta = (b[1]._loop_counter, float(b[1]._t), b[3].get_curr_idx(), a[3].get_curr_idx())
+        _step(*b)                                   # and it keeps running
+        ok = bool(np.all(np.isfinite(pc.host(b[2][:]))))
+    return w_old, h_old, w_new, h_new, meta, ok
+
+
+def expected_rescale(old, nn_new, nm_new):
+    """Signed-mode re-sampling of a (2nn+1, nm) spectrum (NumPy statement of the intent of
+    reference melvin/Variable.py:142-151)."""
+    nn_old, nm_old = (old.shape[0] - 1) // 2, old.shape[1]
+    out = np.zeros((2 * nn_new + 1, nm_new), dtype=np.complex128)
+    k, m = min(nn_old, nn_new), min(nm_old, nm_new)
+    for n in range(-k, k + 1):
+        out[n if n >= 0 else n + 2 * nn_new + 1, :m] = old[n if n >= 0 else n + 2 * nn_old + 1, :m]
+    return out
+
+
+def corrector_formulas(order):
+    """Integrator.corrector(dvar) for AB/AM order 2 and 4 against the formulas of
+    Integrator.py:20-33 evaluated with NumPy on the same history."""
+    rng = np.random.default_rng(order)
+    with pc.scratch_cwd():
+        p, sim, w, dw, psi, ux, uz = _build(32, 2 * np.pi, 2 * np.pi, order=order)
+        levels = []
+        for k in range(order):
+            lv = rng.standard_normal(p.spectral_shape) + 1j * rng.standard_normal(p.spectral_shape)
+            dw[:] = lv
+            levels.append(lv)
+            if k < order - 1:
+                dw.advance()
+        dt = sim._integrator._dt
+        got_c = pc.host(sim._integrator.corrector(dw))
+        got_p = pc.host(sim._integrator.predictor(dw))
+    f = levels[::-1]                                  # f[0] newest
+    if order == 2:
+        want_c = dt / 2 * (f[0] + f[1])
+        want_p = dt / 2 * (3 * f[0] - f[1])
+    else:
+        want_c = dt / 24 * (9 * f[0] + 19 * f[1] - 5 * f[2] + f[3])
+        want_p = dt / 24 * (55 * f[0] - 59 * f[1] + 37 * f[2] - 9 * f[3])
+    return got_c, want_c, got_p, want_p

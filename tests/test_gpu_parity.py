@@ -329,9 +329,10 @@ def test_edge_cases_and_errors():
     from melvin import _backend, _capi
     with pytest.raises(_capi.MlvError):           # non power-of-two transform axis
         Simulation(Parameters({"nx": 48, "nz": 64, "lx": 1.0, "lz": 1.0, "final_time": 1.0}), xp)
-    with pytest.raises(NotImplementedError):      # single precision is not provided
-        Simulation(Parameters({"nx": 64, "nz": 64, "lx": 1.0, "lz": 1.0, "final_time": 1.0,
-                               "precision": "single"}), xp)
+    with pytest.warns(UserWarning, match="computed in float64"):   # "single" is promoted
+        ps = Parameters({"nx": 64, "nz": 64, "lx": 1.0, "lz": 1.0, "final_time": 1.0,
+                         "precision": "single"})
+    assert Simulation(ps, xp).make_variable("w", [pc.CE, pc.CE]).gets().dtype == np.complex128
     with pytest.raises(_backend.BackendUnavailable):
         Simulation(Parameters({"nx": 64, "nz": 64, "lx": 1.0, "lz": 1.0, "final_time": 1.0}), np)
     # smallest grid, odd FDM nz (the reference's own RBC example uses nz=13)
@@ -356,36 +357,47 @@ def test_edge_cases_and_errors():
 def test_dump_and_restart_roundtrip():
     """Checkpoint written in the reference's dump format restarts bit-exactly
     (the reference's own load() is broken)."""
-    from functools import partial
-    from melvin import b200 as xp
-    from melvin.utility import calc_kinetic_energy, calc_velocity_from_vorticity
-    g = mo.Grid(64, 64, 2 * np.pi, 2 * np.pi)
+    import host_cases as hc
+    (lb, la), wb, wa = hc.restart_roundtrip()
+    assert lb == la and np.array_equal(wb, wa)
 
-    def build():
-        d = pc.base_params(64, 64, g.lx, g.lz, initial_dt=1e-3, nu=0.25)
-        p, sim, (w,), (dw,), psi, ux, uz = pc.make_sim(d, ["w"], ["dw"], [pc.CE, pc.CE])
-        sim.config_dump([w], [dw])
-        sim.config_scalar_trackers({"ke": partial(calc_kinetic_energy, ux, uz, xp, p)})
-        return p, sim, w, dw, psi, ux, uz
 
-    def step(p, sim, w, dw, psi, ux, uz):
-        calc_velocity_from_vorticity(w, psi, ux, uz, sim.get_laplacian_solver())
-        dw[:] = -w.vec_dot_nabla(ux.getp(), uz.getp())
-        sim._integrator.integrate(w, dw, p.nu * w.lap())
-        sim.end_loop()
+@pytest.mark.parametrize("n_from,n_to", [(64, 128), (64, 32)])
+def test_restart_at_a_different_resolution(n_from, n_to):
+    import host_cases as hc
+    w_old, h_old, w_new, h_new, meta, ok = hc.restart_resolution_change(n_from, n_to)
+    nn, nm = (n_to - 1) // 3, (n_to - 1) // 3
+    assert np.array_equal(w_new, hc.expected_rescale(w_old, nn, nm))
+    for k in range(h_old.shape[0]):
+        assert np.array_equal(h_new[k], hc.expected_rescale(h_old[k], nn, nm))
+    assert meta[0] == 3 and meta[2] == meta[3] and ok
 
-    with pc.scratch_cwd():
-        a = build()
-        a[2].load(mo.ic_taylor_green(g), is_physical=True)
-        for _ in range(5):
-            step(*a)
-        a[1].dump(a[1]._dump_ticker)
-        idx = a[1]._dump_ticker.times_fired
-        for _ in range(5):
-            step(*a)
-        b = build()
-        b[1].load(idx)
-        for _ in range(5):
-            step(*b)
-        assert b[1]._loop_counter == a[1]._loop_counter
-        assert np.array_equal(b[2][:].get(), a[2][:].get())
+
+@pytest.mark.parametrize("order", [2, 4])
+def test_adams_moulton_corrector_formulas(order):
+    import host_cases as hc
+    got_c, want_c, got_p, want_p = hc.corrector_formulas(order)
+    assert rel_l2(got_c, want_c) < 1e-14 and rel_l2(got_p, want_p) < 1e-14
+
+
+# ---- orderings that only work if deferred work tracks the buffers it reads (ADVICE round 1)
+@pytest.mark.parametrize("inplace_write", [False, True])
+def test_rhs_assigned_before_its_source_changes(inplace_write):
+    import aliasing_cases as ac
+    got, want = ac.swapped_integrate_order(inplace_write=inplace_write)
+    for k in want:
+        assert rel_l2(got[k], want[k]) < 1e-12, k
+
+
+def test_augmented_assignment_and_view_writes_flush_dependants():
+    import aliasing_cases as ac
+    got, want = ac.augmented_assignment_after_velocity()
+    for k in want:
+        assert rel_l2(got[k], want[k]) < 1e-12, k
+
+
+def test_held_handle_stays_current():
+    import aliasing_cases as ac
+    same, rows_ok, col0 = ac.held_handle_stays_current()
+    assert all(same) and all(rows_ok)
+    assert np.all(col0 == 0.0)
