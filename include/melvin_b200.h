@@ -95,6 +95,7 @@ typedef struct mlv_info {
     int32_t ipitch;                 /* row pitch (complex elements) of I buffers */
     int32_t nm_local;               /* retained columns owned by this rank (= nm when unsharded) */
     int64_t ibytes;                 /* bytes of one field of an I / exchange buffer */
+    int64_t red_doubles;            /* doubles of a caller-owned buffer of reduction partials */
 } mlv_info;
 
 typedef struct mlv_view {           /* 2-D strided view, strides in elements */
@@ -209,6 +210,13 @@ int mlv_advect_z(mlv_ctx* ctx, const void* iux, const void* iuz, const void* iq,
  * partials of all rows below row0 + nrows (pass it with the last range) */
 int mlv_advect_z_rows(mlv_ctx* ctx, const void* iux, const void* iuz, const void* iq,
                       void* ia, void* ib, int row0, int nrows, double* red4);
+/* The four reductions are needed at ticker cadence only (Simulation.end_loop: CFL every
+ * cfl_cadence loops, trackers every tracker_cadence).  With red4 == NULL the fused stage leaves
+ * its per-CTA partials behind -- in the context's scratch, or in a caller-owned buffer of
+ * mlv_info.red_doubles doubles registered with mlv_set_reduction_partials (NULL = scratch again)
+ * -- and mlv_reduce_partials combines them into red4 whenever somebody asks. */
+int mlv_set_reduction_partials(mlv_ctx* ctx, double* partials);
+int mlv_reduce_partials(mlv_ctx* ctx, const double* partials, double* red4);
 /* materialised physical operands: out = pddx(ux*q) + pddz(uz*q) */
 int mlv_advect_phys(mlv_ctx* ctx, const double* ux, const double* uz, const double* q,
                     double* out);

@@ -48,6 +48,8 @@ struct mlv_ctx {
     double* tri_inv = nullptr;
     double* red = nullptr;      // reduction partials
     size_t red_cap = 0;
+    double* red_user = nullptr; // caller-owned partials of the fused z stage (mlv_set_reduction_partials)
+    int red_count = 0;          // per-CTA partials written by the latest fused z stage over all local rows
     // slab decomposition (mlv_set_sharding); defaults describe the unsharded case
     int rank = 0, nranks = 1;
     int nml = 0;                // local column pitch of spectral arrays / inverse buffers
@@ -384,7 +386,7 @@ static int launch_zadv_real(mlv_ctx* c, ZAdvArgs& a, unsigned& grid_out) {
     grid_out = grid;
     int rc = ensure_red(c, (size_t)(a.nx / a.nrows) * grid * 4);
     if (rc) return rc;
-    a.red = c->red + (size_t)(a.row0 / a.nrows) * grid * 4;
+    a.red = (c->red_user ? c->red_user : c->red) + (size_t)(a.row0 / a.nrows) * grid * 4;
     a.wave = 148;
     MLV_LAUNCH(kfn, grid, (unsigned)F::T, smem, c->stream, a);
     return 0;
@@ -444,7 +446,7 @@ static int launch_zadv(mlv_ctx* c, ZAdvArgs& a, unsigned& grid_out) {
     // per-CTA partials: the launch over rows [row0, row0 + nrows) owns slots [k grid, (k+1) grid), k = row0 / nrows
     int rc = ensure_red(c, (size_t)(a.nx / a.nrows) * grid * 4);
     if (rc) return rc;
-    a.red = c->red + (size_t)(a.row0 / a.nrows) * grid * 4;
+    a.red = (c->red_user ? c->red_user : c->red) + (size_t)(a.row0 / a.nrows) * grid * 4;
     a.wave = 148 * (smem > 113 * 1024 ? 1 : 2);
 
     MLV_LAUNCH(kfn, grid, (unsigned)(LPC * F::T), smem, c->stream, a);
@@ -481,7 +483,7 @@ using namespace mlv;
 // =========================================================================== ABI
 extern "C" {
 
-int mlv_abi_version(void) { return 1; }
+int mlv_abi_version(void) { return 2; }
 
 long long mlv_launch_count(void) { return (long long)g_launches; }
 
@@ -697,6 +699,7 @@ int mlv_get_info(const mlv_ctx* c, mlv_info* o) {
         const int64_t fwd = (int64_t)c->nranks * c->sh.tpr * c->nxl * c->ct;
         o->ibytes = (inv > fwd ? inv : fwd) * (int64_t)sizeof(cplx);
     }
+    o->red_doubles = 4 * ((int64_t)(c->nxl > 0 ? c->nxl : c->p.nx) + 64);   // >= one partial per row (+ row-block slack)
     return MLV_OK;
 }
 
@@ -901,11 +904,24 @@ int mlv_advect_z_rows(mlv_ctx* c, const void* iux, const void* iuz, const void* 
 #undef MLV_GO
     }
     if (rc) return rc;
-    if (red4) {     // per-CTA partials of the rows [0, row0 + nrows) launched so far -> 4 doubles
-        const int ncta = (int)((long long)grid * (row0 + nrows) / nrows);
-        auto kfn = k_reduce_final4;
-        MLV_LAUNCH(kfn, 4u, 256u, 256 * sizeof(double), c->stream, (const double*)c->red, ncta, red4);
-    }
+    // per-CTA partials of the rows [0, row0 + nrows) launched so far
+    c->red_count = (int)((long long)grid * (row0 + nrows) / nrows);
+    if (red4) return mlv_reduce_partials(c, nullptr, red4);
+    return MLV_OK;
+}
+
+int mlv_set_reduction_partials(mlv_ctx* c, double* partials) {
+    if (!c) { set_error("mlv_set_reduction_partials: null context"); return MLV_ERR_INVALID; }
+    c->red_user = partials;
+    return MLV_OK;
+}
+
+int mlv_reduce_partials(mlv_ctx* c, const double* partials, double* red4) {
+    if (!c || !red4) { set_error("mlv_reduce_partials: null argument"); return MLV_ERR_INVALID; }
+    if (c->red_count <= 0) { set_error("mlv_reduce_partials: no fused z stage has run"); return MLV_ERR_INVALID; }
+    const double* src = partials ? partials : (c->red_user ? c->red_user : c->red);
+    auto kfn = k_reduce_final4;
+    MLV_LAUNCH(kfn, 4u, 256u, 256 * sizeof(double), c->stream, src, c->red_count, red4);
     return MLV_OK;
 }
 

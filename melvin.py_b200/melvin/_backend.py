@@ -150,6 +150,7 @@ class Context:
         self.nn, self.nm = info.nn, info.nm
         self.spec_shape = (info.spec_rows, info.spec_cols)
         self.ipitch = info.ipitch
+        self.red_doubles = int(info.red_doubles)
         self.nx, self.nz = int(nx), int(nz)
         self.fdm_z = bool(fdm_z)
         self.fd_order = int(fd_order)

@@ -7,7 +7,7 @@ carrying ``mlv_last_error()``.
 """
 import ctypes as C
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # operator codes (include/melvin_b200.h)
 OP_IDENT, OP_PSI, OP_UX, OP_UZ, OP_DDX, OP_DDZ, OP_D2DX2, OP_D2DZ2, OP_LAP, OP_INVLAP = range(10)
@@ -21,7 +21,7 @@ EXPORTS = [
     "mlv_create", "mlv_destroy", "mlv_set_stream", "mlv_get_info", "mlv_long_lines", "mlv_set_sharding", "mlv_set_forward_blocks", "mlv_p2p_alloc", "mlv_p2p_copy", "mlv_p2p_open",
     "mlv_p2p_close", "mlv_set_peer_buffers", "mlv_last_error",
     "mlv_abi_version", "mlv_launch_count", "mlv_to_physical", "mlv_to_spectral", "mlv_x_inverse",
-    "mlv_z_inverse", "mlv_z_forward", "mlv_x_forward", "mlv_advect_z", "mlv_advect_z_rows", "mlv_advect_phys",
+    "mlv_z_inverse", "mlv_z_forward", "mlv_x_forward", "mlv_advect_z", "mlv_advect_z_rows", "mlv_set_reduction_partials", "mlv_reduce_partials", "mlv_advect_phys",
     "mlv_spec_lincomb", "mlv_lap_array", "mlv_stencil", "mlv_solve_fdm", "mlv_integrate",
     "mlv_elementwise", "mlv_reduce",
 ]
@@ -41,7 +41,7 @@ class Params(C.Structure):
 class Info(C.Structure):
     _fields_ = [("nn", C.c_int32), ("nm", C.c_int32), ("spec_rows", C.c_int32),
                 ("spec_cols", C.c_int32), ("ipitch", C.c_int32), ("nm_local", C.c_int32),
-                ("ibytes", C.c_int64)]
+                ("ibytes", C.c_int64), ("red_doubles", C.c_int64)]
 
 
 class View(C.Structure):
@@ -115,6 +115,8 @@ def declare(lib):
         "mlv_x_forward": [vp, C.POINTER(XFwd)],
         "mlv_advect_z": [vp, vp, vp, vp, vp, vp, vp],
         "mlv_advect_z_rows": [vp, vp, vp, vp, vp, vp, i32, i32, vp],
+        "mlv_set_reduction_partials": [vp, vp],
+        "mlv_reduce_partials": [vp, vp, vp],
         "mlv_advect_phys": [vp, vp, vp, vp, vp],
         "mlv_spec_lincomb": [vp, C.POINTER(LinTerms), vp],
         "mlv_lap_array": [vp, f64, vp],

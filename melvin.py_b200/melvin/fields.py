@@ -97,7 +97,8 @@ class Variable:
         self._i_state = _I_NONE
         self._i_def = None                   # (op, DeviceArray) the pending x pass reads
         self._p_valid = True
-        self._red = None                     # (red4 tensor, max index, sumsq index)
+        self._red = None                     # (shared {"part", "host"}, max index, sumsq index)
+        self._red_part = None                # per-CTA partials of the fused z stage (velocity owner)
         self._ctx_vars().add(self)
 
     # ------------------------------------------------------------ registry
@@ -320,12 +321,20 @@ class Variable:
         # then turns its copy into psi for the two velocity components
         _run_x_inverse(ctx, [v for v in (self, uxo, uzo) if v._i_state == _I_PENDING])
         ia, ib = ctx.take_i(), ctx.take_i()
-        red4 = _backend.empty((4,), np.float64)
+        # the CFL / kinetic-energy reductions of the velocities ride in this kernel, but the
+        # tickers want them only every cfl_cadence / tracker_cadence loops: the kernel leaves
+        # its per-CTA partials in a buffer owned by the x velocity, _cached_reduction combines
+        # them when (and if) somebody asks
+        if uxo._red_part is None:
+            uxo._red_part = _backend.empty((ctx.red_doubles,), np.float64)
+        ctx.call("mlv_set_reduction_partials", ctypes.c_void_p(uxo._red_part.data_ptr()), count=False)
         ctx.call("mlv_advect_z", ctypes.c_void_p(uxo._i.data_ptr()), ctypes.c_void_p(uzo._i.data_ptr()),
                  ctypes.c_void_p(self._i.data_ptr()), ctypes.c_void_p(ia.data_ptr()),
-                 ctypes.c_void_p(ib.data_ptr()), ctypes.c_void_p(red4.data_ptr()))
-        uxo._red = (red4, 0, 2)
-        uzo._red = (red4, 1, 3)
+                 ctypes.c_void_p(ib.data_ptr()), None)
+        ctx.call("mlv_set_reduction_partials", None, count=False)
+        shared = {"part": uxo._red_part, "host": None}
+        uxo._red = (shared, 0, 2)
+        uzo._red = (shared, 1, 3)
         return SpecExpr(ctx, [], [(1.0, NLTerm(ctx, ia, ib))])
 
     def _vec_dot_nabla_eager(self, ux, uz, out, convert_to_physical):
@@ -353,7 +362,13 @@ class Variable:
         z stage already produced it for the current intermediate."""
         if self._red is None or self._i_state == _I_NONE:
             return None
-        return float(_backend.to_host(self._red[0])[self._red[which]])
+        shared = self._red[0]
+        if shared["host"] is None:
+            red4 = _backend.empty((4,), np.float64)
+            self._ctx.call("mlv_reduce_partials", ctypes.c_void_p(shared["part"].data_ptr()),
+                           ctypes.c_void_p(red4.data_ptr()))
+            shared["host"] = _backend.to_host(red4)
+        return float(shared["host"][self._red[which]])
 
     # ------------------------------------------------------------- I/O
     def save(self, dump_counter):

@@ -43,6 +43,7 @@ import torch
 import torch.distributed as dist
 
 from . import _backend, _capi
+from .b200 import DeviceArray, sum_of_product
 
 
 class ShardedScalarStepper:
@@ -51,7 +52,7 @@ class ShardedScalarStepper:
     MOVED_INV, MOVED_FWD = 3, 2
 
     def __init__(self, nx, nz, lx, lz, coef, dt, fd_order=2, ab_order=2, alpha=0.51,
-                 cfl_cutoff=0.5, cfl_cadence=10, tracker_cadence=100, group=None, p2p=None):
+                 cfl_cutoff=0.5, cfl_cadence=10, tracker_cadence=100, group=None, p2p=None, mode=None):
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -76,7 +77,7 @@ class ShardedScalarStepper:
         cplx = np.complex128
         # bytes this rank sends to its peers per step (3 inverse + 2 forward fields)
         self.bytes_exchanged_per_step = 16 * (self.MOVED_INV * self.inv_field + self.MOVED_FWD * self.fwd_field) * (self.world - 1)
-        mode = os.environ.get("MLV_EXCHANGE", "")
+        mode = mode or os.environ.get("MLV_EXCHANGE", "")
         if os.environ.get("MLV_NO_P2P"):
             mode = "a2a"
         if p2p is not None:
@@ -183,8 +184,8 @@ class ShardedScalarStepper:
     # ------------------------------------------------------------------ state
     def load_spectral(self, w_full):
         """Keep this rank's column slab of a full (2nn+1, nm) spectral array (host)."""
-        self.w[self.cur].copy_(self._slab_local(w_full))
-        self.hist.zero_()
+        self._load_slab(self.w[self.cur], w_full)
+        DeviceArray(self.hist)[...] = 0.0
         self.hidx = 0
 
     def gather_spectral(self):
@@ -234,13 +235,18 @@ class ShardedScalarStepper:
                 (1, 0): self.fwd_send_ptr, (1, 1): self.fwd_recv_ptr}[(which, int(recv))]
         return base + 16 * slot * (self.inv_stride if which == 0 else self.fwd_stride)
 
-    def _slab_local(self, full):
-        """This rank's column slab of a full (2nn+1, nm) spectral array (host) as a device array."""
-        full = np.asarray(full)
-        slab = np.zeros((self.rows, self.nml), dtype=np.complex128)
-        if self.nm_local > 0:
-            slab[:, :self.nm_local] = full[:, self.m_off:self.m_off + self.nm_local]
-        return _backend.from_host(slab)
+    def _load_slab(self, dst, full):
+        """dst (rows, nml) := this rank's column slab of a full (2nn+1, nm) spectral array (host
+        array, or a device tensor of a full-size context)."""
+        out = DeviceArray(dst)
+        out[...] = 0.0
+        if self.nm_local <= 0:
+            return
+        cols = slice(self.m_off, self.m_off + self.nm_local)
+        if isinstance(full, torch.Tensor):
+            out[:, :self.nm_local] = DeviceArray(full)[:, cols]
+        else:
+            out[:, :self.nm_local] = np.ascontiguousarray(np.asarray(full)[:, cols])
 
     def _gather(self, local):
         if self.world == 1:
@@ -338,10 +344,9 @@ class ShardedScalarStepper:
         self._srcs1 = [(vp * 1)(w.data_ptr()) for w in self.w]
         ir, fs = self.inv_recv_ptr, self.fwd_send_ptr
         self._zargs = (vp(ir + 16 * self.inv_stride), vp(ir + 32 * self.inv_stride), vp(ir),
-                       vp(fs), vp(fs + 16 * self.fwd_stride), vp(self.red4.data_ptr()))
-        self._zrows = [self._zargs[:5] + (c * self.chunk_rows, self.chunk_rows,
-                                          self._zargs[5] if c == self.nchunks - 1 else None)
-                       for c in range(self.nchunks)]
+                       vp(fs), vp(fs + 16 * self.fwd_stride))
+        self._redp = vp(self.red4.data_ptr())
+        self._zrows = [self._zargs + (c * self.chunk_rows, self.chunk_rows) for c in range(self.nchunks)]
         d = _capi.XFwd()
         d.nf, d.mode = 2, 1
         d.src[0] = self.fwd_recv_ptr
@@ -354,10 +359,16 @@ class ShardedScalarStepper:
         self._xfwd = d
         self._hist_ptrs = [self.hist[k].data_ptr() for k in range(self.order)]
 
+    def _tickers_due(self):
+        """Will end_loop of this step fire the CFL or the tracker ticker (Ticker.py:14-25)?"""
+        return self._cfl_counter < self.loop + 1 or self._trk_counter < self.loop + 1
+
     def step(self):
         ctx = self.ctx
         w_in, w_out = self.w[self.cur], self.w[1 - self.cur]
         wp = w_in.data_ptr()
+        # the four reductions are combined only on the steps whose tickers read them
+        redp = self._redp if self._tickers_due() else None
         if self.mode == "dma":
             # one launch per field; the copies of field f (row block h -> rank h) run on the copy
             # engines while the x pass of field f+1 runs on the SMs
@@ -368,7 +379,7 @@ class ShardedScalarStepper:
             # z stage block by block; the two fields of a finished row block leave while the
             # next block is computed
             for c in range(self.nchunks):
-                ctx.call("mlv_advect_z_rows", *self._zrows[c])
+                ctx.call("mlv_advect_z_rows", *self._zrows[c], redp if c == self.nchunks - 1 else None)
                 for f in range(2):
                     self._dma(1, f, self._ev[c % 3], chunk=c if self.nchunks > 1 else None)
             self._dma_join(self._ev[4])
@@ -380,7 +391,7 @@ class ShardedScalarStepper:
             if self.world > 1:
                 dist.all_reduce(self._sync, group=self.group)
             # 3. physical-space stage on the local rows
-            ctx.call("mlv_advect_z", *self._zargs)
+            ctx.call("mlv_advect_z", *self._zargs, redp)
             if self.world > 1:
                 dist.all_reduce(self._sync, group=self.group)
         else:
@@ -394,7 +405,7 @@ class ShardedScalarStepper:
                 wk.wait()
             # 3. physical-space stage on the local rows
             for c in range(self.nchunks):
-                ctx.call("mlv_advect_z_rows", *self._zrows[c])
+                ctx.call("mlv_advect_z_rows", *self._zrows[c], redp if c == self.nchunks - 1 else None)
             # 4. transpose back: tile block h goes to rank h
             works = [self._a2a(self.fwd_recv, self.fwd_send, f) for f in range(2)]
             for wk in works:
@@ -477,8 +488,8 @@ class ShardedDoubleDiffusiveStepper(ShardedScalarStepper):
 
     def load_spectral(self, w_full, tmp_full, xi_full):
         for k, full in (("w", w_full), ("tmp", tmp_full), ("xi", xi_full)):
-            self.q[k][self.cur].copy_(self._slab_local(full))
-            self.h[k].zero_()
+            self._load_slab(self.q[k][self.cur], full)
+            DeviceArray(self.h[k])[...] = 0.0
         self.hidx = 0
 
     def gather_spectral(self):
@@ -491,7 +502,8 @@ class ShardedDoubleDiffusiveStepper(ShardedScalarStepper):
         # inverse slots: 0 w, 1 ux, 2 uz (all from the old vorticity), 3 tmp, 4 xi
         self._inverse_round([(w, OP.OP_IDENT, 0), (w, OP.OP_UX, 1), (w, OP.OP_UZ, 2),
                              (tmp, OP.OP_IDENT, 3), (xi, OP.OP_IDENT, 4)])
-        self._advect_round([(1, 2, 0, 0, 1, self.red4), (1, 2, 3, 2, 3, None), (1, 2, 4, 4, 5, None)])
+        red = self.red4 if self._tickers_due() else None
+        self._advect_round([(1, 2, 0, 0, 1, red), (1, 2, 3, 2, 3, None), (1, 2, 4, 4, 5, None)])
         Pr, R0, tau = self.Pr, self.R0, self.tau
         self._forward((0, 1), (-1.0, -1.0), [(Pr, OP.OP_DDX, xi), (-Pr, OP.OP_DDX, tmp)], Pr,
                       w, self.q["w"][n], self.h["w"], self.hidx)
@@ -500,8 +512,8 @@ class ShardedDoubleDiffusiveStepper(ShardedScalarStepper):
         self._forward((4, 5), (-1.0, -1.0), [(-1.0 / R0, OP.OP_UZ, w)], tau,
                       xi, self.q["xi"][n], self.h["xi"], self.hidx)
         if self.m_off == 0 and self.nm_local > 0:      # the rank that owns the m = 0 column
-            self.q["tmp"][n][:, 0] = 0.0
-            self.q["xi"][n][:, 0] = 0.0
+            DeviceArray(self.q["tmp"][n])[:, 0] = 0.0
+            DeviceArray(self.q["xi"][n])[:, 0] = 0.0
         self.cur = n
         self.hidx = (self.hidx + 1) % self.order
         self.end_loop()
@@ -514,7 +526,8 @@ class ShardedDoubleDiffusiveStepper(ShardedScalarStepper):
             self._phys = [_backend.zeros((self.nxl, self.nz), np.float64) for _ in range(2)]
         for slot, out in ((3, self._phys[0]), (2, self._phys[1])):
             self.ctx.call("mlv_z_inverse", vp(self._slot(0, True, slot)), vp(out.data_ptr()))
-        sm = (self._phys[0] * self._phys[1]).sum().reshape(1)
+        local = sum_of_product(DeviceArray(self._phys[0]), DeviceArray(self._phys[1]))   # mlv_reduce
+        sm = torch.tensor([local], dtype=torch.float64, device=_backend.device())
         if self.world > 1:
             dist.all_reduce(sm, group=self.group)
         self.nu.append(1.0 - float(_backend.to_host(sm)[0]) / (self.nx * self.nz))
@@ -546,8 +559,8 @@ class ShardedTearingStepper(ShardedScalarStepper):
 
     def load_spectral(self, w_full, j_full):
         for k, full in (("w", w_full), ("j", j_full)):
-            self.q[k][self.cur].copy_(self._slab_local(full))
-            self.h[k].zero_()
+            self._load_slab(self.q[k][self.cur], full)
+            DeviceArray(self.h[k])[...] = 0.0
         self.hidx = 0
 
     def gather_spectral(self):
@@ -562,7 +575,8 @@ class ShardedTearingStepper(ShardedScalarStepper):
         self._inverse_round([(w, OP.OP_IDENT, 0), (w, OP.OP_UX, 1), (w, OP.OP_UZ, 2),
                              (j, OP.OP_IDENT, 3), (j, OP.OP_UX, 4), (j, OP.OP_UZ, 5)])
         # forward slots: (0,1) u.grad w, (2,3) b.grad j, (4,5) u.grad j, (6,7) b.grad w_new
-        self._advect_round([(1, 2, 0, 0, 1, self.red4), (4, 5, 3, 2, 3, None), (1, 2, 3, 4, 5, None)])
+        red = self.red4 if self._tickers_due() else None
+        self._advect_round([(1, 2, 0, 0, 1, red), (4, 5, 3, 2, 3, None), (1, 2, 3, 4, 5, None)])
         self._forward((0, 1, 2, 3), (-1.0, -1.0, 1.0, 1.0), [], 1.0 / self.Re, w, w_new, self.h["w"], self.hidx)
         self._inverse_round([(w_new, OP.OP_IDENT, 6)])
         self._advect_round([(4, 5, 6, 6, 7, None)])

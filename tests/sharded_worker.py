@@ -38,21 +38,18 @@ def rel(a, b):
     return np.linalg.norm((a - b).ravel()) / np.linalg.norm(np.asarray(b).ravel())
 
 
-if case == "tg64":
-    gl = np.load(os.path.join(ROOT, "tests", "golden", "loop_tg_64x64.npz"))
-    g = mo.Grid(64, 64, float(gl["lx"]), float(gl["lz"]))
-    st = ShardedScalarStepper(64, 64, g.lx, g.lz, float(gl["coef"]), float(gl["dt"]), tracker_cadence=1)
-    st.load_spectral(mo.to_spectral(g, mo.ic_taylor_green(g)))
-    errs = {}
-    for k in range(1, 21):
-        st.step()
-        if k in (1, 2, 10, 20):
-            errs[k] = rel(st.gather_spectral(), gl[f"w_step{k}"])
-    ke_err = float(np.max(np.abs(np.array(st.ke) / gl["ke"] - 1)))
-    ok = all(e < 1e-12 for e in errs.values()) and ke_err < 1e-9
+def report(res):
     if rank == 0:
-        print(f"SHARDED world={world} field_err={max(errs.values()):.2e} ke_err={ke_err:.2e} "
-              f"{'OK' if ok else 'FAIL'}", flush=True)
+        print(f"SHARDED world={world} " + " ".join(f"{k}={v:.2e}" if isinstance(v, float) else f"{k}={v}"
+                                                   for k, v in res.items()) + (" OK" if res["ok"] else " FAIL"),
+              flush=True)
+    return res["ok"]
+
+
+st = None
+if case == "tg64":
+    import sharded_parity as sp
+    ok = report(sp.check_taylor_green())
 elif case in ("kh", "khlong"):
     # uneven column split (nm not a multiple of the rank count), order-2 KH vs the oracle;
     # "khlong": the long-line kernels (16384-point lines) forced onto a small grid
@@ -76,45 +73,27 @@ elif case in ("kh", "khlong"):
     if rank == 0:
         print(f"SHARDED world={world} field_err={err:.2e} ke_err={ke_err:.2e} {'OK' if ok else 'FAIL'}",
               flush=True)
+elif case == "bench":
+    # bench.py's multi-GPU host logic: the parity preflight and the three workload builders
+    import bench
+    res = bench.parity_sharded()
+    ok = res["ok"] and len(res["cases"]) == 5
+    for cfg in ("kh", "ddc", "tearing"):
+        bst = bench.build_sharded(cfg, 64, 64)
+        for _ in range(3):
+            bst.step()
+        ok = ok and all(np.all(np.isfinite(a)) for a in np.atleast_1d(bst.gather_spectral()))
+        bst.close()
+    if rank == 0:
+        print(f"SHARDED world={world} bench preflight + builders {'OK' if ok else 'FAIL'}", flush=True)
 elif case == "ddc":
-    # three coupled scalars (BASELINE config 4 loop) vs the golden of the unmodified reference
-    gl = np.load(os.path.join(ROOT, "tests", "golden", "loop_ddc_64x64.npz"))
-    g = mo.Grid(64, 64, float(gl["lx"]), float(gl["lz"]))
-    st = ShardedDoubleDiffusiveStepper(64, 64, g.lx, g.lz, float(gl["Pr"]), float(gl["R0"]), float(gl["tau"]),
-                                       float(gl["dt"]), tracker_cadence=1)
-    noise = mo.to_spectral(g, mo.ic_noise(g))
-    st.load_spectral(noise, noise, noise)
-    errs = {}
-    for k in range(1, 21):
-        st.step()
-        if k in (1, 10, 20):
-            got = st.gather_spectral()
-            errs[k] = max(rel(a, gl[f"{nm}_step{k}"]) for a, nm in zip(got, ("w", "tmp", "xi")))
-    ke_err = float(np.max(np.abs(np.array(st.ke) / gl["ke"] - 1)))
-    nu_err = float(np.max(np.abs((np.array(st.nu) - 1) - (gl["nu"] - 1)) / np.maximum(np.abs(gl["nu"] - 1), 1e-17)))
-    ok = all(e < 1e-12 for e in errs.values()) and ke_err < 1e-9 and nu_err < 1e-6
-    if rank == 0:
-        print(f"SHARDED world={world} field_err={max(errs.values()):.2e} ke_err={ke_err:.2e} "
-              f"nu_err={nu_err:.2e} {'OK' if ok else 'FAIL'}", flush=True)
+    import sharded_parity as sp
+    ok = report(sp.check_double_diffusive())
 elif case == "tearing":
-    # MHD loop (BASELINE config 5 loop), two exchange rounds per step, vs the reference golden
-    gl = np.load(os.path.join(ROOT, "tests", "golden", "loop_tearing_64x64.npz"))
-    g = mo.Grid(64, 64, float(gl["lx"]), float(gl["lz"]))
-    st = ShardedTearingStepper(64, 64, g.lx, g.lz, float(gl["Re"]), float(gl["S"]), float(gl["dt"]),
-                               tracker_cadence=1)
-    st.load_spectral(np.zeros(g.spectral_shape, complex), mo.to_spectral(g, gl["j0_phys"]))
-    jerr, werr = 0.0, 0.0
-    for k in range(1, 21):
-        st.step()
-        if k in (1, 10, 20):
-            w, j = st.gather_spectral()
-            jerr = max(jerr, rel(j, gl[f"j_step{k}"]))
-            werr = max(werr, rel(w, gl[f"w_step{k}"]))
-    # w starts from exactly zero and is driven by rounding-level asymmetries of j
-    ok = jerr < 1e-12 and werr < 1e-9
-    if rank == 0:
-        print(f"SHARDED world={world} j_err={jerr:.2e} w_err={werr:.2e} {'OK' if ok else 'FAIL'}", flush=True)
-st.close()
+    import sharded_parity as sp
+    ok = report(sp.check_tearing())
+if st is not None:
+    st.close()
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)

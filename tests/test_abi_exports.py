@@ -39,7 +39,8 @@ def test_library_exports_every_declared_symbol(libpath):
     for sym in declared_symbols():
         assert hasattr(lib, sym), sym
     lib.mlv_abi_version.restype = ctypes.c_int
-    assert lib.mlv_abi_version() == 1
+    from melvin import _capi
+    assert lib.mlv_abi_version() == _capi.ABI_VERSION
     lib.mlv_last_error.restype = ctypes.c_char_p
     assert lib.mlv_last_error() is not None
 

@@ -52,3 +52,8 @@ def test_multi_field_steppers(case, world):
     """double-diffusive (3 coupled scalars) and MHD tearing (2 exchange rounds per step)
     slab-decomposed, vs the goldens of the unmodified reference"""
     run_world(world, case, 29620 + world)
+
+
+def test_bench_multi_gpu_host_logic():
+    """bench.py's sharded parity preflight and workload builders over gloo (world 2)"""
+    run_world(2, "bench", 29631)
