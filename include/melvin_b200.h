@@ -49,6 +49,12 @@ extern "C" {
 #define MLV_OP_D2DZ2 7  /* SpatialDifferentiator.py:65  */
 #define MLV_OP_LAP 8    /* Variable.py:111-113 (spectral snabla2) */
 #define MLV_OP_INVLAP 9 /* LaplacianSolver.py:58-68 */
+/* FDM-z mode only: operators that act along a spectral row (z is the finite-difference axis) */
+#define MLV_OP_FDM_D2DZ2 10  /* pd2dz2, interior only         SpatialDifferentiator.py:106-128     */
+#define MLV_OP_FDM_DDZ 11    /* pddz, edge columns zero       SpatialDifferentiator.py:91-104,157-185 */
+#define MLV_OP_FDM_NABLA2 12 /* sd2dx2 + pd2dz2               Variable.py:111-113 (FDM snabla2)    */
+#define MLV_OP_FDX_SYM 13    /* i * Fourier symbol of the periodic central x stencil   */
+#define MLV_MAXLIN 6
 
 /* multiplier symbols of the forward x pass */
 #define MLV_SYM_ONE 0
@@ -105,9 +111,9 @@ typedef struct mlv_view {           /* 2-D strided view, strides in elements */
 
 typedef struct mlv_lin_terms {      /* sum_i (cre_i + i cim_i) * op_i(src_i) */
     int32_t n;
-    int32_t op[4];
-    const void* src[4];
-    double cre[4], cim[4];
+    int32_t op[MLV_MAXLIN];
+    const void* src[MLV_MAXLIN];
+    double cre[MLV_MAXLIN], cim[MLV_MAXLIN];
 } mlv_lin_terms;
 
 typedef struct mlv_integ {          /* melvin/Integrator.py:5-18,53-63; TimeDerivative.py:9-45 */
@@ -118,6 +124,8 @@ typedef struct mlv_integ {          /* melvin/Integrator.py:5-18,53-63; TimeDeri
     const void* q_in;               /* state (may equal q_out) */
     void* q_out;
     void* f0;                       /* history level curr_idx (read; rewritten if lin.n > 0) */
+    int32_t f0_set;                 /* mlv_integrate: 1 = f0 := the linear terms (whole right-hand side, not read) */
+    int32_t reserved_;
     const void* fm1;                /* curr_idx-1 .. curr_idx-3 (ring order) */
     const void* fm2;
     const void* fm3;
@@ -232,6 +240,18 @@ int mlv_stencil(mlv_ctx* ctx, const void* in, void* out, int rows, int cols, int
 /* ---- LaplacianSolver.solve (melvin/LaplacianSolver.py:58-79) --------------
  * fully spectral: mlv_spec_lincomb with MLV_OP_INVLAP; FDM-z: batched tridiagonal */
 int mlv_solve_fdm(mlv_ctx* ctx, const void* rhs, void* out);
+
+/* ---- fused Fourier-x / FDM-z step (examples/rayleigh_benard_convection.py:95-145) ---------
+ * mlv_fdm_velocity: utility.calc_velocity_from_vorticity, FDM branch (utility.py:62-79) in one
+ *   row-wise pass: psi = solve(-w); uxh = -pddz(psi) and uzh = (i kx n) psi are the x spectra of
+ *   the two velocity components (the z stencil commutes with the x transform).  (nn, nz) each.
+ * mlv_fdm_advect: the physical-space stage of Variable.vec_dot_nabla (Variable.py:119-128) on
+ *   x spectra: a = Fx[ux q]/nx, b = Fx[uz q]/nx; the caller forms
+ *   d/dx(ux q) + d/dz(uz q) = MLV_OP_FDX_SYM(a) + MLV_OP_FDM_DDZ(b) as linear terms of
+ *   mlv_integrate.  Reductions as mlv_advect_z (red4 / mlv_set_reduction_partials). */
+int mlv_fdm_velocity(mlv_ctx* ctx, const void* w, void* psi, void* uxh, void* uzh);
+int mlv_fdm_advect(mlv_ctx* ctx, const void* uxh, const void* uzh, const void* q, void* a, void* b,
+                   double* red4);
 
 /* ---- Integrator.integrate (melvin/Integrator.py:53-63) -------------------- */
 int mlv_integrate(mlv_ctx* ctx, const mlv_lin_terms* extra, const mlv_integ* g);

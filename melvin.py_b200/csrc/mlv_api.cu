@@ -44,8 +44,8 @@ struct mlv_ctx {
     mlv::SpecConsts k;
     mlv::Plan planx, planz;
     double* symz = nullptr;     // [nm]
-    double* tri_cp = nullptr;   // FDM-z: (nn, nz)
-    double* tri_inv = nullptr;
+    double* tri_inv = nullptr;  // FDM-z: (nn, nz) pivots of the Thomas factorisation
+    double* symx = nullptr;     // FDM-z: [nn] Fourier symbol of the periodic central x stencil
     double* red = nullptr;      // reduction partials
     size_t red_cap = 0;
     double* red_user = nullptr; // caller-owned partials of the fused z stage (mlv_set_reduction_partials)
@@ -254,17 +254,27 @@ static int check_lin(const mlv_ctx* c, const mlv_lin_terms* t, const char* fn) {
     }
     for (int i = 0; i < t->n; ++i) {
         const int op = t->op[i];
-        if (op < MLV_OP_IDENT || op > MLV_OP_INVLAP) {
+        if (op < MLV_OP_IDENT || op > MLV_OP_FDX_SYM) {
             set_error("%s: bad operator code %d", fn, op);
             return MLV_ERR_INVALID;
         }
-        if (c->p.fdm_z && !(op == MLV_OP_IDENT || op == MLV_OP_DDX || op == MLV_OP_D2DX2)) {
+        if (c->p.fdm_z && !(op == MLV_OP_IDENT || op == MLV_OP_DDX || op == MLV_OP_D2DX2 || op >= MLV_OP_FDM_D2DZ2)) {
             set_error("%s: operator %d needs a spectral z axis", fn, op);
+            return MLV_ERR_INVALID;
+        }
+        if (!c->p.fdm_z && op >= MLV_OP_FDM_D2DZ2) {
+            set_error("%s: operator %d needs a finite-difference z axis", fn, op);
             return MLV_ERR_INVALID;
         }
         if (!t->src[i]) { set_error("%s: null source", fn); return MLV_ERR_INVALID; }
     }
     return 0;
+}
+
+static FdmConsts fdm_consts(const mlv_ctx* c) {
+    FdmConsts f;
+    f.nz = c->p.nz; f.order = c->p.fd_order; f.dz = c->dz; f.symx = c->symx;
+    return f;
 }
 
 static void fill_integ(IntegArgs& o, const mlv_integ* g) {
@@ -469,6 +479,42 @@ static int launch_x1d(mlv_ctx* c, X1dArgs& a, bool inverse) {
     return 0;
 }
 
+static int launch_fdm_solve(mlv_ctx* c, const void* rhs, double sign, void* out, void* uxh, void* uzh) {
+    FdmSolveArgs a;
+    a.rhs = (const cplx*)rhs; a.sign = sign; a.out = (cplx*)out; a.uxh = (cplx*)uxh; a.uzh = (cplx*)uzh;
+    a.inv = c->tri_inv; a.nn = c->nn; a.nz = c->p.nz; a.off = 1.0 / (c->dz * c->dz); a.kx0 = c->k.kx0;
+    a.f = fdm_consts(c);
+    // MLV_FDM_PER consecutive unknowns per thread
+    const unsigned nt = a.nz <= 256 * MLV_FDM_PER ? 256u : 512u;
+    if ((long long)nt * MLV_FDM_PER < a.nz) {
+        set_error("FDM-z solve: nz=%d unsupported (at most %d)", a.nz, 512 * MLV_FDM_PER);
+        return MLV_ERR_UNSUPPORTED;
+    }
+    size_t smem = (size_t)(a.nz + (a.nz >> 3) + 1) * sizeof(cplx) + 96 * sizeof(double);
+#ifdef MLV_EMU
+    smem += 3 * (size_t)nt * sizeof(double);
+#endif
+    auto kfn = k_fdm_solve;
+    MLV_LAUNCH(kfn, (unsigned)a.nn, nt, smem, c->stream, a);
+    return MLV_OK;
+}
+
+template <int L>
+static int launch_x1d_advect(mlv_ctx* c, X1dAdvArgs& a, unsigned& grid_out) {
+    constexpr int C = xcols(L);
+    typedef FftCfg<L> F;
+    auto kfn = k_x1d_advect<L, C>;
+    const size_t smem = (size_t)F::XSLOTS * C * sizeof(double) + (size_t)F::N * C * sizeof(cplx) +
+                        (size_t)4 * C * F::T * sizeof(double);
+    const unsigned grid = (unsigned)(((a.nz + 1) / 2 + C - 1) / C);
+    grid_out = grid;
+    int rc = ensure_red(c, (size_t)grid * 4);
+    if (rc) return rc;
+    a.red = c->red_user ? c->red_user : c->red;
+    MLV_LAUNCH(kfn, grid, (unsigned)(C * F::T), smem, c->stream, a);
+    return 0;
+}
+
 static int reduce_final(mlv_ctx* c, const double* partial, int n, int stride, int off, int op,
                         double* out) {
     auto kfn = k_reduce_final;
@@ -549,26 +595,29 @@ int mlv_create(const mlv_params* p, mlv_ctx** out) {
     }
     if (!rc && p->fdm_z) {
         // Thomas factors of the nn tridiagonal systems (LaplacianSolver.py:22-49)
+        // inv[i] = 1/(b - a c'[i-1]), c'[i] = a inv[i]; identity first and last rows
         const size_t tot = (size_t)c->nn * p->nz;
-        std::vector<double> cp(tot), inv(tot);
+        std::vector<double> inv(tot);
         const double off = 1.0 / (c->dz * c->dz);
         for (int n = 0; n < c->nn; ++n) {
             const double kx = n * p->kx0;
             const double b = -(kx * kx + 2.0 / (c->dz * c->dz));
-            double* cpr = &cp[(size_t)n * p->nz];
             double* ivr = &inv[(size_t)n * p->nz];
-            cpr[0] = 0.0; ivr[0] = 1.0;                       // identity first row
+            double cprev = 0.0;
+            ivr[0] = 1.0;
             for (int i = 1; i < p->nz - 1; ++i) {
-                const double den = b - off * cpr[i - 1];
+                const double den = b - off * cprev;
                 ivr[i] = 1.0 / den;
-                cpr[i] = off / den;
+                cprev = off * ivr[i];
             }
-            cpr[p->nz - 1] = 0.0; ivr[p->nz - 1] = 1.0;       // identity last row
+            ivr[p->nz - 1] = 1.0;
         }
-        rc = rt_malloc((void**)&c->tri_cp, tot * sizeof(double));
-        if (!rc) rc = rt_malloc((void**)&c->tri_inv, tot * sizeof(double));
-        if (!rc) rc = rt_h2d(c->tri_cp, cp.data(), tot * sizeof(double), c->stream);
+        rc = rt_malloc((void**)&c->tri_inv, tot * sizeof(double));
         if (!rc) rc = rt_h2d(c->tri_inv, inv.data(), tot * sizeof(double), c->stream);
+        std::vector<double> sx(c->nn > 0 ? c->nn : 1);
+        for (int n = 0; n < c->nn; ++n) sx[n] = stencil_symbol(p->fd_order, n, p->nx, c->dx);
+        if (!rc) rc = rt_malloc((void**)&c->symx, sx.size() * sizeof(double));
+        if (!rc) rc = rt_h2d(c->symx, sx.data(), sx.size() * sizeof(double), c->stream);
     }
     if (!rc) rc = ensure_red(c, 148 * 16 * 4);
     if (!rc && !p->fdm_z) configure_shard(c, 0, 1, 1, 1);
@@ -585,8 +634,8 @@ int mlv_destroy(mlv_ctx* c) {
     if (c->tws_x) rt_free(c->tws_x);
     if (c->tws_z) rt_free(c->tws_z);
     if (c->symz) rt_free(c->symz);
-    if (c->tri_cp) rt_free(c->tri_cp);
     if (c->tri_inv) rt_free(c->tri_inv);
+    if (c->symx) rt_free(c->symx);
     if (c->red) rt_free(c->red);
     delete c;
     return MLV_OK;
@@ -699,7 +748,8 @@ int mlv_get_info(const mlv_ctx* c, mlv_info* o) {
         const int64_t fwd = (int64_t)c->nranks * c->sh.tpr * c->nxl * c->ct;
         o->ibytes = (inv > fwd ? inv : fwd) * (int64_t)sizeof(cplx);
     }
-    o->red_doubles = 4 * ((int64_t)(c->nxl > 0 ? c->nxl : c->p.nx) + 64);   // >= one partial per row (+ row-block slack)
+    // >= one partial per row (+ row-block slack); FDM-z: per pair of z columns
+    o->red_doubles = 4 * ((int64_t)(c->p.fdm_z ? c->p.nz : (c->nxl > 0 ? c->nxl : c->p.nx)) + 64);
     return MLV_OK;
 }
 
@@ -944,7 +994,7 @@ int mlv_spec_lincomb(mlv_ctx* c, const mlv_lin_terms* t, void* out) {
     a.rows = c->spec_rows; a.cols = c->spec_cols; a.nn = c->nn; a.fdm = c->p.fdm_z;
     a.m_off = c->sh.m_off; a.nm_glob = c->p.fdm_z ? 0 : c->nm;
     fill_lin(a.lin, t);
-    a.out = (cplx*)out; a.k = c->k;
+    a.out = (cplx*)out; a.k = c->k; a.f = fdm_consts(c);
     auto kfn = k_spec_lincomb;
     MLV_LAUNCH(kfn, grid1d((size_t)a.rows * a.cols), 256u, 0, c->stream, a);
     return MLV_OK;
@@ -979,13 +1029,33 @@ int mlv_stencil(mlv_ctx* c, const void* in, void* out, int rows, int cols, int n
 int mlv_solve_fdm(mlv_ctx* c, const void* rhs, void* out) {
     if (!c || !rhs || !out) { set_error("mlv_solve_fdm: null argument"); return MLV_ERR_INVALID; }
     if (!c->p.fdm_z) { set_error("mlv_solve_fdm: context is fully spectral"); return MLV_ERR_INVALID; }
-    TriArgs a;
-    a.rhs = (const cplx*)rhs; a.out = (cplx*)out; a.cp = c->tri_cp; a.inv = c->tri_inv;
-    a.nn = c->nn; a.nz = c->p.nz; a.off = 1.0 / (c->dz * c->dz);
-    constexpr int ROWS = 8, CHUNK = 128;
-    auto kfn = k_tridiag<ROWS, CHUNK>;
-    const size_t smem = (size_t)ROWS * (CHUNK + 1) * sizeof(cplx);
-    MLV_LAUNCH(kfn, (unsigned)((a.nn + ROWS - 1) / ROWS), 256u, smem, c->stream, a);
+    return launch_fdm_solve(c, rhs, 1.0, out, nullptr, nullptr);
+}
+
+int mlv_fdm_velocity(mlv_ctx* c, const void* w, void* psi, void* uxh, void* uzh) {
+    if (!c || !w || !psi || !uxh || !uzh) { set_error("mlv_fdm_velocity: null argument"); return MLV_ERR_INVALID; }
+    if (!c->p.fdm_z) { set_error("mlv_fdm_velocity: context is fully spectral"); return MLV_ERR_INVALID; }
+    return launch_fdm_solve(c, w, -1.0, psi, uxh, uzh);          // psi = solve(-w), utility.py:65
+}
+
+int mlv_fdm_advect(mlv_ctx* c, const void* uxh, const void* uzh, const void* q, void* ia, void* ib,
+                   double* red4) {
+    if (!c || !uxh || !uzh || !q || !ia || !ib) { set_error("mlv_fdm_advect: null argument"); return MLV_ERR_INVALID; }
+    if (!c->p.fdm_z) { set_error("mlv_fdm_advect: context is fully spectral"); return MLV_ERR_INVALID; }
+    X1dAdvArgs a{};
+    a.nn = c->nn; a.nz = c->p.nz;
+    a.uxh = (const cplx*)uxh; a.uzh = (const cplx*)uzh; a.q = (const cplx*)q;
+    a.A = (cplx*)ia; a.B = (cplx*)ib;
+    a.scale = 1.0 / (double)c->p.nx;                          // SpectralTransformer.py:85
+    a.tw = c->planx.tw;
+    unsigned grid = 0;
+    int rc = 0;
+#define MLV_GO(L) rc = launch_x1d_advect<L>(c, a, grid)
+    MLV_SWITCH_LOG2(c->log2nx, MLV_GO)
+#undef MLV_GO
+    if (rc) return rc;
+    c->red_count = (int)grid;
+    if (red4) return mlv_reduce_partials(c, nullptr, red4);
     return MLV_OK;
 }
 
@@ -996,9 +1066,10 @@ int mlv_integrate(mlv_ctx* c, const mlv_lin_terms* extra, const mlv_integ* g) {
     IntegKArgs a;
     a.rows = c->spec_rows; a.cols = c->spec_cols; a.nn = c->nn; a.fdm = c->p.fdm_z;
     a.m_off = c->sh.m_off;
+    a.f0_set = g->f0_set ? 1 : 0;
     fill_lin(a.lin, extra);
     fill_integ(a.integ, g);
-    a.k = c->k;
+    a.k = c->k; a.f = fdm_consts(c);
     auto kfn = k_integrate;
     MLV_LAUNCH(kfn, grid1d((size_t)a.rows * a.cols), 256u, 0, c->stream, a);
     return MLV_OK;

@@ -212,7 +212,7 @@ MLV_DEV cplx integrate_value(const IntegArgs& g, cplx f0, cplx q, cplx f1, cplx 
 }
 
 // Extra linear right-hand-side terms  sum_i coef_i * op_i(src_i)
-#define MLV_MAXLIN 4
+#define MLV_MAXLIN 6
 struct LinTerms {
     int n;
     const cplx* src[MLV_MAXLIN];

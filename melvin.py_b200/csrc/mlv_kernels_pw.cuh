@@ -3,7 +3,7 @@
 // across lanes (16-byte complex128 or 8-byte float64 per lane).
 #pragma once
 
-#include "mlv_kernels_fft.cuh"
+#include "mlv_kernels_fdm.cuh"
 
 namespace mlv {
 
@@ -23,6 +23,7 @@ struct SpecLinArgs {
     LinTerms lin;
     cplx* out;
     SpecConsts k;
+    FdmConsts f;                 // FDM-z: row-wise stencil operators
 };
 
 __global__ void __launch_bounds__(256) k_spec_lincomb(const SpecLinArgs a) {
@@ -32,7 +33,8 @@ __global__ void __launch_bounds__(256) k_spec_lincomb(const SpecLinArgs a) {
         const int r = (int)(i / a.cols), m = (int)(i % a.cols);
         const int n = a.fdm ? r : (r <= a.nn ? r : r - 2 * a.nn - 1);
         const int mg = a.fdm ? 0 : m + a.m_off;
-        a.out[i] = (a.fdm || mg < a.nm_glob) ? lin_terms_at(a.lin, i, n, mg, a.k) : mk(0.0, 0.0);
+        if (a.fdm) a.out[i] = fdm_lin_terms_at(a.lin, i, n, m, a.k, a.f);
+        else a.out[i] = mg < a.nm_glob ? lin_terms_at(a.lin, i, n, mg, a.k) : mk(0.0, 0.0);
     }
 }
 
@@ -52,9 +54,11 @@ k_lap_array(double* out, int rows, int cols, int nn, SpecConsts k, double coef, 
 struct IntegKArgs {
     int rows, cols, nn, fdm;
     int m_off;
+    int f0_set;                  // 1: f0 := linear terms (the whole right-hand side); 0: f0 += linear terms
     LinTerms lin;
     IntegArgs integ;
     SpecConsts k;
+    FdmConsts f;
 };
 
 __global__ void __launch_bounds__(256) k_integrate(const IntegKArgs a) {
@@ -64,9 +68,9 @@ __global__ void __launch_bounds__(256) k_integrate(const IntegKArgs a) {
         const int r = (int)(i / a.cols), m = (int)(i % a.cols);
         const int n = a.fdm ? r : (r <= a.nn ? r : r - 2 * a.nn - 1);
         const int mg = a.fdm ? 0 : m + a.m_off;
-        cplx f0 = a.integ.f0[i];
-        if (a.lin.n > 0) {
-            f0 = cadd(f0, lin_terms_at(a.lin, i, n, mg, a.k));
+        cplx f0 = a.f0_set ? mk(0.0, 0.0) : a.integ.f0[i];
+        if (a.lin.n > 0 || a.f0_set) {
+            f0 = cadd(f0, a.fdm ? fdm_lin_terms_at(a.lin, i, n, m, a.k, a.f) : lin_terms_at(a.lin, i, n, mg, a.k));
             a.integ.f0[i] = f0;
         }
         integrate_point(a.integ, f0, i, n, mg, a.k);
@@ -315,93 +319,6 @@ __global__ void __launch_bounds__(256) k_reduce_final4(const double* partial, in
         __syncthreads();
     }
     if (threadIdx.x == 0) out[w] = sm[0];
-}
-
-// ------------------------------------------------------- tridiagonal solve
-// nn independent systems (LaplacianSolver.py:22-56):  rows 1..nz-2:
-//   x[i-1]/dz^2 - (kx_n^2 + 2/dz^2) x[i] + x[i+1]/dz^2 = rhs[i],  x[0]=rhs[0], x[nz-1]=rhs[nz-1].
-// Thomas recurrence with the (real, rhs-independent) forward coefficients
-// cp[n][i] precomputed at context creation.  One warp-sized group of systems per
-// CTA would be uncoalesced (row-major systems), so each CTA stages ROWS systems
-// through shared memory with coalesced loads/stores, one thread per system for
-// the recurrence.
-struct TriArgs {
-    const cplx* rhs;
-    cplx* out;
-    const double* cp;        // (nn, nz) modified upper coefficients c'_i
-    const double* inv;       // (nn, nz) 1/(b_i - a_i c'_{i-1})
-    int nn, nz;
-    double off;              // 1/dz^2 (sub/super diagonal)
-};
-
-template <int ROWS, int CHUNK>
-__global__ void __launch_bounds__(ROWS* CHUNK >= 256 ? 256 : 64) k_tridiag(const TriArgs a) {
-    // Shared tile [ROWS][CHUNK+1] of cplx; processed chunk by chunk along z.
-    cplx* tile = reinterpret_cast<cplx*>(MLV_SMEM_BASE());
-    const int row0 = blockIdx.x * ROWS;
-    const int nt = blockDim.x;
-    // ---- forward sweep: d'_i = (rhs_i - a_i d'_{i-1}) * inv_i   (stored into out)
-    cplx carry = mk(0.0, 0.0);
-    for (int z0 = 0; z0 < a.nz; z0 += CHUNK) {
-        const int len = (a.nz - z0 < CHUNK) ? (a.nz - z0) : CHUNK;
-        for (int t = threadIdx.x; t < ROWS * CHUNK; t += nt) {
-            const int r = t / CHUNK, c = t % CHUNK;
-            if (row0 + r < a.nn && c < len)
-                tile[r * (CHUNK + 1) + c] = a.rhs[(size_t)(row0 + r) * a.nz + z0 + c];
-        }
-        __syncthreads();
-        if ((int)threadIdx.x < ROWS && row0 + (int)threadIdx.x < a.nn) {
-            const int r = threadIdx.x;
-            const size_t base = (size_t)(row0 + r) * a.nz + z0;
-            for (int c = 0; c < len; ++c) {
-                const int i = z0 + c;
-                const double lower = (i == 0 || i == a.nz - 1) ? 0.0 : a.off;
-                const double iv = a.inv[base + c];
-                cplx d = tile[r * (CHUNK + 1) + c];
-                d = mk((d.x - lower * carry.x) * iv, (d.y - lower * carry.y) * iv);
-                tile[r * (CHUNK + 1) + c] = d;
-                carry = d;
-            }
-        }
-        __syncthreads();
-        for (int t = threadIdx.x; t < ROWS * CHUNK; t += nt) {
-            const int r = t / CHUNK, c = t % CHUNK;
-            if (row0 + r < a.nn && c < len)
-                a.out[(size_t)(row0 + r) * a.nz + z0 + c] = tile[r * (CHUNK + 1) + c];
-        }
-        __syncthreads();
-    }
-    // ---- back substitution: x_i = d'_i - c'_i x_{i+1}
-    carry = mk(0.0, 0.0);
-    const int nchunk = (a.nz + CHUNK - 1) / CHUNK;
-    for (int ch = nchunk - 1; ch >= 0; --ch) {
-        const int z0 = ch * CHUNK;
-        const int len = (a.nz - z0 < CHUNK) ? (a.nz - z0) : CHUNK;
-        for (int t = threadIdx.x; t < ROWS * CHUNK; t += nt) {
-            const int r = t / CHUNK, c = t % CHUNK;
-            if (row0 + r < a.nn && c < len)
-                tile[r * (CHUNK + 1) + c] = a.out[(size_t)(row0 + r) * a.nz + z0 + c];
-        }
-        __syncthreads();
-        if ((int)threadIdx.x < ROWS && row0 + (int)threadIdx.x < a.nn) {
-            const int r = threadIdx.x;
-            const size_t base = (size_t)(row0 + r) * a.nz + z0;
-            for (int c = len - 1; c >= 0; --c) {
-                const double cpv = a.cp[base + c];
-                cplx d = tile[r * (CHUNK + 1) + c];
-                d = mk(d.x - cpv * carry.x, d.y - cpv * carry.y);
-                tile[r * (CHUNK + 1) + c] = d;
-                carry = d;
-            }
-        }
-        __syncthreads();
-        for (int t = threadIdx.x; t < ROWS * CHUNK; t += nt) {
-            const int r = t / CHUNK, c = t % CHUNK;
-            if (row0 + r < a.nn && c < len)
-                a.out[(size_t)(row0 + r) * a.nz + z0 + c] = tile[r * (CHUNK + 1) + c];
-        }
-        __syncthreads();
-    }
 }
 
 }  // namespace mlv

@@ -177,11 +177,11 @@ class Context:
             calls = _state["calls"]
             calls[name] = calls.get(name, 0) + 1
 
-    # pool of x-transformed intermediates (nx, ipitch) complex128
+    # pool of x-transformed intermediates: (nx, ipitch) complex128, FDM-z mode: (nn, nz) x spectra
     def take_i(self):
         if self._ipool:
             return self._ipool.pop()
-        return empty((self.nx, self.ipitch), np.complex128)
+        return empty(self.spec_shape if self.fdm_z else (self.nx, self.ipitch), np.complex128)
 
     def give_i(self, t):
         if t is not None and len(self._ipool) < 8:

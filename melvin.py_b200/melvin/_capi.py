@@ -11,6 +11,8 @@ ABI_VERSION = 2
 
 # operator codes (include/melvin_b200.h)
 OP_IDENT, OP_PSI, OP_UX, OP_UZ, OP_DDX, OP_DDZ, OP_D2DX2, OP_D2DZ2, OP_LAP, OP_INVLAP = range(10)
+OP_FDM_D2DZ2, OP_FDM_DDZ, OP_FDM_NABLA2, OP_FDX_SYM = range(10, 14)
+MAXLIN = 6
 SYM_ONE, SYM_FDX, SYM_FDZ = range(3)
 SCHEME_SI_LAP, SCHEME_SI_ARR, SCHEME_EXPLICIT = range(3)
 EW_ADD, EW_SUB, EW_MUL, EW_DIV, EW_COPY, EW_POW = range(6)
@@ -22,7 +24,8 @@ EXPORTS = [
     "mlv_p2p_close", "mlv_set_peer_buffers", "mlv_last_error",
     "mlv_abi_version", "mlv_launch_count", "mlv_to_physical", "mlv_to_spectral", "mlv_x_inverse",
     "mlv_z_inverse", "mlv_z_forward", "mlv_x_forward", "mlv_advect_z", "mlv_advect_z_rows", "mlv_set_reduction_partials", "mlv_reduce_partials", "mlv_advect_phys",
-    "mlv_spec_lincomb", "mlv_lap_array", "mlv_stencil", "mlv_solve_fdm", "mlv_integrate",
+    "mlv_spec_lincomb", "mlv_lap_array", "mlv_stencil", "mlv_solve_fdm", "mlv_fdm_velocity",
+    "mlv_fdm_advect", "mlv_integrate",
     "mlv_elementwise", "mlv_reduce",
 ]
 
@@ -49,14 +52,15 @@ class View(C.Structure):
 
 
 class LinTerms(C.Structure):
-    _fields_ = [("n", C.c_int32), ("op", C.c_int32 * 4), ("src", C.c_void_p * 4),
-                ("cre", C.c_double * 4), ("cim", C.c_double * 4)]
+    _fields_ = [("n", C.c_int32), ("op", C.c_int32 * MAXLIN), ("src", C.c_void_p * MAXLIN),
+                ("cre", C.c_double * MAXLIN), ("cim", C.c_double * MAXLIN)]
 
 
 class Integ(C.Structure):
     _fields_ = [("ab_order", C.c_int32), ("scheme", C.c_int32), ("dt", C.c_double),
                 ("alpha", C.c_double), ("lcoef", C.c_double), ("larr", C.c_void_p),
                 ("q_in", C.c_void_p), ("q_out", C.c_void_p), ("f0", C.c_void_p),
+                ("f0_set", C.c_int32), ("reserved_", C.c_int32),
                 ("fm1", C.c_void_p), ("fm2", C.c_void_p), ("fm3", C.c_void_p)]
 
 
@@ -78,8 +82,8 @@ def make_lin_terms(terms):
     """terms: iterable of (coef: complex, op: int, src_ptr: int)"""
     lt = LinTerms()
     terms = list(terms)
-    if len(terms) > 4:
-        raise MlvError("at most 4 linear terms per call")
+    if len(terms) > MAXLIN:
+        raise MlvError(f"at most {MAXLIN} linear terms per call")
     lt.n = len(terms)
     for i, (coef, op, ptr) in enumerate(terms):
         coef = complex(coef)
@@ -122,6 +126,8 @@ def declare(lib):
         "mlv_lap_array": [vp, f64, vp],
         "mlv_stencil": [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, f64],
         "mlv_solve_fdm": [vp, vp, vp],
+        "mlv_fdm_velocity": [vp, vp, vp, vp, vp],
+        "mlv_fdm_advect": [vp, vp, vp, vp, vp, vp, vp],
         "mlv_integrate": [vp, C.POINTER(LinTerms), C.POINTER(Integ)],
         "mlv_elementwise": [vp, C.POINTER(Ew)],
         "mlv_reduce": [vp, i32, i32, i32, C.POINTER(View), C.POINTER(View), vp],

@@ -411,9 +411,11 @@ def _eval_terms(ctx, terms, out_t, accumulate):
     terms = list(terms)
     first = not accumulate
     while terms:
-        room = 4 if first else 3
+        room = _capi.MAXLIN if first else _capi.MAXLIN - 1
         chunk, terms = terms[:room], terms[room:]
         packed = [(c, op, a._touch()._t.data_ptr()) for c, op, a in chunk]
+        if any(p[2] == out_t.data_ptr() and p[1] >= _capi.OP_FDM_D2DZ2 for p in packed):
+            raise NotImplementedError("a row stencil cannot be evaluated in place")
         if not first:
             packed.append((1.0, _capi.OP_IDENT, out_t.data_ptr()))
         lt = _capi.make_lin_terms(packed)
@@ -427,6 +429,12 @@ class NLTerm:
 
     def __init__(self, ctx, ia, ib):
         self.ctx, self.ia, self.ib = ctx, ia, ib
+
+    def lin_terms(self, coef):
+        """FDM-z mode: ia, ib are the x spectra of ux*q, uz*q and the nonlinear term is
+        d/dx(ux q) + d/dz(uz q) = (i symx) ia + pddz(ib), two row-wise linear terms."""
+        return [(complex(coef), _capi.OP_FDX_SYM, DeviceArray(self.ia)),
+                (complex(coef), _capi.OP_FDM_DDZ, DeviceArray(self.ib))]
 
     def __del__(self):
         try:
@@ -538,6 +546,10 @@ class SpecExpr:
         terms = list(self.terms)
         first = True
         nls = list(self.nls)
+        if ctx.fdm_z:
+            for coef, nl in nls:
+                terms += nl.lin_terms(coef)
+            nls = []
         while nls:
             chunk, nls = nls[:2], nls[2:]
             d = _capi.XFwd()

@@ -87,6 +87,11 @@ class Variable:
         self._fused = (not self._ctx.fdm_z
                        and basis_functions[0] is BasisFunctions.COMPLEX_EXP
                        and basis_functions[1] is BasisFunctions.COMPLEX_EXP)
+        # Fourier-x / FDM-z: the "intermediate" is an x spectrum (nn, nz) itself -- the state,
+        # or a private buffer for ux -- and the deferred physical field is its c2r transform
+        self._fused_fdm = (self._ctx.fdm_z and basis_functions[0] is BasisFunctions.COMPLEX_EXP
+                           and basis_functions[1] is BasisFunctions.FDM)
+        self._hat = None                     # FDM-z: private x spectrum (ux = -pddz(psi))
         # ONE handle per Variable for its whole life (gets() / _sdata always return it, as the
         # reference returns the same ndarray); double buffering re-points its tensor
         self._s = _SpecHandle(_backend.zeros(params.spectral_shape, np.complex128), self)
@@ -207,14 +212,32 @@ class Variable:
     def _ensure_i(self):
         """Make the x-transformed intermediate valid (runs the pending x pass)."""
         if self._i_state == _I_PENDING:
-            _run_x_inverse(self._ctx, [self])
+            if self._ctx.fdm_z:
+                self._fdm_physical()
+            else:
+                _run_x_inverse(self._ctx, [self])
         return self._i_state == _I_VALID
+
+    def _fdm_physical(self):
+        """FDM-z: evaluate the pending definition `pdata = c2r(op(x spectrum))`."""
+        op, src = self._i_def
+        ctx, vp = self._ctx, ctypes.c_void_p
+        self._i_def, self._i_state, self._p_valid = None, _I_VALID, True
+        if op == _capi.OP_PSI:           # streamfunction of a vorticity: psi = solve(-w) = -solve(w)
+            tmp = ctx.take_i()
+            ctx.call("mlv_solve_fdm", vp(src._t.data_ptr()), vp(tmp.data_ptr()))
+            ctx.call("mlv_to_physical", vp(tmp.data_ptr()), None, vp(self._p._t.data_ptr()))
+            ctx.give_i(tmp)
+            DeviceArray(self._p._t)[...] = DeviceArray(self._p._t) * -1.0
+        else:
+            ctx.call("mlv_to_physical", vp(src._t.data_ptr()), None, vp(self._p._t.data_ptr()))
 
     def _ensure_p(self):
         if self._p_valid:
             return
         if self._ctx.fdm_z:
-            raise RuntimeError("internal: FDM-z transforms are eager")
+            self._ensure_i()
+            return
         self._ensure_i()
         self._ctx.call("mlv_z_inverse", ctypes.c_void_p(self._i.data_ptr()),
                        ctypes.c_void_p(self._p._t.data_ptr()))
@@ -230,7 +253,7 @@ class Variable:
     # ------------------------------------------------------- transforms
     def to_physical(self):
         """Convert spectral data to physical"""
-        if self._fused:
+        if self._fused or self._fused_fdm:
             self._request_physical()
         else:
             self._st.to_physical(self._sdata, DeviceArray(self._p._t), self._basis_functions)
@@ -253,8 +276,9 @@ class Variable:
             # takes the (complex-discarding) scaling route (Variable.py:82); here a
             # state of the right shape is loaded as it is and any other resolution is re-sampled
             # in spectral space, on the host for host data (one upload of the final size)
-            nn, nm = self._params.nn, self._params.nm
-            if tuple(data.shape) != (2 * nn + 1, nm):
+            if tuple(data.shape) != tuple(self._params.spectral_shape):
+                # (FDM-z mode has no params.nm: re-sampling fails there as in the reference, App. A-14)
+                nn, nm = self._params.nn, self._params.nm
                 data = scale_variable(data, (nn, nm), np if isinstance(data, np.ndarray) else self._xp)
             self.sets(self._dt.from_host(data))
 
@@ -296,6 +320,8 @@ class Variable:
         """Calculate nabla^2 in spectral form"""
         if self._fused:
             return SpecExpr(self._ctx, [(1.0 + 0j, _capi.OP_LAP, self._sdata)])
+        if self._fused_fdm:
+            return SpecExpr(self._ctx, [(1.0 + 0j, _capi.OP_FDM_NABLA2, self._sdata)])
         return self.sd2dx2() + self.sd2dz2()
 
     def lap(self):
@@ -307,6 +333,14 @@ class Variable:
         """d/dx(ux q) + d/dz(uz q) -> spectral (reference melvin/Variable.py:119-128)."""
         uxo = ux._owner() if isinstance(ux, _PhysHandle) else None
         uzo = uz._owner() if isinstance(uz, _PhysHandle) else None
+        if (self._fused_fdm and out is None and uxo is not None and uzo is not None
+                and uxo._fused_fdm and uzo._fused_fdm
+                and uxo._i_state == _I_PENDING and uzo._i_state == _I_PENDING
+                and uxo._i_def[0] == _capi.OP_IDENT and uzo._i_def[0] == _capi.OP_IDENT):
+            if convert_to_physical:
+                self._request_physical()
+            if self._i_state == _I_PENDING and self._i_def[0] == _capi.OP_IDENT:
+                return self._vec_dot_nabla_fdm(uxo, uzo)
         fused = (self._fused and out is None and uxo is not None and uzo is not None
                  and uxo._fused and uzo._fused
                  and uxo._i_state != _I_NONE and uzo._i_state != _I_NONE)
@@ -331,6 +365,23 @@ class Variable:
         ctx.call("mlv_advect_z", ctypes.c_void_p(uxo._i.data_ptr()), ctypes.c_void_p(uzo._i.data_ptr()),
                  ctypes.c_void_p(self._i.data_ptr()), ctypes.c_void_p(ia.data_ptr()),
                  ctypes.c_void_p(ib.data_ptr()), None)
+        ctx.call("mlv_set_reduction_partials", None, count=False)
+        shared = {"part": uxo._red_part, "host": None}
+        uxo._red = (shared, 0, 2)
+        uzo._red = (shared, 1, 3)
+        return SpecExpr(ctx, [], [(1.0, NLTerm(ctx, ia, ib))])
+
+    def _vec_dot_nabla_fdm(self, uxo, uzo):
+        """Fourier-x / FDM-z: fused c2r x 3 -> products -> r2c x 2 on the x spectra of the
+        velocities and of the scalar; the two derivatives become row-wise linear terms of the
+        right-hand side (NLTerm.lin_terms)."""
+        ctx, vp = self._ctx, ctypes.c_void_p
+        ia, ib = ctx.take_i(), ctx.take_i()
+        if uxo._red_part is None:
+            uxo._red_part = _backend.empty((ctx.red_doubles,), np.float64)
+        ctx.call("mlv_set_reduction_partials", vp(uxo._red_part.data_ptr()), count=False)
+        ctx.call("mlv_fdm_advect", vp(uxo._i_def[1]._t.data_ptr()), vp(uzo._i_def[1]._t.data_ptr()),
+                 vp(self._i_def[1]._t.data_ptr()), vp(ia.data_ptr()), vp(ib.data_ptr()), None)
         ctx.call("mlv_set_reduction_partials", None, count=False)
         shared = {"part": uxo._red_part, "host": None}
         uxo._red = (shared, 0, 2)

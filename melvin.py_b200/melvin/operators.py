@@ -180,7 +180,7 @@ class SpatialDifferentiator:
         self.sd2dx2 = self.__s_d2dx2
         if params.discretisation[1] == "fdm":
             self.sddz = lambda var, bs: self.pddz(var)
-            self.sd2dz2 = lambda var, bs: self.pd2dz2(var)
+            self.sd2dz2 = self.__s_d2dz2_fdm
         else:
             self.sddz = self.__s_ddz
             self.sd2dz2 = self.__s_d2dz2
@@ -212,6 +212,14 @@ class SpatialDifferentiator:
 
     def __s_d2dz2(self, var, basis_fn):
         return self._term(var, basis_fn, _capi.OP_D2DZ2)
+
+    def __s_d2dz2_fdm(self, var, basis_fn):
+        """FDM-z: the second z difference of a spectral array (SpatialDifferentiator.py:36-40,
+        106-128) as a deferred row-stencil term; other operands go through the eager stencil."""
+        a = var if isinstance(var, DeviceArray) else None
+        if a is not None and SpecExpr._lift(self._ctx, a) is not None:
+            return SpecExpr(self._ctx, [(1.0 + 0j, _capi.OP_FDM_D2DZ2, a)])
+        return self.pd2dz2(var)
 
     def calc_lap(self, basis_fns):
         """SpatialDifferentiator.py:70-74"""
@@ -399,6 +407,10 @@ class Integrator:
             # somebody (psi/ux/uz, a requested transform, another deferred right-hand side)
             # still reads the old state: write the new one into the second buffer
             double = var._has_dependants(q_in, exclude=pending)
+            # a row stencil of the state itself reads neighbours other threads are updating
+            stencil = any(op >= _capi.OP_FDM_D2DZ2 and op != _capi.OP_FDX_SYM and a._t.data_ptr() == q_in.data_ptr()
+                          for _, op, a in (list(pending.terms) if pending is not None else []) + list(extra))
+            double = double or stencil
             if double:
                 if var._s_spare is None:
                     var._s_spare = _backend.empty(tuple(q_in.shape), np.complex128)
@@ -420,9 +432,20 @@ class Integrator:
             g.fm2, g.fm3 = older[1].data_ptr(), older[2].data_ptr()
         keep = [larr]
         lin = list(extra)
-        fused = (pending is not None and 1 <= len(pending.nls) <= 2
+        fused = (not ctx.fdm_z and pending is not None and 1 <= len(pending.nls) <= 2
                  and len(pending.terms) + len(lin) <= 4)
-        if fused:
+        fdm_terms = None
+        if ctx.fdm_z and pending is not None:
+            fdm_terms = [t for coef, nl in pending.nls for t in nl.lin_terms(coef)] + list(pending.terms) + lin
+            if len(fdm_terms) > _capi.MAXLIN:
+                fdm_terms = None
+        if fdm_terms is not None:
+            # K3: the whole right-hand side (row stencils included), the history write and the
+            # update in one row-wise kernel
+            g.f0_set = 1
+            lt = _capi.make_lin_terms([(c, op, a._touch()._t.data_ptr()) for c, op, a in fdm_terms])
+            ctx.call("mlv_integrate", ctypes.byref(lt), ctypes.byref(g))
+        elif fused:
             d = _capi.XFwd()
             d.nf, d.mode = 2 * len(pending.nls), 1
             for i, (coef, nl) in enumerate(pending.nls):
@@ -447,11 +470,11 @@ class Integrator:
         """dvar += diffusion; var += AB(dvar); advance (Integrator.py:53-56)"""
         if isinstance(diffusion_term, SpecExpr) and not diffusion_term.nls \
                 and len(diffusion_term.terms) <= 4:
-            extra = diffusion_term.terms
+            extra = list(diffusion_term.terms)
         else:
             extra = [(1.0 + 0j, _capi.OP_IDENT, _dev(diffusion_term, np.complex128))]
         pend = dvar._pending
-        if pend is not None and (len(pend.terms) + len(extra) > 4 or not pend.nls):
+        if pend is not None and not self._ctx.fdm_z and (len(pend.terms) + len(extra) > 4 or not pend.nls):
             dvar._flush()
         self._launch(var, dvar, _capi.SCHEME_EXPLICIT, 0.0, None, extra)
 

@@ -66,6 +66,10 @@ def calc_velocity_from_vorticity(vorticity, streamfunction, ux, uz, laplacian_so
         uz._request_physical()
         return
 
+    if all(getattr(v, "_fused_fdm", False) for v in (vorticity, psi, ux, uz)):
+        _velocity_fdm(vorticity, psi, ux, uz)
+        return
+
     laplacian_solver.solve(-vorticity.gets(), out=psi._sdata)
     if psi._basis_functions[1] is BasisFunctions.FDM:
         psi.to_physical()
@@ -79,3 +83,34 @@ def calc_velocity_from_vorticity(vorticity, streamfunction, ux, uz, laplacian_so
     else:
         uz[:] = psi.sddx()
         uz.to_physical()
+
+
+def _velocity_fdm(vorticity, psi, ux, uz):
+    """Fourier-x / FDM-z branch in ONE row-wise kernel (mlv_fdm_velocity): the batched
+    tridiagonal solve psi = solve(-w), uz^ = (i kx n) psi written to uz's spectral data as the
+    reference does, and ux^ = -pddz(psi) kept as a private x spectrum (the reference never
+    writes ux._sdata in this mode; its z stencil acts on psi in physical
+    space, which commutes with the x transform).  The three physical fields are deferred."""
+    import ctypes
+    from . import _backend
+    from .b200 import DeviceArray
+    from .fields import _I_NONE, _I_PENDING
+    ctx, vp = vorticity._ctx, ctypes.c_void_p
+    w_t = vorticity.gets()._touch()._t
+    for v in (psi, ux, uz):                   # their pending physical requests are being replaced
+        v._i_state, v._i_def, v._red = _I_NONE, None, None
+    psi._virt = uz._virt = None
+    psi._flush_dependants(psi._s._t)
+    uz._flush_dependants(uz._s._t)
+    if ux._hat is None:
+        ux._hat = _backend.empty(ctx.spec_shape, np.complex128)
+    else:
+        ux._flush_dependants(ux._hat)
+    ctx.call("mlv_fdm_velocity", vp(w_t.data_ptr()), vp(psi._s._t.data_ptr()),
+             vp(ux._hat.data_ptr()), vp(uz._s._t.data_ptr()))
+    # psi.to_physical(); ux.setp(-psi.pddz()); uz.to_physical()  (utility.py:67-79), all deferred.
+    # psi's physical field is re-derived from the vorticity buffer if somebody asks: the scripts'
+    # boundary fix-ups write psi's spectral data every step and must not force a transform
+    psi._i_def, psi._i_state, psi._p_valid = (_capi.OP_PSI, DeviceArray(w_t)), _I_PENDING, False
+    ux._i_def, ux._i_state, ux._p_valid = (_capi.OP_IDENT, DeviceArray(ux._hat)), _I_PENDING, False
+    uz._i_def, uz._i_state, uz._p_valid = (_capi.OP_IDENT, DeviceArray(uz._s._t)), _I_PENDING, False

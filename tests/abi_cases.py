@@ -207,6 +207,111 @@ def case_fdm_solver_and_stencils(H):
         ctx.close()
 
 
+def case_fdm_fused_step(H, nx, nz, order, truth_rows=4):
+    """K1 (batched solve + velocities), K2 (fused 1-D advection) and K3 (row-wise right-hand side +
+    AB + explicit update) against the oracle's eager statements of the same operations
+    (utility.py:62-79, Variable.py:119-128, Integrator.py:53-56)."""
+    g = mo.Grid(nx, nz, 2.44, 1.0, fdm_z=True, fd_order=order, integrator="explicit", int_order=4)
+    ctx = H.Ctx(nx, nz, 2.44, 1.0, fdm_z=True, fd_order=order)
+    rng = np.random.default_rng(nx + nz + order)
+    cplx = lambda: rng.standard_normal(g.spectral_shape) + 1j * rng.standard_normal(g.spectral_shape)  # noqa: E731
+    w = mo.to_spectral(g, rng.standard_normal((nx, nz)))
+    q = mo.to_spectral(g, rng.standard_normal((nx, nz)))
+    # ---- K1: psi = solve(-w), uxh = -pddz(psi), uzh = i kx psi
+    psi, uxh, uzh = (np.zeros(g.spectral_shape, complex) for _ in range(3))
+    ctx.call("mlv_fdm_velocity", H.ptr(w), H.ptr(psi), H.ptr(uxh), H.ptr(uzh))
+    vel = mo.velocity_from_vorticity(g, w)
+    # two fp64 Thomas variants (c' = a/den there, a * (1/den) here) differ by an ulp per pivot, which
+    # the conditioning of the n = 0 system (~nz^2) amplifies; identical when 1/dz^2 is a power of two
+    assert rel(psi, vel["psi_s"]) < 1e-11
+    assert rel(uzh, vel["uz_s"]) < 1e-11
+    # the z stencil commutes with the x transform: c2r(uxh) == -pddz(c2r(psi))
+    assert rel(mo.to_physical(g, uxh), vel["ux_p"]) < 1e-11
+    # F8 gate: at least as close to the extended-precision solution as the oracle's fp64 Thomas
+    rows = sorted(set(np.linspace(0, g.nn - 1, truth_rows).astype(int)))
+    truth = np.stack([thomas_longdouble_row(g, -w[n], n) for n in rows])
+    err_dev = max(float(np.linalg.norm(psi[n] - t) / np.linalg.norm(t)) for n, t in zip(rows, truth))
+    err_ora = max(float(np.linalg.norm(vel["psi_s"][n] - t) / np.linalg.norm(t)) for n, t in zip(rows, truth))
+    # ... and than the reference's own SuperLU solve of the same systems (scipy.sparse.linalg.factorized,
+    # LaplacianSolver.py:53-55), which is the accuracy the 1e-12 parity gate cannot exceed on this path
+    err_slu = max(float(np.linalg.norm(superlu_row(g, -w[n], n) - t) / np.linalg.norm(t)) for n, t in zip(rows, truth))
+    assert err_dev < 1e-9 and err_dev < 2 * err_ora + 1e-15 and err_dev < 2 * err_slu + 1e-15, (err_dev, err_ora, err_slu)
+    out = np.zeros_like(w)
+    ctx.call("mlv_solve_fdm", H.ptr(q), H.ptr(out))
+    assert rel(out, mo.solve_fdm(g, q)) < 1e-11
+    # ---- K2: x spectra of ux q and uz q, reductions
+    A, B = np.zeros_like(w), np.zeros_like(w)
+    red = np.zeros(4)
+    ctx.call("mlv_fdm_advect", H.ptr(uxh), H.ptr(uzh), H.ptr(q), H.ptr(A), H.ptr(B), H.ptr(red))
+    ux_p, uz_p, q_p = mo.to_physical(g, uxh), mo.to_physical(g, uzh), mo.to_physical(g, q)
+    assert rel(A, mo.to_spectral(g, ux_p * q_p)) < 1e-12
+    assert rel(B, mo.to_spectral(g, uz_p * q_p)) < 1e-12
+    np.testing.assert_allclose(red, [ux_p.max(), uz_p.max(), (ux_p ** 2).sum(), (uz_p ** 2).sum()], rtol=1e-12)
+    # ---- K3: f0 = -(d/dx(ux q) + d/dz(uz q)) - 3 ddx(w) + 0.5 snabla2(q); AB4 explicit update of q
+    nl, _ = mo.vec_dot_nabla(g, q, ux_p, uz_p)
+    f0_want = -nl - 3.0 * mo.sddx(g, w) + 0.5 * mo.snabla2(g, q)
+    hist = mo.History(g)
+    for k in range(1, 4):
+        hist.data[k] = cplx()
+    hist.curr = 0
+    hist.set_current(f0_want)
+    q_want = mo.integrate_explicit(g, q.copy(), hist, 0.0 * q, 1e-3)
+    f0, q_new = np.zeros_like(w), np.zeros_like(w)
+    fm = [hist.data[k].copy() for k in (3, 2, 1)]            # curr-1, curr-2, curr-3 with negative wrap
+    lt = _capi.make_lin_terms([(-1.0, _capi.OP_FDX_SYM, H.ptr(A)), (-1.0, _capi.OP_FDM_DDZ, H.ptr(B)),
+                               (-3.0, _capi.OP_DDX, H.ptr(w)), (0.5, _capi.OP_FDM_NABLA2, H.ptr(q))])
+    gi = _capi.Integ()
+    gi.ab_order, gi.scheme, gi.dt, gi.f0_set = 4, _capi.SCHEME_EXPLICIT, 1e-3, 1
+    gi.q_in, gi.q_out, gi.f0 = H.ptr(q), H.ptr(q_new), H.ptr(f0)
+    gi.fm1, gi.fm2, gi.fm3 = H.ptr(fm[0]), H.ptr(fm[1]), H.ptr(fm[2])
+    ctx.call("mlv_integrate", ctypes.byref(lt), ctypes.byref(gi))
+    assert rel(f0, f0_want) < 1e-11
+    assert rel(q_new, q_want) < 1e-12
+    # the stencil operators alone, through the expression kernel
+    for op, want in ((_capi.OP_FDM_D2DZ2, mo.pd2dz2(g, q)), (_capi.OP_FDM_DDZ, mo.pddz(g, q)),
+                     (_capi.OP_FDM_NABLA2, mo.snabla2(g, q))):
+        lt1 = _capi.make_lin_terms([(1.0, op, H.ptr(q))])
+        ctx.call("mlv_spec_lincomb", ctypes.byref(lt1), H.ptr(out))
+        assert rel(out, want) < 1e-13, op
+    ctx.close()
+
+
+def superlu_row(g, r, n):
+    """The reference's solver for system n: the matrix of LaplacianSolver.py:25-49 factorised by SuperLU."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spl
+    nz = r.shape[0]
+    kx = n * 2 * np.pi / g.lx
+    diag = np.full(nz, -(kx ** 2 + 2.0 / g.dz ** 2))
+    off = np.full(nz, 1.0 / g.dz ** 2)
+    m = sp.dia_matrix((np.array([off, diag, off]), np.array([-1, 0, 1])), shape=(nz, nz), dtype=np.complex128).tolil()
+    m[0, 0], m[0, 1], m[-1, -1], m[-1, -2] = 1.0, 0.0, 1.0, 0.0
+    return spl.factorized(m.tocsc())(r.astype(np.complex128))
+
+
+def thomas_longdouble_row(g, r, n):
+    """One system of LaplacianSolver.py:22-56 in extended precision."""
+    ld, cld = np.longdouble, np.clongdouble
+    nz = r.shape[0]
+    off = ld(1) / (ld(g.dz) * ld(g.dz))
+    kx = ld(n) * ld(2) * ld(np.pi) / ld(g.lx)
+    b = -(kx * kx + ld(2) * off)
+    rr = r.astype(cld)
+    cp = np.zeros(nz, dtype=ld)
+    dp = np.zeros(nz, dtype=cld)
+    dp[0] = rr[0]
+    for i in range(1, nz - 1):
+        den = b - off * cp[i - 1]
+        cp[i] = off / den
+        dp[i] = (rr[i] - off * dp[i - 1]) / den
+    dp[nz - 1] = rr[nz - 1]
+    x = np.zeros(nz, dtype=cld)
+    x[nz - 1] = dp[nz - 1]
+    for i in range(nz - 2, -1, -1):
+        x[i] = dp[i] - cp[i] * x[i + 1]
+    return x
+
+
 def case_integrate_and_array_ops(H):
     nx, nz = 32, 32
     ctx = H.Ctx(nx, nz, 1.0, 1.0)

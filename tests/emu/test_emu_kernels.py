@@ -56,3 +56,10 @@ def test_fdm_solver_and_stencils():
 
 def test_integrate_and_array_ops():
     ac.case_integrate_and_array_ops(H)
+
+
+@pytest.mark.parametrize("nx,nz,order", [(64, 13, 2), (64, 40, 4), (32, 300, 4), (16, 2048, 2), (16, 2500, 4)])
+def test_fdm_fused_step(nx, nz, order):
+    """batched scan solver (one and several unknowns per thread, 256 and 512 threads), fused
+    1-D advection and the row-wise right-hand side / update"""
+    ac.case_fdm_fused_step(H, nx, nz, order)

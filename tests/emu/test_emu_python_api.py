@@ -198,9 +198,16 @@ def test_tearing_loop_matches_golden():
 def test_rbc_fdm_loop_matches_golden(order, ab):
     import parity_cases as pc
     gl = golden(f"loop_rbc_64x32_o{order}_ab{ab}.npz")
+    before = _backend.call_counts()
     with pc.scratch_cwd():
         out = pc.run_rbc(64, 32, order, ab, float(gl["dt"]), 10, float(gl["Pr"]), float(gl["Ra"]),
                          snaps=(1, 10))
+    after = _backend.call_counts()
+    used = {k: after.get(k, 0) - before.get(k, 0) for k in after}
+    # the fused three-kernel step ran: one solve+velocities, one fused advection and one row-wise
+    # right-hand side + update per scalar and step; nothing through the eager stencil kernels
+    assert used["mlv_fdm_velocity"] == 10 and used["mlv_fdm_advect"] == 20 and used["mlv_integrate"] == 20
+    assert not any(used.get(k, 0) for k in ("mlv_stencil", "mlv_advect_phys", "mlv_solve_fdm", "mlv_to_physical"))
     for k in (1, 10):
         for nm in ("w", "tmp", "psi"):
             assert rel(out[f"{nm}_step{k}"], gl[f"{nm}_step{k}"]) < 1e-10, (nm, k)

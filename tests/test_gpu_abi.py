@@ -60,6 +60,15 @@ def test_fdm_solver_and_stencils(H):
     ac.case_fdm_solver_and_stencils(H)
 
 
+@pytest.mark.parametrize("nx,nz,order", [(64, 13, 2), (64, 40, 4), (32, 300, 4), (16, 2048, 2), (16, 2500, 4),
+                                         (4096, 2048, 4)])
+def test_fdm_fused_step(H, nx, nz, order):
+    """Fourier-x / FDM-z kernels (batched scan solver + velocities, fused 1-D advection, row-wise
+    right-hand side and update) vs the oracle, incl. the BASELINE config-3 grid 4096 x 2048 and the
+    F8 gate of the solver against an extended-precision solution and the reference's SuperLU."""
+    ac.case_fdm_fused_step(H, nx, nz, order)
+
+
 def test_integrate_and_array_ops(H):
     ac.case_integrate_and_array_ops(H)
 

@@ -264,6 +264,28 @@ def test_one_step_at_baseline_size_4096():
     np.testing.assert_allclose(out["ke"], run.ke, rtol=SERIES_TOL)
 
 
+@pytest.mark.parametrize("nx,nz,nsteps", [(4096, 2048, 3), (256, 300, 6)])
+def test_rayleigh_benard_at_baseline_size(nx, nz, nsteps):
+    """BASELINE config 3 (Fourier-x / 4th-order FD z, AB4 explicit) at 4096 x 2048 through the
+    public API -- the fused three-kernel step with the batched scan solver at nz = 2048 -- vs the
+    oracle's eager restatement of examples/rayleigh_benard_convection.py:95-145.  FDM gate (SURVEY
+    F8): the two fp64 tridiagonal solvers differ at the conditioning level of the n = 0 system."""
+    Pr, Ra = 0.5, 1e6
+    dt = min(1e-6, 0.05 / nz ** 2)
+    g = mo.Grid(nx, nz, 2.44, 1.0, fdm_z=True, fd_order=4, int_order=4, integrator="explicit")
+    run = mo.Run(g, dt, tracker_cadence=1)
+    state = (mo.to_spectral(g, mo.ic_noise(g)), mo.to_spectral(g, mo.ic_rbc_temperature(g)),
+             np.zeros(g.spectral_shape, complex))
+    hists = (mo.History(g), mo.History(g))
+    for _ in range(nsteps):
+        state = mo.step_rayleigh_benard(g, run, state, hists, Pr, Ra)
+    with pc.scratch_cwd():
+        out = pc.run_rbc(nx, nz, 4, 4, dt, nsteps, Pr, Ra, snaps=(nsteps,))
+    for nm, arr in zip(("w", "tmp", "psi"), state):
+        assert rel_l2(out[f"{nm}_step{nsteps}"], arr) < 1e-10, nm
+    np.testing.assert_allclose(out["ke"], run.ke, rtol=SERIES_TOL)
+
+
 @pytest.mark.parametrize("nx,nz", [(16384, 64), (64, 16384)])
 def test_steps_with_16384_point_lines(nx, nz):
     """BASELINE config-5 line length through the public API (long-line kernels: split x
