@@ -186,6 +186,12 @@ int mlv_p2p_alloc(mlv_ctx* ctx, int64_t bytes, void** ptr, void* handle64);
 int mlv_p2p_open(mlv_ctx* ctx, const void* handle64, void** ptr);
 int mlv_p2p_close(mlv_ctx* ctx, void* ptr, int opened);
 int mlv_set_peer_buffers(mlv_ctx* ctx, int which, void* const* bufs);
+/* Device-side ordering of the peer-store exchange: counters[h] = rank h's pair of 64-bit arrival
+ * counters (zero-initialised peer-mapped memory, [0] inverse, [1] forward).  Producer CTAs bump
+ * the counter of every rank after their stores (release.sys), consumer CTAs spin on their own
+ * (acquire.sys) -- no collective and no host synchronisation between the kernels of a step.
+ * All ranks must issue the same sequence of calls.  NULL switches it off. */
+int mlv_set_peer_flags(mlv_ctx* ctx, void* const* counters);
 /* Alternative for large grids: the kernels write their blocks locally and the caller moves
  * each contiguous peer block with an asynchronous device-to-device copy into the peer's
  * (IPC-mapped) receive buffer on `cuda_stream` -- copy engines drive NVLink at full width and

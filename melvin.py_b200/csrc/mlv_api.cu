@@ -62,6 +62,11 @@ struct mlv_ctx {
     mlv::cplx* peer_inv[MLV_MAXPEER] = {};
     mlv::cplx* peer_fwd[MLV_MAXPEER] = {};
     bool p2p_inv = false, p2p_fwd = false;
+    // device-side ordering of the peer-store exchange (mlv_set_peer_flags): per rank two arrival
+    // counters [0] inverse blocks, [1] forward blocks; expect[] = arrivals due at this rank so far
+    unsigned long long* peer_flags[MLV_MAXPEER] = {};
+    bool flags_on = false;
+    unsigned long long expect[2] = {0, 0};
     mlv::stream_t stream = 0;
 };
 
@@ -733,6 +738,15 @@ int mlv_set_peer_buffers(mlv_ctx* c, int which, void* const* bufs) {
     return MLV_OK;
 }
 
+int mlv_set_peer_flags(mlv_ctx* c, void* const* counters) {
+    if (!c) { set_error("mlv_set_peer_flags: null context"); return MLV_ERR_INVALID; }
+    c->flags_on = counters != nullptr;
+    for (int h = 0; h < c->nranks && h < MLV_MAXPEER; ++h)
+        c->peer_flags[h] = counters ? (unsigned long long*)counters[h] : nullptr;
+    c->expect[0] = c->expect[1] = 0;
+    return MLV_OK;
+}
+
 int mlv_long_lines(const mlv_ctx* c) {
     return c ? ((c->xsplit ? 1 : 0) | (c->zreal ? 2 : 0)) : 0;
 }
@@ -761,6 +775,17 @@ int mlv_x_inverse(mlv_ctx* c, int nf, const void* const* spec, const int32_t* op
     XInvArgs a;
     a.nn = c->nn; a.nm = c->nm_loc; a.spitch = c->spec_cols; a.ipitch = c->nml; a.nf = nf;
     a.sh = c->sh;
+    a.sig.n = 0;
+    if (c->p2p_inv && c->flags_on) {
+        // every x-pass CTA of every rank will bump the inverse counter of every rank once
+        for (int r = 0; r < c->nranks; ++r) {
+            int left = c->nm - r * c->nml;
+            left = left < 0 ? 0 : (left > c->nml ? c->nml : left);
+            c->expect[0] += (unsigned long long)((left + c->ct - 1) / c->ct);
+            a.sig.counter[r] = c->peer_flags[r];
+        }
+        a.sig.n = c->nranks;
+    }
     if (c->nm_loc <= 0) return MLV_OK;              // this rank owns no retained column
     for (int f = 0; f < nf; ++f) {
         if (!spec[f] || !idst[f] || op[f] < MLV_OP_IDENT || op[f] > MLV_OP_INVLAP) {
@@ -837,6 +862,8 @@ int mlv_x_forward(mlv_ctx* c, const mlv_xfwd* d) {
     XFwdArgs a;
     a.nn = c->nn; a.nm = c->nm_loc; a.spitch = c->spec_cols; a.ipitch = c->nml; a.nf = d->nf;
     a.sh = c->sh;
+    a.wait_counter = nullptr; a.wait_value = 0;
+    if (c->p2p_fwd && c->flags_on) { a.wait_counter = c->peer_flags[c->rank] + 1; a.wait_value = c->expect[1]; }
     if (c->nm_loc <= 0) return MLV_OK;
     for (int f = 0; f < d->nf; ++f) {
         if (!d->src[f] || d->sym[f] < MLV_SYM_ONE || d->sym[f] > MLV_SYM_FDZ) {
@@ -941,6 +968,11 @@ int mlv_advect_z_rows(mlv_ctx* c, const void* iux, const void* iuz, const void* 
             a.out.blk[h] = (cplx*)ia + (size_t)h * c->sh.fwd_peer;
         }
     }
+    if (c->p2p_inv && c->flags_on) { a.wait_counter = c->peer_flags[c->rank]; a.wait_value = c->expect[0]; }
+    if (c->p2p_fwd && c->flags_on) {
+        a.sig.n = c->nranks;
+        for (int r = 0; r < c->nranks; ++r) a.sig.counter[r] = c->peer_flags[r] + 1;
+    }
     unsigned grid = 0;
     int rc = 0;
     a.tws = c->tws_z;
@@ -954,6 +986,7 @@ int mlv_advect_z_rows(mlv_ctx* c, const void* iux, const void* iuz, const void* 
 #undef MLV_GO
     }
     if (rc) return rc;
+    if (a.sig.n) c->expect[1] += (unsigned long long)grid * (unsigned long long)c->nranks;
     // per-CTA partials of the rows [0, row0 + nrows) launched so far
     c->red_count = (int)((long long)grid * (row0 + nrows) / nrows);
     if (red4) return mlv_reduce_partials(c, nullptr, red4);

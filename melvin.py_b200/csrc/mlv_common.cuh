@@ -238,6 +238,30 @@ MLV_DEV void tma_load_2d(void* smem, const CUtensorMap* map, int c0, int c1, uns
 #endif
 }
 
+// ---- cross-GPU ordering of producer and consumer kernels (peer-memory exchange): every
+// producer CTA bumps a 64-bit arrival counter in each consumer rank's memory after its stores
+// (release at system scope); consumer CTAs spin on their own rank's counter (acquire at system
+// scope) until the arrivals of all producer CTAs of all ranks are in.  Counters only grow; the
+// host passes the cumulative count a launch has to wait for.
+MLV_DEV void flag_signal(unsigned long long* counter) {
+#ifndef MLV_EMU
+    __threadfence_system();
+    asm volatile("red.release.sys.global.add.u64 [%0], 1;" ::"l"(counter) : "memory");
+#else
+    (void)counter;
+#endif
+}
+MLV_DEV void flag_wait(const unsigned long long* counter, unsigned long long value) {
+#ifndef MLV_EMU
+    unsigned long long cur;
+    do {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(cur) : "l"(counter) : "memory");
+    } while (cur < value);
+#else
+    (void)counter; (void)value;
+#endif
+}
+
 // Reciprocal to ~1 ulp without the branchy IEEE division sequence: 20-bit hardware
 // seed + two Newton steps (operands here are O(1)..O(1e9), never denormal or zero).
 MLV_DEV double fast_rcp(double x) {

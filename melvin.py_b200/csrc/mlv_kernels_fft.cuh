@@ -128,6 +128,23 @@ struct Shard {
 struct PeerBlocks {
     cplx* blk[MLV_MAXPEER];
 };
+// Arrival counters of one exchange direction, one per rank (null: no device-side ordering).
+struct PeerSignals {
+    int n;                                   // ranks to signal (0: none)
+    unsigned long long* counter[MLV_MAXPEER];
+};
+// last statement of a producer CTA: all of its stores are done
+MLV_DEV void signal_peers(const PeerSignals& s) {
+    if (s.n == 0) return;
+    __syncthreads();
+    if ((int)threadIdx.x < s.n) flag_signal(s.counter[threadIdx.x]);
+}
+// first statement of a consumer CTA
+MLV_DEV void wait_arrivals(const unsigned long long* counter, unsigned long long value) {
+    if (counter == nullptr) return;
+    if (threadIdx.x == 0) flag_wait(counter, value);
+    __syncthreads();
+}
 
 // element (local row xl, tile tl of its owner, column cc of the tile) inside the send region of
 // the tile owner
@@ -239,6 +256,7 @@ struct XInvArgs {
     cplx* dst[MLV_XMAXF];
     Shard sh;                    // nm = local valid columns; spectral ops use m + sh.m_off
     PeerBlocks out;              // destination block per row owner; dst[f] are offsets into it
+    PeerSignals sig;             // peer stores: arrival counters of the inverse exchange
     long long dstoff[MLV_XMAXF];
     SpecConsts k;
     FftTw tw;
@@ -403,6 +421,7 @@ k_xinv(const __grid_constant__ XInvArgs a) {
         }
     }
     if (tma_pending && threadIdx.x == 0) tma_wait_read();       // shared memory must outlive the reads
+    signal_peers(a.sig);
 }
 
 // ===================================================================== x forward
@@ -425,6 +444,8 @@ struct XFwdArgs {
     FftTw tw;
     const cplx* tws;             // SPLIT = 2: e^{-2 pi i p/nx}, p < nx/2
     int stage;                   // 1: the block of operand 0 is staged in shared memory by bulk copies
+    const unsigned long long* wait_counter;   // peer stores: forward blocks of all ranks have arrived
+    unsigned long long wait_value;            // when *wait_counter >= wait_value
 };
 
 // I (tile layout) x nf -> spectral: value = scale * FFT_x( sum_f coef_f * D_f[src_f] ), rows
@@ -451,6 +472,7 @@ k_xfwd(const XFwdArgs a) {
     xc.c = c;
     const double sz = a.symz[m + a.sh.m_off];
     const int rpc = 1 << a.sh.fwd_rshift;             // rows per block of the forward buffers
+    wait_arrivals(a.wait_counter, a.wait_value);
     {   // L2 prefetch: the other fields' blocks, the next CTA's first block, and the
         // state / history columns the epilogue will read
         constexpr unsigned CHUNK = 16384;
@@ -901,6 +923,9 @@ struct ZAdvArgs {
     const cplx* Iuz;
     const cplx* Iq;
     PeerBlocks out;                // destination block per tile owner; IA/IB given as offsets
+    PeerSignals sig;               // peer stores: arrival counters of the forward exchange
+    const unsigned long long* wait_counter;   // peer stores: inverse blocks of all ranks have arrived
+    unsigned long long wait_value;
     long long outoff[2];
     cplx* IA;                      // out: z-spectrum of ux q   (tile layout)
     cplx* IB;                      // out: z-spectrum of uz q
@@ -929,6 +954,7 @@ k_z_advect(const ZAdvArgs a) {
     const size_t rowoff = (size_t)(2 * rp) * a.ipitch;
     const int cts = log2_pow2(a.ct);                 // tile width is a power of two
     const bool sharded = a.sh.fwd_chunk != 0;
+    wait_arrivals(a.wait_counter, a.wait_value);
 
     // announce the rows of the two velocity components (needed one and two transforms
     // from now) and the scalar rows of the CTA that will follow this one on the SM
@@ -1026,6 +1052,7 @@ k_z_advect(const ZAdvArgs a) {
         }
         if (w < 4 && g == 0) a.red[(size_t)blockIdx.x * 4 + w] = rbuf[w * NT];
     }
+    signal_peers(a.sig);
 }
 
 }  // namespace mlv

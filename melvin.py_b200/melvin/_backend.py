@@ -132,7 +132,7 @@ def synchronize():
 class Context:
     """One mlv_ctx per Parameters object (plans for one grid)."""
 
-    def __init__(self, nx, nz, lx, lz, fdm_z, fd_order):
+    def __init__(self, nx, nz, lx, lz, fdm_z, fd_order, shard=None):
         self.lib = lib()
         p = _capi.Params()
         p.nx, p.nz, p.fdm_z, p.fd_order = int(nx), int(nz), int(bool(fdm_z)), int(fd_order)
@@ -145,11 +145,22 @@ class Context:
         h = ctypes.c_void_p()
         _capi.check(self.lib, self.lib.mlv_create(ctypes.byref(p), ctypes.byref(h)))
         self.handle = h
+        # slab decomposition behind the public API (melvin/_dist.py): local shapes from here on
+        self.rank, self.world = shard if shard else (0, 1)
+        if self.world > 1:
+            _capi.check(self.lib, self.lib.mlv_set_sharding(h, self.rank, self.world, 1, 1))
         info = _capi.Info()
         _capi.check(self.lib, self.lib.mlv_get_info(h, ctypes.byref(info)))
         self.nn, self.nm = info.nn, info.nm
-        self.spec_shape = (info.spec_rows, info.spec_cols)
+        self.spec_shape = (info.spec_rows, info.spec_cols)           # local (rows, columns of this rank)
+        self.global_spec_shape = (info.spec_rows, info.nm if self.world > 1 else info.spec_cols)
         self.ipitch = info.ipitch
+        self.nm_local = info.nm_local
+        self.m_off = self.rank * info.spec_cols if self.world > 1 else 0
+        self.nxl = int(nx) // self.world
+        self.x_off = self.rank * self.nxl
+        self.phys_shape = (self.nxl, int(nz))                        # local rows
+        self.ifield = int(info.ibytes) // 16                         # elements of one exchange field
         self.red_doubles = int(info.red_doubles)
         self.nx, self.nz = int(nx), int(nz)
         self.fdm_z = bool(fdm_z)
@@ -181,7 +192,23 @@ class Context:
     def take_i(self):
         if self._ipool:
             return self._ipool.pop()
+        if self.world > 1:
+            return empty((self.ifield,), np.complex128)
         return empty(self.spec_shape if self.fdm_z else (self.nx, self.ipitch), np.complex128)
+
+    # ---- slab decomposition: the all-to-all between the two passes of a transform
+    def exchange(self, send, forward):
+        """send: field in [peer][block] layout -> the blocks received from the peers.  Inverse
+        blocks are (nx/G rows, nml columns), forward blocks (column tiles of a rank, nx/G rows)."""
+        from . import _dist
+        n = self.world * self.nxl * self.ipitch if not forward else self._fwd_len()
+        recv = self.take_i()
+        _dist.all_to_all(recv[:n], send[:n])
+        return recv
+
+    def _fwd_len(self):
+        tiles = self.ifield // (self.world * self.nxl)               # tpr * ct
+        return self.world * tiles * self.nxl
 
     def give_i(self, t):
         if t is not None and len(self._ipool) < 8:
@@ -189,7 +216,8 @@ class Context:
 
     def scratch_i(self):
         if self._scratch_i is None:
-            self._scratch_i = empty((self.nx, max(self.ipitch, 1)), np.complex128)
+            self._scratch_i = (empty((self.ifield,), np.complex128) if self.world > 1
+                               else empty((self.nx, max(self.ipitch, 1)), np.complex128))
         return self._scratch_i
 
     def __del__(self):
@@ -211,11 +239,20 @@ def context_for(params):
         raise NotImplementedError("Finite difference not implemented in x direction")
     if getattr(params, "precision", "double") not in ("double", "single"):
         raise NotImplementedError("precision must be 'double' or 'single' (promoted to double)")
+    from . import _dist
+    shard = None
+    if _dist.world() > 1:
+        if fdm_z:
+            raise NotImplementedError(
+                "Fourier-x / FDM-z runs are not slab-decomposed (replicas only): set MLV_SHARD=0")
+        if int(params.nx) % (2 * _dist.world()):
+            raise NotImplementedError("slab decomposition needs nx divisible by twice the rank count")
+        shard = (_dist.rank(), _dist.world())
     key = (int(params.nx), int(params.nz), float(params.lx), float(params.lz), fdm_z,
-           int(params.spatial_derivative_order), str(device()))
+           int(params.spatial_derivative_order), str(device()), shard)
     ctx = _contexts.get(key)
     if ctx is None:
         ctx = Context(params.nx, params.nz, params.lx, params.lz, fdm_z,
-                      params.spatial_derivative_order)
+                      params.spatial_derivative_order, shard)
         _contexts[key] = ctx
     return ctx

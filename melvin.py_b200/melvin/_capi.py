@@ -21,7 +21,7 @@ RED_SUM, RED_MAX, RED_MIN, RED_SUMSQ, RED_SUMPROD = range(5)
 
 EXPORTS = [
     "mlv_create", "mlv_destroy", "mlv_set_stream", "mlv_get_info", "mlv_long_lines", "mlv_set_sharding", "mlv_set_forward_blocks", "mlv_p2p_alloc", "mlv_p2p_copy", "mlv_p2p_open",
-    "mlv_p2p_close", "mlv_set_peer_buffers", "mlv_last_error",
+    "mlv_p2p_close", "mlv_set_peer_buffers", "mlv_set_peer_flags", "mlv_last_error",
     "mlv_abi_version", "mlv_launch_count", "mlv_to_physical", "mlv_to_spectral", "mlv_x_inverse",
     "mlv_z_inverse", "mlv_z_forward", "mlv_x_forward", "mlv_advect_z", "mlv_advect_z_rows", "mlv_set_reduction_partials", "mlv_reduce_partials", "mlv_advect_phys",
     "mlv_spec_lincomb", "mlv_lap_array", "mlv_stencil", "mlv_solve_fdm", "mlv_fdm_velocity",
@@ -110,6 +110,7 @@ def declare(lib):
         "mlv_p2p_close": [vp, vp, i32],
         "mlv_p2p_copy": [vp, vp, vp, C.c_int64, vp],
         "mlv_set_peer_buffers": [vp, i32, C.POINTER(vp)],
+        "mlv_set_peer_flags": [vp, C.POINTER(vp)],
         "mlv_abi_version": [],
         "mlv_to_physical": [vp, vp, vp, vp],
         "mlv_to_spectral": [vp, vp, vp, vp],

@@ -19,6 +19,7 @@ Three array-like types live here:
 ``LazyLap``      ``coef * lap`` (``Variable.lap()``) kept symbolic for the same
                  reason; materialises to a real DeviceArray on any other use.
 """
+import builtins as _bi
 import ctypes
 import numbers
 
@@ -50,18 +51,82 @@ def _is_complex_scalar(x):
     return isinstance(x, (complex, np.complexfloating))
 
 
+# ================================================================== slabs
+class Dist:
+    """One axis of an array is distributed over the ranks (melvin/_dist.py): the array
+    stands for the GLOBAL index range [start, start + count) of that axis -- spectral columns m
+    ("cols") or physical rows x ("rows") -- and the local tensor holds the part of it this rank
+    owns.  Indexing uses global indices; host reads gather."""
+
+    def __init__(self, ctx, kind, axis, start, count, squeeze=False):
+        self.ctx, self.kind, self.axis, self.start, self.count, self.squeeze = ctx, kind, axis, start, count, squeeze
+
+    def owned(self):
+        c = self.ctx
+        return (c.m_off, c.nm_local) if self.kind == "cols" else (c.x_off, c.nxl)
+
+    def local_range(self):
+        own0, ownn = self.owned()
+        lo = _bi.max(self.start, own0)
+        return lo, _bi.max(lo, _bi.min(self.start + self.count, own0 + ownn))
+
+    def global_size(self):
+        return self.ctx.nm if self.kind == "cols" else self.ctx.nx
+
+    def root(self, axis):
+        return Dist(self.ctx, self.kind, axis, 0, self.global_size())
+
+
+def _expand_index(idx, ndim):
+    idx = idx if isinstance(idx, tuple) else (idx,)
+    if any(i is Ellipsis for i in idx):
+        k = idx.index(Ellipsis)
+        idx = idx[:k] + (slice(None),) * (ndim - (len(idx) - 1)) + idx[k + 1:]
+    return tuple(idx) + (slice(None),) * (ndim - len(idx))
+
+
+def _dist_index(d, idx, ndim):
+    """Global index of an array distributed by `d` -> (local index, Dist of the result or None,
+    (lo, hi) position of the local part inside the indexed global range)."""
+    idx = _expand_index(idx, ndim)
+    if len(idx) != ndim or any(not isinstance(i, (int, np.integer, slice)) for i in idx):
+        raise NotImplementedError("slab-decomposed arrays support basic (int / slice) indexing only")
+    comp = idx[d.axis]
+    L0, L1 = d.local_range()
+    squeeze = False
+    if isinstance(comp, (int, np.integer)):
+        g = int(comp) + (d.count if comp < 0 else 0)
+        if not 0 <= g < d.count:
+            raise IndexError("index out of range")
+        a, b, squeeze = g, g + 1, True
+    else:
+        a, b, step = comp.indices(d.count)
+        if step != 1:
+            raise NotImplementedError("slab-decomposed axis: unit-stride slices only")
+        b = _bi.max(a, b)
+    lo, hi = _bi.max(d.start + a, L0), _bi.min(d.start + b, L1)
+    hi = _bi.max(lo, hi)
+    local = list(idx)
+    local[d.axis] = slice(lo - L0, hi - L0)
+    new_axis = d.axis - _bi.sum(1 for i in idx[:d.axis] if isinstance(i, (int, np.integer)))
+    nd = Dist(d.ctx, d.kind, new_axis, d.start + a, b - a, squeeze or d.squeeze)
+    return tuple(local), nd, (lo - (d.start + a), hi - (d.start + a))
+
+
 # ============================================================= DeviceArray
 class DeviceArray:
     __array_priority__ = 1000
     __array_ufunc__ = None          # make NumPy scalars defer to our reflected operators
 
-    def __init__(self, tensor, base=None, idx=None):
+    def __init__(self, tensor, base=None, idx=None, dist=None, gidx=None):
         self._t = tensor
         # a view keeps its parent: reads and in-place writes through the view go through the
         # parent's hooks (deferred definitions, dependants), and the view follows the parent
         # when a Variable re-points its state buffer (double buffering)
         self._base = base
         self._idx = idx
+        self._dist = dist            # slab decomposition of one axis (Dist) or None
+        self._gidx = gidx            # view of a slab-decomposed array: its global index
 
     # -- hooks for lazily materialised subclasses
     def _touch(self):
@@ -103,7 +168,23 @@ class DeviceArray:
     # -- host interop
     def get(self):
         self._touch()
+        if self._dist is not None:
+            return self._gather()
         return _backend.to_host(self._t)
+
+    def _gather(self):
+        """Host copy of the GLOBAL array (collective: every rank calls it)."""
+        from . import _dist
+        if self._base is not None and self._gidx is not None:
+            full = self._base.get()
+            return full[self._gidx]
+        d = self._dist
+        full = _dist.gather(self._t, d.axis)
+        if d.kind == "cols":                       # drop the padding columns of the last slab
+            full = np.take(full, range(d.ctx.nm), axis=d.axis)
+        if not (d.start == 0 and d.count == d.global_size()):
+            full = np.take(full, range(d.start, d.start + d.count), axis=d.axis)
+        return full
 
     def __array__(self, dtype=None, copy=None):
         a = self.get()
@@ -122,22 +203,35 @@ class DeviceArray:
         return f"DeviceArray({self.get()!r})"
 
     def copy(self):
-        out = DeviceArray(_backend.empty(self.shape, self.dtype))
-        out[...] = self
+        out = DeviceArray(_backend.empty(self.shape, self.dtype), dist=self._dist)
+        DeviceArray(out._t)[...] = DeviceArray(self._touch()._t)
         return out
 
     # -- views
     def __getitem__(self, idx):
         self._touch()
+        if self._dist is not None:
+            local, nd, _ = _dist_index(self._dist, idx, self._t.dim())
+            return DeviceArray(self._t[local], self, local, dist=nd, gidx=idx)
         tracked = self._base is not None or type(self) is not DeviceArray
         return DeviceArray(self._t[idx], self if tracked else None, idx if tracked else None)
 
     def __setitem__(self, idx, value):
         self._touch()
         self._pre_write()
-        target = self._t[idx]
         if isinstance(value, (SpecExpr, LazyLap)):
             value = value.materialize()
+        if self._dist is not None:
+            local, nd, (lo, hi) = _dist_index(self._dist, idx, self._t.dim())
+            target = self._t[local]
+            if isinstance(value, np.ndarray) and value.ndim == target.dim():
+                # a global-shaped host block: keep the part this rank owns
+                value = np.take(value, range(lo, hi), axis=nd.axis) if value.shape[nd.axis] != 1 else value
+            if isinstance(value, DeviceArray) and value._dist is None and value._t.dim() == target.dim() \
+                    and value.shape[nd.axis] not in (1, target.shape[nd.axis]):
+                value = DeviceArray(value._touch()._t.narrow(nd.axis, lo, hi - lo))
+        else:
+            target = self._t[idx]
         if isinstance(value, np.ndarray):
             value = DeviceArray(_backend.from_host(value))
         _elementwise(_capi.EW_COPY, value, None, out=target)
@@ -156,7 +250,10 @@ class DeviceArray:
         if not (isinstance(other, DeviceArray) or _is_scalar(other)):
             return NotImplemented
         a, b = (other, self) if reflected else (self, other)
-        return DeviceArray(_elementwise(op, a, b))
+        dist = self._dist if self._dist is not None else getattr(other, "_dist", None)
+        if dist is not None and (self._base is not None or dist.squeeze):
+            dist = None if dist.squeeze else Dist(dist.ctx, dist.kind, dist.axis, dist.start, dist.count)
+        return DeviceArray(_elementwise(op, a, b), dist=dist)
 
     def __add__(self, o): return self._bin(_capi.EW_ADD, o)
     def __radd__(self, o): return self._bin(_capi.EW_ADD, o, True)
@@ -290,7 +387,12 @@ def _reduce(op, a, b=None):
     out = _backend.empty((1,), np.float64)
     _ctx().call("mlv_reduce", op, rows, cols, ctypes.byref(va),
                 ctypes.byref(vb) if vb is not None else None, ctypes.c_void_p(out.data_ptr()))
-    return float(_backend.to_host(out)[0])
+    val = float(_backend.to_host(out)[0])
+    if a._dist is not None:                        # slabs: combine over the ranks
+        from . import _dist
+        kind = {_capi.RED_MAX: "max", _capi.RED_MIN: "min"}.get(op, "sum")
+        val = float(_dist.all_reduce_host([val], kind)[0])
+    return val
 
 
 # ------------------------------------------------------ namespace functions
@@ -321,11 +423,15 @@ def ones(shape, dtype=np.float64):
 
 
 def zeros_like(a, dtype=None):
-    return zeros(a.shape, dtype or a.dtype)
+    out = zeros(a.shape, dtype or a.dtype)
+    out._dist = getattr(a, "_dist", None)
+    return out
 
 
 def empty_like(a, dtype=None):
-    return empty(a.shape, dtype or a.dtype)
+    out = empty(a.shape, dtype or a.dtype)
+    out._dist = getattr(a, "_dist", None)
+    return out
 
 
 def array(obj, dtype=None):
@@ -359,7 +465,10 @@ def sum(a):   # noqa: A001
 
 def mean(a):
     a = _as_dev(a)
-    return _reduce(_capi.RED_SUM, a) / a.size
+    size = a.size
+    if a._dist is not None:                        # global element count
+        size = int(np.prod([a._dist.count if i == a._dist.axis else n for i, n in enumerate(a.shape)]))
+    return _reduce(_capi.RED_SUM, a) / size
 
 
 def sum_of_squares(a):
@@ -370,20 +479,126 @@ def sum_of_product(a, b):
     return _reduce(_capi.RED_SUMPROD, _as_dev(a), _as_dev(b))
 
 
+class _OutputPipeline:
+    """Asynchronous frame output (Variable.save -> xp.save, reference melvin/Variable.py:130-133):
+    the array is snapshotted into a device staging buffer by the library's copy kernel on the
+    compute stream, travels to pinned host memory on a separate copy stream, and is written to
+    disk by a background thread -- the time step never waits for PCIe or the file system.
+    Files are complete after flush() (called at interpreter exit, by load() and by
+    synchronize()); MLV_SYNC_OUTPUT=1 restores the reference's blocking behaviour."""
+    SLOTS = 2
+
+    def __init__(self):
+        import queue
+        import threading
+        self._queue = queue.Queue()
+        self._free = []                      # (device staging, pinned host) pairs by byte size
+        self._busy = 0
+        self._cv = threading.Condition()
+        self._stream = None
+        self._thread = threading.Thread(target=self._writer, daemon=True)
+        self._thread.start()
+        self.frames_written = 0
+
+    def _writer(self):
+        while True:
+            item = self._queue.get()
+            if item is None:
+                return
+            fname, host, shape, dtype, event, slot = item
+            try:
+                event.synchronize()
+                np.save(fname, host.numpy().view(dtype).reshape(shape))
+                self.frames_written += 1
+            finally:
+                with self._cv:
+                    self._free.append(slot)
+                    self._busy -= 1
+                    self._cv.notify_all()
+
+    def submit(self, fname, a):
+        import torch
+        t = a._touch()._t
+        nbytes = t.numel() * t.element_size()
+        with self._cv:
+            while self._busy >= self.SLOTS:              # both staging pairs in flight: wait for one
+                self._cv.wait()
+            slot = next((s for s in self._free if s[0].numel() == nbytes), None)
+            if slot is not None:
+                self._free.remove(slot)
+            self._busy += 1
+        if slot is None:
+            slot = (torch.empty(nbytes, dtype=torch.uint8, device=t.device),
+                    torch.empty(nbytes, dtype=torch.uint8, pin_memory=True))
+        stage, host = slot
+        dtype = torch.complex128 if t.is_complex() else torch.float64
+        snap = stage.view(dtype).reshape(tuple(t.shape))
+        _elementwise(_capi.EW_COPY, a, None, out=snap)          # snapshot on the compute stream
+        if self._stream is None:
+            self._stream = torch.cuda.Stream()
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream())
+        done = torch.cuda.Event()
+        with torch.cuda.stream(self._stream):
+            self._stream.wait_event(ready)
+            host.copy_(stage, non_blocking=True)
+            done.record(self._stream)
+        self._queue.put((fname, host, tuple(t.shape), np.complex128 if t.is_complex() else np.float64,
+                         done, slot))
+
+    def flush(self):
+        with self._cv:
+            while self._busy:
+                self._cv.wait()
+
+
+_output = None
+
+
+def flush_output():
+    """Block until every frame handed to save() is on disk."""
+    if _output is not None:
+        _output.flush()
+
+
 def save(fname, a):
+    """numpy.save of a device array (reference: xp.save in Variable.save).  Device arrays on a
+    GPU go through the asynchronous output pipeline."""
+    import os
+    global _output
+    fname = fname if str(fname).endswith(".npy") else str(fname) + ".npy"
+    if isinstance(a, DeviceArray) and a._dist is not None:
+        from . import _dist
+        full = a.get()                               # collective gather; one writer
+        if _dist.rank() == 0:
+            np.save(fname, full)
+        return
+    if (isinstance(a, DeviceArray) and _backend.is_cuda() and not os.environ.get("MLV_SYNC_OUTPUT")
+            and a._touch()._t.is_contiguous()):
+        if _output is None:
+            import atexit
+            _output = _OutputPipeline()
+            atexit.register(flush_output)
+        _output.submit(fname, a)
+        return
     np.save(fname, asnumpy(a))
 
 
 def savez(fname, **arrays):
-    np.savez(fname, **{k: asnumpy(v) for k, v in arrays.items()})
+    from . import _dist
+    host = {k: asnumpy(v) for k, v in arrays.items()}
+    if _dist.rank() == 0:
+        np.savez(fname, **host)
 
 
 def load(fname, **kw):
+    flush_output()
     return np.load(fname, **kw)
 
 
 def synchronize():
     _backend.synchronize()
+    flush_output()
 
 
 class _FFT:
@@ -542,6 +757,8 @@ class SpecExpr:
         ctx = self.ctx
         if out is None:
             out = DeviceArray(_backend.empty(ctx.spec_shape, np.complex128))
+            if ctx.world > 1:
+                out._dist = Dist(ctx, "cols", 1, 0, ctx.nm)
         out_t = out._t
         terms = list(self.terms)
         first = True
@@ -623,6 +840,8 @@ class LazyLap:
             out = _backend.empty(self.ctx.spec_shape, np.float64)
             self.ctx.call("mlv_lap_array", ctypes.c_double(self.coef), ctypes.c_void_p(out.data_ptr()))
             self._mat = DeviceArray(out)
+            if self.ctx.world > 1:
+                self._mat._dist = Dist(self.ctx, "cols", 1, 0, self.ctx.nm)
         return self._mat
 
     def __add__(self, o): return self.materialize() + o

@@ -22,7 +22,7 @@ import weakref
 import numpy as np
 
 from . import _backend, _capi
-from .b200 import DeviceArray, LazyLap, NLTerm, SpecExpr, _frozen
+from .b200 import DeviceArray, Dist, LazyLap, NLTerm, SpecExpr, _frozen
 from .basis import BasisFunctions
 
 _I_NONE, _I_PENDING, _I_VALID = 0, 1, 2
@@ -94,9 +94,14 @@ class Variable:
         self._hat = None                     # FDM-z: private x spectrum (ux = -pddz(psi))
         # ONE handle per Variable for its whole life (gets() / _sdata always return it, as the
         # reference returns the same ndarray); double buffering re-points its tensor
-        self._s = _SpecHandle(_backend.zeros(params.spectral_shape, np.complex128), self)
+        # (under a process group: this rank's kz-slab / x-slab, melvin/_dist.py)
+        ctx = self._ctx
+        self._s = _SpecHandle(_backend.zeros(ctx.spec_shape, np.complex128), self)
         self._s_spare = None                 # second state tensor (double buffering)
-        self._p = _PhysHandle(_backend.zeros(params.physical_shape, np.float64), self)
+        self._p = _PhysHandle(_backend.zeros(ctx.phys_shape, np.float64), self)
+        if ctx.world > 1:
+            self._s._dist = Dist(ctx, "cols", 1, 0, ctx.nm)
+            self._p._dist = Dist(ctx, "rows", 0, 0, ctx.nx)
         self._virt = None                    # (op, frozen DeviceArray): deferred spectral definition
         self._i = None                       # torch tensor (nx, ipitch) complex128
         self._i_state = _I_NONE
@@ -187,7 +192,10 @@ class Variable:
             return
         self._flush_dependants(self._s._t)
         self._virt = None
-        self._s[:, :] = data[:, :]
+        if self._ctx.world > 1 and getattr(data, "_dist", None) is not None:
+            DeviceArray(self._s._t)[:, :] = DeviceArray(data._touch()._t)[:, :]     # slab to slab
+        else:
+            self._s[:, :] = data[:, :]              # (slabs: a full array, cut by the handle)
 
     def gets(self):
         return self._sdata
@@ -195,10 +203,13 @@ class Variable:
     # ---------------------------------------------------- physical storage
     def setp(self, data):
         """Setter for physical data"""
+        ctx = self._ctx
+        if ctx.world > 1 and tuple(data.shape) == (ctx.nx, ctx.nz) and getattr(data, "_dist", None) is None:
+            data = data[ctx.x_off:ctx.x_off + ctx.nxl]          # a full field: keep this rank's rows
         if isinstance(data, np.ndarray):
             data = DeviceArray(_backend.from_host(data))
         self._p_written()
-        DeviceArray(self._p._t)[:, :] = data[:, :]
+        DeviceArray(self._p._t)[:, :] = DeviceArray(data._touch()._t)[:, :]
 
     def getp(self):
         return self._p
@@ -366,6 +377,11 @@ class Variable:
                  ctypes.c_void_p(self._i.data_ptr()), ctypes.c_void_p(ia.data_ptr()),
                  ctypes.c_void_p(ib.data_ptr()), None)
         ctx.call("mlv_set_reduction_partials", None, count=False)
+        if ctx.world > 1:                           # tile block h of both products to rank h
+            sa, sb = ia, ib
+            ia, ib = ctx.exchange(sa, True), ctx.exchange(sb, True)
+            ctx.give_i(sa)
+            ctx.give_i(sb)
         shared = {"part": uxo._red_part, "host": None}
         uxo._red = (shared, 0, 2)
         uzo._red = (shared, 1, 3)
@@ -389,6 +405,10 @@ class Variable:
         return SpecExpr(ctx, [], [(1.0, NLTerm(ctx, ia, ib))])
 
     def _vec_dot_nabla_eager(self, ux, uz, out, convert_to_physical):
+        if self._ctx.world > 1:
+            raise NotImplementedError("slab-decomposed runs advect with the velocities of "
+                                      "calc_velocity_from_vorticity (the fused path); a physical-space "
+                                      "x stencil on raw arrays would need a halo exchange")
         if convert_to_physical:
             self.to_physical()
         if isinstance(ux, np.ndarray):
@@ -419,6 +439,11 @@ class Variable:
             self._ctx.call("mlv_reduce_partials", ctypes.c_void_p(shared["part"].data_ptr()),
                            ctypes.c_void_p(red4.data_ptr()))
             shared["host"] = _backend.to_host(red4)
+            if self._ctx.world > 1:                 # slabs: global maxima and sums
+                from . import _dist
+                h = shared["host"]
+                shared["host"] = np.concatenate((_dist.all_reduce_host(h[:2], "max"),
+                                                 _dist.all_reduce_host(h[2:], "sum")))
         return float(shared["host"][self._red[which]])
 
     # ------------------------------------------------------------- I/O
@@ -442,15 +467,24 @@ def _run_x_inverse(ctx, variables):
         srcs = (ctypes.c_void_p * n)()
         ops = (ctypes.c_int32 * n)()
         dsts = (ctypes.c_void_p * n)()
+        sends = []
         for k, v in enumerate(chunk):
             op, src = v._i_def
-            if v._i is None:
-                v._i = _backend.empty((ctx.nx, ctx.ipitch), np.complex128)
+            if ctx.world > 1:                       # [peer][block] send buffer, exchanged below
+                sends.append(ctx.take_i())
+                dsts[k] = sends[-1].data_ptr()
+            else:
+                if v._i is None:
+                    v._i = _backend.empty((ctx.nx, ctx.ipitch), np.complex128)
+                dsts[k] = v._i.data_ptr()
             srcs[k] = src._t.data_ptr()
             ops[k] = op
-            dsts[k] = v._i.data_ptr()
         ctx.call("mlv_x_inverse", n, srcs, ops, dsts)
-        for v in chunk:
+        for k, v in enumerate(chunk):
+            if ctx.world > 1:                       # row block h of every field to rank h
+                ctx.give_i(v._i)
+                v._i = ctx.exchange(sends[k], False)
+                ctx.give_i(sends[k])
             v._i_state = _I_VALID
             v._i_def = None
 
@@ -481,8 +515,11 @@ class TimeDerivative:
         self._params = params
         self._xp = xp
         self._curr_idx = 0
+        ctx = _backend.context_for(params)
         self._store = DeviceArray(_backend.zeros(
-            (params.integrator_order,) + tuple(params.spectral_shape), np.complex128))
+            (params.integrator_order,) + tuple(ctx.spec_shape), np.complex128))
+        if ctx.world > 1:
+            self._store._dist = Dist(ctx, "cols", 2, 0, ctx.nm)
         self._dump_name = dump_name
         self._pending = None
 
@@ -494,7 +531,11 @@ class TimeDerivative:
 
     def _level(self, back):
         """History level curr_idx+back with Python negative wrap (:38-39)."""
-        return self._store[self._curr_idx + back]
+        k = (self._curr_idx + back) % self._params.integrator_order
+        lv = DeviceArray(self._store._t[k])
+        if self._store._dist is not None:
+            lv._dist = Dist(self._store._dist.ctx, "cols", 1, 0, self._store._dist.count)
+        return lv
 
     @property
     def _data(self):
@@ -544,7 +585,7 @@ class TimeDerivative:
             level = data[i]
             if tuple(level.shape) != (2 * nn + 1, nm):
                 level = scale_variable(level, (nn, nm), np if isinstance(level, np.ndarray) else self._xp)
-            self._store[i][...] = level
+            self._level(i - self._curr_idx)[...] = level
 
     def get_name(self):
         return self._dump_name

@@ -10,7 +10,7 @@ import ctypes
 import numpy as np
 
 from . import _backend, _capi
-from .b200 import DeviceArray, LazyLap, SpecExpr
+from .b200 import DeviceArray, Dist, LazyLap, SpecExpr
 from .basis import BasisFunctions
 
 _CE = BasisFunctions.COMPLEX_EXP
@@ -68,12 +68,25 @@ class ArrayFactory:
             n, m = np.arange(0, p.nn), np.arange(0, p.nz)
         return np.meshgrid(n, m, indexing="ij")
 
+    def _ctx(self):
+        return _backend.context_for(self._p)
+
     def make_spectral(self, ni=None, nj=None):
+        if ni is None and nj is None and self._p.is_fully_spectral() and self._ctx().world > 1:
+            ctx = self._ctx()                         # this rank's kz-slab
+            out = self._xp.zeros(ctx.spec_shape, dtype=self._p.complex)
+            out._dist = Dist(ctx, "cols", 1, 0, ctx.nm)
+            return out
         ni = self._p.spectral_shape[0] if ni is None else ni
         nj = self._p.spectral_shape[1] if nj is None else nj
         return self._xp.zeros((ni, nj), dtype=self._p.complex)
 
     def make_physical(self, nx=None, nz=None):
+        if nx is None and nz is None and self._p.is_fully_spectral() and self._ctx().world > 1:
+            ctx = self._ctx()                         # this rank's x-slab
+            out = self._xp.zeros(ctx.phys_shape, dtype=self._p.float)
+            out._dist = Dist(ctx, "rows", 0, 0, ctx.nx)
+            return out
         nx = self._p.nx if nx is None else nx
         nz = self._p.nz if nz is None else nz
         return self._xp.zeros((nx, nz), dtype=self._p.float)
@@ -116,25 +129,68 @@ class SpectralTransformer:
         self._only_fourier(basis_functions)
         if out is None:
             out = self._array_factory.make_physical()
+        ctx = self._ctx
+        if ctx.world > 1:
+            in_arr = self._local(in_arr, ctx, spectral=True)
         src = _contig(_dev(in_arr, np.complex128))
         dst = out._t if isinstance(out, DeviceArray) else None
         if dst is None or not dst.is_contiguous():
             raise TypeError("out must be a contiguous device array")
         out._pre_write()
-        self._ctx.call("mlv_to_physical", _ptr(src), _ptr(self._ctx.scratch_i()), _ptr(dst))
+        if ctx.world > 1:
+            # x pass on the local columns -> row block h to rank h -> z pass on the local rows
+            send = ctx.take_i()
+            ctx.call("mlv_x_inverse", 1, (ctypes.c_void_p * 1)(src.data_ptr()),
+                     (ctypes.c_int32 * 1)(_capi.OP_IDENT), (ctypes.c_void_p * 1)(send.data_ptr()))
+            recv = ctx.exchange(send, False)
+            ctx.call("mlv_z_inverse", _ptr(recv), _ptr(dst))
+            ctx.give_i(send)
+            ctx.give_i(recv)
+            return out
+        ctx.call("mlv_to_physical", _ptr(src), _ptr(ctx.scratch_i()), _ptr(dst))
         return out
+
+    @staticmethod
+    def _local(arr, ctx, spectral):
+        """Slab-decomposed runs: a full (global-shaped) host or device array is cut to this
+        rank's slab; arrays that are slabs already pass through."""
+        if getattr(arr, "_dist", None) is not None or isinstance(arr, (SpecExpr, LazyLap)):
+            return arr
+        if spectral and tuple(arr.shape) == tuple(ctx.global_spec_shape):
+            out = DeviceArray(_backend.zeros(ctx.spec_shape, np.complex128))
+            out._dist = Dist(ctx, "cols", 1, 0, ctx.nm)
+            out[:, :] = arr
+            return out
+        if not spectral and tuple(arr.shape) == (ctx.nx, ctx.nz):
+            return arr[ctx.x_off:ctx.x_off + ctx.nxl]
+        return arr
 
     def __to_spectral_2d(self, in_arr, out=None, basis_functions=_DEFAULT):
         """SpectralTransformer.py:152-199"""
         self._only_fourier(basis_functions)
         if out is None:
             out = self._array_factory.make_spectral()
+        ctx = self._ctx
+        if ctx.world > 1:
+            in_arr = self._local(in_arr, ctx, spectral=False)
         src = _contig(_dev(in_arr, np.float64))
         if src.is_complex():
             raise TypeError("to_spectral expects a real physical array")
         out._touch()
         out._pre_write()
-        self._ctx.call("mlv_to_spectral", _ptr(src), _ptr(self._ctx.scratch_i()), _ptr(out._t))
+        if ctx.world > 1:
+            # z pass on the local rows -> tile block h to rank h -> x pass on the local columns
+            send = ctx.take_i()
+            ctx.call("mlv_z_forward", _ptr(src), _ptr(send))
+            recv = ctx.exchange(send, True)
+            d = _capi.XFwd()
+            d.nf, d.mode = 1, 0
+            d.src[0], d.sym[0], d.coef[0], d.dst = recv.data_ptr(), _capi.SYM_ONE, 1.0, out._t.data_ptr()
+            ctx.call("mlv_x_forward", ctypes.byref(d))
+            ctx.give_i(send)
+            ctx.give_i(recv)
+            return out
+        ctx.call("mlv_to_spectral", _ptr(src), _ptr(ctx.scratch_i()), _ptr(out._t))
         return out
 
     def __to_physical_1d(self, in_arr, out=None, basis_functions=_DEFAULT):

@@ -88,6 +88,7 @@ class ShardedScalarStepper:
             mode = "a2a"                               # (world 1: no exchange at all)
         self.mode = mode
         self.p2p = mode == "p2p"
+        self._flags = False
         self._ipc = []
         if mode == "p2p":
             # receive buffers live in peer-mapped memory; the producer kernels of every rank
@@ -96,6 +97,17 @@ class ShardedScalarStepper:
             self.fwd_recv_ptr = self._setup_peers(1, self.N_FWD * self.fwd_stride * 16)[self.rank]
             self.inv_send_ptr, self.fwd_send_ptr = self.inv_recv_ptr, self.fwd_recv_ptr
             self._sync = _backend.zeros((1,), np.float64)
+            # producers and consumers of the exchange are ordered across ranks ON THE DEVICE:
+            # every producer CTA bumps an arrival counter in each rank's memory, consumer CTAs
+            # spin on their own (mlv_set_peer_flags).  MLV_P2P_BARRIER=nccl: the older form, a
+            # one-element all-reduce between the kernels
+            self._flags = os.environ.get("MLV_P2P_BARRIER", "flags") != "nccl"
+            if self._flags:
+                ptrs = self._setup_peers(None, 64, register=False)
+                arr = (ctypes.c_void_p * self.world)(*ptrs)
+                _capi.check(self.ctx.lib, self.ctx.lib.mlv_set_peer_flags(self.ctx.handle, arr))
+                _backend.synchronize()
+                dist.barrier(group=self.group)
         elif mode == "dma":
             # peer-mapped receive buffers filled by copy engines from local send buffers
             self.inv_peers = self._setup_peers(0, self.N_INV * self.inv_stride * 16, register=False)
@@ -280,7 +292,7 @@ class ShardedScalarStepper:
             ctx.call("mlv_x_inverse", n, (vp * n)(*[g[0].data_ptr() for g in grp]),
                      (ctypes.c_int32 * n)(*[g[1] for g in grp]),
                      (vp * n)(*[self._slot(0, False, g[2]) for g in grp]))
-        if self.world > 1:
+        if self.world > 1 and not self._flags:
             dist.all_reduce(self._sync, group=self.group)
 
     def _advect_round(self, jobs):
@@ -306,7 +318,7 @@ class ShardedScalarStepper:
                 works += [self._a2a(self.fwd_recv, self.fwd_send, f) for f in (fa, fb)]
         if self.mode == "dma":
             self._dma_join(self._ev[4])
-        elif not chunked and self.world > 1:
+        elif not chunked and self.world > 1 and not self._flags:
             dist.all_reduce(self._sync, group=self.group)
         for wk in works:
             wk.wait()
@@ -387,12 +399,13 @@ class ShardedScalarStepper:
             # 1. inverse x pass on the local columns: q = w, ux, uz (psi shared inside the
             #    kernel); with peer memory every block lands in its consumer's buffer
             ctx.call("mlv_x_inverse", 3, self._srcs[self.cur], self._ops, self._dsts)
-            # 2. order producers and consumers across ranks (stream-ordered, no host sync)
-            if self.world > 1:
+            # 2. producers and consumers are ordered across ranks by arrival counters in peer
+            #    memory (no collective, no host synchronisation)
+            if self.world > 1 and not self._flags:
                 dist.all_reduce(self._sync, group=self.group)
             # 3. physical-space stage on the local rows
             ctx.call("mlv_advect_z", *self._zargs, redp)
-            if self.world > 1:
+            if self.world > 1 and not self._flags:
                 dist.all_reduce(self._sync, group=self.group)
         else:
             # 1.+2. one launch and one all-to-all per field: the transpose of field f (row block

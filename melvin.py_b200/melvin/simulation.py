@@ -80,6 +80,9 @@ class ScalarTracker:
         self._values += [val]
 
     def save(self, _index):
+        from . import _dist
+        if _dist.rank() != 0:
+            return
         np.savez(self._filename, t=np.array(self._times, dtype=np.float64),
                  values=np.array([float(v) for v in self._values]))
 
@@ -197,6 +200,9 @@ class Simulation:
         data = {v.get_name(): self._data_trans.to_host(v[:]) for v in self._dump_vars}
         data.update({d.get_name(): self._data_trans.to_host(d.get_all()) for d in self._dump_dvars})
         tickers = {t.get_name(): t.dump() for t in self._tickers}
+        from . import _dist
+        if _dist.rank() != 0:                   # slabs were gathered above by every rank; one writer
+            return
         np.savez(fname, **data, **tickers, curr_idx=self._dump_dvars[0].get_curr_idx(),
                  dt=self._integrator._dt, t=self._t, loop_counter=self._loop_counter,
                  params=self._params._original_params)

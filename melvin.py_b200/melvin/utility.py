@@ -25,7 +25,7 @@ def load_scipy_sparse_linalg(xp):
 def init_var_with_noise(var, epsilon, seed=0):
     """Uniform noise in physical space (melvin/utility.py:31-39)."""
     rng = default_rng(seed)
-    shape = var.getp().shape
+    shape = tuple(var._params.physical_shape)      # the global field (slab runs keep their rows in load)
     data_p = np.zeros(shape)
     data_p += epsilon * (2 * rng.random(shape) - 1.0)
     var.load(data_p, is_physical=True)

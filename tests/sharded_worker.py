@@ -73,6 +73,45 @@ elif case in ("kh", "khlong"):
     if rank == 0:
         print(f"SHARDED world={world} field_err={err:.2e} ke_err={ke_err:.2e} {'OK' if ok else 'FAIL'}",
               flush=True)
+elif case.startswith("api_"):
+    # N4: the UNCHANGED public-API loops of tests/parity_cases.py under the process group --
+    # Simulation / Variable shard themselves (melvin/_dist.py) -- vs the reference goldens
+    import parity_cases as pc
+    G = lambda name: np.load(os.path.join(ROOT, "tests", "golden", name))   # noqa: E731
+    errs = {}
+    if case == "api_tg":
+        gl = G("loop_tg_64x64.npz")
+        g = mo.Grid(64, 64, float(gl["lx"]), float(gl["lz"]))
+        with pc.scratch_cwd():
+            out = pc.run_single_scalar(64, 64, g.lx, g.lz, float(gl["coef"]), float(gl["dt"]), 20,
+                                       mo.ic_taylor_green(g), snaps=(1, 2, 10, 20), strict_reads=True)
+        errs["field"] = max(rel(out[f"w_step{k}"], gl[f"w_step{k}"]) for k in (1, 2, 10, 20))
+        errs["ke"] = float(np.max(np.abs(out["ke"] / gl["ke"] - 1)))
+        vel = mo.velocity_from_vorticity(g, mo.to_spectral(g, mo.ic_taylor_green(g)))
+        errs["psi_read_after_update"] = rel(out["psi_after_step1"], vel["psi_s"])
+        errs["ux_read_after_update"] = rel(out["ux_p_after_step1"], vel["ux_p"])
+        ok = errs["field"] < 1e-12 and errs["ke"] < 1e-9 and errs["psi_read_after_update"] < 1e-12 \
+            and errs["ux_read_after_update"] < 1e-12
+    elif case == "api_ddc":
+        gl = G("loop_ddc_64x64.npz")
+        with pc.scratch_cwd():
+            out = pc.run_ddc(64, 64, float(gl["lx"]), float(gl["lz"]), float(gl["dt"]), 10,
+                             float(gl["Pr"]), float(gl["R0"]), float(gl["tau"]), snaps=(1, 10))
+        errs["field"] = max(rel(out[f"{nm}_step{k}"], gl[f"{nm}_step{k}"]) for k in (1, 10) for nm in ("w", "tmp", "xi"))
+        errs["ke"] = float(np.max(np.abs(out["ke"] / gl["ke"][:10] - 1)))
+        errs["nu"] = float(np.max(np.abs((out["nu"] - 1) - (gl["nu"][:10] - 1)) / np.maximum(np.abs(gl["nu"][:10] - 1), 1e-17)))
+        ok = errs["field"] < 1e-12 and errs["ke"] < 1e-9 and errs["nu"] < 1e-6
+    else:
+        gl = G("loop_tearing_64x64.npz")
+        with pc.scratch_cwd():
+            out = pc.run_tearing(64, 64, float(gl["lx"]), float(gl["lz"]), float(gl["dt"]), 10,
+                                 float(gl["Re"]), float(gl["S"]), gl["j0_phys"], snaps=(1, 10))
+        errs["j"] = max(rel(out[f"j_step{k}"], gl[f"j_step{k}"]) for k in (1, 10))
+        errs["w"] = max(rel(out[f"w_step{k}"], gl[f"w_step{k}"]) for k in (1, 10))
+        ok = errs["j"] < 1e-12 and errs["w"] < 1e-9
+    if rank == 0:
+        print(f"SHARDED world={world} " + " ".join(f"{k}={v:.2e}" for k, v in errs.items())
+              + (" OK" if ok else " FAIL"), flush=True)
 elif case == "bench":
     # bench.py's multi-GPU host logic: the parity preflight and the three workload builders
     import bench

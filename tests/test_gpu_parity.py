@@ -423,3 +423,28 @@ def test_held_handle_stays_current():
     same, rows_ok, col0 = ac.held_handle_stays_current()
     assert all(same) and all(rows_ok)
     assert np.all(col0 == 0.0)
+
+
+def test_async_frame_output_is_a_snapshot():
+    """Variable.save hands the frame to the asynchronous output pipeline (device
+    snapshot -> copy stream -> pinned host -> writer thread); the file holds the field as it was
+    at save() time even though stepping continues, and files are complete after flush."""
+    from melvin import b200 as xp
+    from melvin.utility import calc_velocity_from_vorticity
+    g = mo.Grid(256, 256, 2 * np.pi, 2 * np.pi)
+    with pc.scratch_cwd():
+        d = pc.base_params(256, 256, g.lx, g.lz, initial_dt=1e-3, nu=0.25)
+        p, sim, (w,), (dw,), psi, ux, uz = pc.make_sim(d, ["w"], ["dw"], [pc.CE, pc.CE])
+        w.load(mo.ic_taylor_green(g) + 0.3 * mo.ic_noise(g, 1.0, 1), is_physical=True)
+        frames = []
+        for k in range(6):
+            calc_velocity_from_vorticity(w, psi, ux, uz, sim.get_laplacian_solver())
+            dw[:] = -w.vec_dot_nabla(ux.getp(), uz.getp())
+            frames.append(w.getp().get().copy())          # what the reference would write now
+            w.save(k)                                      # returns immediately
+            sim._integrator.integrate(w, dw, p.nu * w.lap())
+            sim.end_loop()
+        xp.flush_output()
+        assert xp._output is not None and xp._output.frames_written == 6
+        for k in range(6):
+            assert np.array_equal(np.load(f"w{k:04d}.npy"), frames[k]), k

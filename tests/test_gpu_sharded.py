@@ -49,6 +49,22 @@ def test_multi_field_steppers_nccl(case, mode):
     assert out.returncode == 0 and lines and lines[-1].endswith("OK"), out.stdout[-2000:] + out.stderr[-2000:]
 
 
+@pytest.mark.parametrize("case", ["api_tg", "api_ddc", "api_tearing"])
+def test_public_api_shards_itself_nccl(case):
+    """N4: the unchanged public-API loops under torchrun on GPUs (slabs + NCCL all-to-all behind
+    Simulation / Variable), vs the goldens of the unmodified reference"""
+    n = _ngpu()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    world = 2 if n < 4 else 4
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", "29703",
+           os.path.join(ROOT, "tests", "sharded_worker.py"), "cuda", case]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("SHARDED")]
+    assert out.returncode == 0 and lines and lines[-1].endswith("OK"), out.stdout[-2000:] + out.stderr[-2000:]
+
+
 def test_single_rank_stepper_matches_python_api_path():
     """The rank-local stepper (world 1) against the golden: same kernels as the public API."""
     import numpy as np

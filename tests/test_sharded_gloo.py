@@ -57,3 +57,12 @@ def test_multi_field_steppers(case, world):
 def test_bench_multi_gpu_host_logic():
     """bench.py's sharded parity preflight and workload builders over gloo (world 2)"""
     run_world(2, "bench", 29631)
+
+
+@pytest.mark.parametrize("case,world", [("api_tg", 2), ("api_tg", 4), ("api_ddc", 2), ("api_tearing", 2),
+                                        ("api_tearing", 4)])
+def test_public_api_shards_itself(case, world):
+    """N4: the UNCHANGED loops of tests/parity_cases.py (Simulation / Variable / Integrator API)
+    under a process group: the package decomposes the fields into slabs itself (melvin/_dist.py),
+    results gathered on read; vs the goldens of the unmodified reference"""
+    run_world(world, case, 29640 + world)
