@@ -66,7 +66,7 @@ struct mlv_ctx {
     // counters [0] inverse blocks, [1] forward blocks; expect[] = arrivals due at this rank so far
     unsigned long long* peer_flags[MLV_MAXPEER] = {};
     bool flags_on = false;
-    unsigned long long expect[2] = {0, 0};
+    unsigned long long* expect = nullptr;       // device: arrivals due at this rank so far, [0] inverse, [1] forward
     mlv::stream_t stream = 0;
 };
 
@@ -520,6 +520,17 @@ static int launch_x1d_advect(mlv_ctx* c, X1dAdvArgs& a, unsigned& grid_out) {
     return 0;
 }
 
+// one-warp kernel behind a producer launch: arrival counter `which` of every rank += 1 (if this
+// rank produced anything), this rank's count of arrivals due += `due`
+static int signal_arrival(mlv_ctx* c, int which, bool produced, int due) {
+    PeerSignals s;
+    s.n = produced ? c->nranks : 0;
+    for (int r = 0; r < c->nranks; ++r) s.counter[r] = c->peer_flags[r] + which;
+    auto kfn = k_signal_peers;
+    MLV_LAUNCH(kfn, 1u, 32u, 0, c->stream, s, c->expect + which, (unsigned long long)due);
+    return 0;
+}
+
 static int reduce_final(mlv_ctx* c, const double* partial, int n, int stride, int off, int op,
                         double* out) {
     auto kfn = k_reduce_final;
@@ -642,6 +653,7 @@ int mlv_destroy(mlv_ctx* c) {
     if (c->tri_inv) rt_free(c->tri_inv);
     if (c->symx) rt_free(c->symx);
     if (c->red) rt_free(c->red);
+    if (c->expect) rt_free(c->expect);
     delete c;
     return MLV_OK;
 }
@@ -743,7 +755,11 @@ int mlv_set_peer_flags(mlv_ctx* c, void* const* counters) {
     c->flags_on = counters != nullptr;
     for (int h = 0; h < c->nranks && h < MLV_MAXPEER; ++h)
         c->peer_flags[h] = counters ? (unsigned long long*)counters[h] : nullptr;
-    c->expect[0] = c->expect[1] = 0;
+    if (c->flags_on && !c->expect) {
+        const unsigned long long zero[2] = {0, 0};
+        if (int rc = rt_malloc((void**)&c->expect, sizeof(zero))) return rc;
+        if (int rc = rt_h2d(c->expect, zero, sizeof(zero), c->stream)) return rc;
+    }
     return MLV_OK;
 }
 
@@ -775,18 +791,11 @@ int mlv_x_inverse(mlv_ctx* c, int nf, const void* const* spec, const int32_t* op
     XInvArgs a;
     a.nn = c->nn; a.nm = c->nm_loc; a.spitch = c->spec_cols; a.ipitch = c->nml; a.nf = nf;
     a.sh = c->sh;
-    a.sig.n = 0;
-    if (c->p2p_inv && c->flags_on) {
-        // every x-pass CTA of every rank will bump the inverse counter of every rank once
-        for (int r = 0; r < c->nranks; ++r) {
-            int left = c->nm - r * c->nml;
-            left = left < 0 ? 0 : (left > c->nml ? c->nml : left);
-            c->expect[0] += (unsigned long long)((left + c->ct - 1) / c->ct);
-            a.sig.counter[r] = c->peer_flags[r];
-        }
-        a.sig.n = c->nranks;
-    }
-    if (c->nm_loc <= 0) return MLV_OK;              // this rank owns no retained column
+    const bool signal = c->p2p_inv && c->flags_on;
+    int owners = 0;                                 // ranks that own columns: each signals once per launch
+    for (int r = 0; r < c->nranks; ++r) owners += (c->nm - r * c->nml > 0);
+    if (c->nm_loc <= 0)                             // this rank owns no retained column
+        return signal ? signal_arrival(c, 0, false, owners) : MLV_OK;
     for (int f = 0; f < nf; ++f) {
         if (!spec[f] || !idst[f] || op[f] < MLV_OP_IDENT || op[f] > MLV_OP_INVLAP) {
             set_error("mlv_x_inverse: bad field %d", f);
@@ -804,15 +813,18 @@ int mlv_x_inverse(mlv_ctx* c, int nf, const void* const* spec, const int32_t* op
         }
     }
     a.k = c->k; a.tw = c->planx.tw; a.tws = c->tws_x;
+    int rc = MLV_OK;
     if (c->xsplit) {
-#define MLV_GO(L) return launch_xinv_split<L>(c, a)
+#define MLV_GO(L) rc = launch_xinv_split<L>(c, a)
         MLV_SWITCH_SPLIT(c->planlx, MLV_GO)
 #undef MLV_GO
-    }
-#define MLV_GO(L) return launch_xinv<L>(c, a)
-    MLV_SWITCH_LOG2(c->log2nx, MLV_GO)
+    } else {
+#define MLV_GO(L) rc = launch_xinv<L>(c, a)
+        MLV_SWITCH_LOG2(c->log2nx, MLV_GO)
 #undef MLV_GO
-    return MLV_OK;
+    }
+    if (!rc && signal) rc = signal_arrival(c, 0, true, owners);
+    return rc;
 }
 
 int mlv_z_inverse(mlv_ctx* c, const void* isrc, double* phys) {
@@ -862,8 +874,8 @@ int mlv_x_forward(mlv_ctx* c, const mlv_xfwd* d) {
     XFwdArgs a;
     a.nn = c->nn; a.nm = c->nm_loc; a.spitch = c->spec_cols; a.ipitch = c->nml; a.nf = d->nf;
     a.sh = c->sh;
-    a.wait_counter = nullptr; a.wait_value = 0;
-    if (c->p2p_fwd && c->flags_on) { a.wait_counter = c->peer_flags[c->rank] + 1; a.wait_value = c->expect[1]; }
+    a.wait_counter = nullptr; a.wait_expect = nullptr;
+    if (c->p2p_fwd && c->flags_on) { a.wait_counter = c->peer_flags[c->rank] + 1; a.wait_expect = c->expect + 1; }
     if (c->nm_loc <= 0) return MLV_OK;
     for (int f = 0; f < d->nf; ++f) {
         if (!d->src[f] || d->sym[f] < MLV_SYM_ONE || d->sym[f] > MLV_SYM_FDZ) {
@@ -968,11 +980,7 @@ int mlv_advect_z_rows(mlv_ctx* c, const void* iux, const void* iuz, const void* 
             a.out.blk[h] = (cplx*)ia + (size_t)h * c->sh.fwd_peer;
         }
     }
-    if (c->p2p_inv && c->flags_on) { a.wait_counter = c->peer_flags[c->rank]; a.wait_value = c->expect[0]; }
-    if (c->p2p_fwd && c->flags_on) {
-        a.sig.n = c->nranks;
-        for (int r = 0; r < c->nranks; ++r) a.sig.counter[r] = c->peer_flags[r] + 1;
-    }
+    if (c->p2p_inv && c->flags_on) { a.wait_counter = c->peer_flags[c->rank]; a.wait_expect = c->expect; }
     unsigned grid = 0;
     int rc = 0;
     a.tws = c->tws_z;
@@ -986,7 +994,8 @@ int mlv_advect_z_rows(mlv_ctx* c, const void* iux, const void* iuz, const void* 
 #undef MLV_GO
     }
     if (rc) return rc;
-    if (a.sig.n) c->expect[1] += (unsigned long long)grid * (unsigned long long)c->nranks;
+    if (c->p2p_fwd && c->flags_on)         // every rank bumps the forward counter of every rank once per launch
+        if (int rs = signal_arrival(c, 1, true, c->nranks)) return rs;
     // per-CTA partials of the rows [0, row0 + nrows) launched so far
     c->red_count = (int)((long long)grid * (row0 + nrows) / nrows);
     if (red4) return mlv_reduce_partials(c, nullptr, red4);

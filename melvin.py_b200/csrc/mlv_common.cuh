@@ -238,11 +238,11 @@ MLV_DEV void tma_load_2d(void* smem, const CUtensorMap* map, int c0, int c1, uns
 #endif
 }
 
-// ---- cross-GPU ordering of producer and consumer kernels (peer-memory exchange): every
-// producer CTA bumps a 64-bit arrival counter in each consumer rank's memory after its stores
-// (release at system scope); consumer CTAs spin on their own rank's counter (acquire at system
-// scope) until the arrivals of all producer CTAs of all ranks are in.  Counters only grow; the
-// host passes the cumulative count a launch has to wait for.
+// ---- cross-GPU ordering of producer and consumer kernels (peer-memory exchange): after a
+// producer kernel a one-warp kernel bumps a 64-bit arrival counter in each consumer rank's
+// memory (release at system scope); consumer CTAs spin on their own rank's counter (acquire at
+// system scope) until the arrivals of all ranks are in.  Counters only grow; the host passes
+// the cumulative count a launch has to wait for.
 MLV_DEV void flag_signal(unsigned long long* counter) {
 #ifndef MLV_EMU
     __threadfence_system();

@@ -133,16 +133,22 @@ struct PeerSignals {
     int n;                                   // ranks to signal (0: none)
     unsigned long long* counter[MLV_MAXPEER];
 };
-// last statement of a producer CTA: all of its stores are done
-MLV_DEV void signal_peers(const PeerSignals& s) {
-    if (s.n == 0) return;
-    __syncthreads();
+// Runs right after a producer kernel on the same stream: the kernel boundary has completed all
+// of the producer's peer stores, one thread per rank publishes the arrival.  (Signalling from
+// every producer CTA instead costs a system-scope fence per CTA, which waits for thousands of
+// outstanding NVLink stores with one CTA per SM: measured slower than this extra launch.)
+// It also advances this rank's own count of arrivals due (`expect`, device memory, += inc): the
+// consumer kernels read it from there, so no launch argument changes from step to step and a whole
+// step can be replayed as a CUDA graph.
+__global__ void __launch_bounds__(32) k_signal_peers(const PeerSignals s, unsigned long long* expect,
+                                                     unsigned long long inc) {
     if ((int)threadIdx.x < s.n) flag_signal(s.counter[threadIdx.x]);
+    if (threadIdx.x == 31) *expect += inc;
 }
 // first statement of a consumer CTA
-MLV_DEV void wait_arrivals(const unsigned long long* counter, unsigned long long value) {
+MLV_DEV void wait_arrivals(const unsigned long long* counter, const unsigned long long* expect) {
     if (counter == nullptr) return;
-    if (threadIdx.x == 0) flag_wait(counter, value);
+    if (threadIdx.x == 0) flag_wait(counter, *reinterpret_cast<const volatile unsigned long long*>(expect));
     __syncthreads();
 }
 
@@ -256,7 +262,6 @@ struct XInvArgs {
     cplx* dst[MLV_XMAXF];
     Shard sh;                    // nm = local valid columns; spectral ops use m + sh.m_off
     PeerBlocks out;              // destination block per row owner; dst[f] are offsets into it
-    PeerSignals sig;             // peer stores: arrival counters of the inverse exchange
     long long dstoff[MLV_XMAXF];
     SpecConsts k;
     FftTw tw;
@@ -283,9 +288,10 @@ k_xinv(const __grid_constant__ XInvArgs a) {
     const bool valid = mreal < a.nm;
     const int m = valid ? mreal : a.nm - 1;          // clamp: loads stay unpredicated
     XchgFull<C> xc;
-    xc.buf = reinterpret_cast<cplx*>(MLV_SMEM_BASE());
+    cplx* const xbase = reinterpret_cast<cplx*>(MLV_SMEM_BASE());
+    xc.buf = xbase;
     xc.c = c;
-    cplx* stash = xc.buf + (size_t)F::XSLOTS * C;
+    cplx* stash = xbase + (size_t)F::XSLOTS * C;
     // source column tiles (C*16-byte pieces of 2nn+1 rows) are gathered by the copy engine into
     // the stash: one tensor load per ld_rows rows instead of a scattered load per row and warp
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(stash + (size_t)a.ld_rows * a.ld_boxes * C);
@@ -402,12 +408,12 @@ k_xinv(const __grid_constant__ XInvArgs a) {
             // engine; the stores overlap the next field's loads, prologue and first butterflies
             __syncthreads();
             MLV_UNROLL
-            for (int j = 0; j < 16; ++j) xc.buf[(size_t)(tau + F::T * j) * C + c] = v[j];
+            for (int j = 0; j < 16; ++j) xbase[(size_t)(tau + F::T * j) * C + c] = v[j];
             tma_fence_smem();
             __syncthreads();
             if (threadIdx.x == 0) {
                 for (int r0 = 0; r0 < F::N; r0 += a.tma_rows)
-                    tma_store_2d(&a.tmap[f], xc.buf + (size_t)r0 * C, 2 * C * (int)blockIdx.x, r0);
+                    tma_store_2d(&a.tmap[f], xbase + (size_t)r0 * C, 2 * C * (int)blockIdx.x, r0);
                 tma_commit();
             }
             tma_pending = true;
@@ -421,7 +427,6 @@ k_xinv(const __grid_constant__ XInvArgs a) {
         }
     }
     if (tma_pending && threadIdx.x == 0) tma_wait_read();       // shared memory must outlive the reads
-    signal_peers(a.sig);
 }
 
 // ===================================================================== x forward
@@ -445,7 +450,7 @@ struct XFwdArgs {
     const cplx* tws;             // SPLIT = 2: e^{-2 pi i p/nx}, p < nx/2
     int stage;                   // 1: the block of operand 0 is staged in shared memory by bulk copies
     const unsigned long long* wait_counter;   // peer stores: forward blocks of all ranks have arrived
-    unsigned long long wait_value;            // when *wait_counter >= wait_value
+    const unsigned long long* wait_expect;    // when *wait_counter >= *wait_expect
 };
 
 // I (tile layout) x nf -> spectral: value = scale * FFT_x( sum_f coef_f * D_f[src_f] ), rows
@@ -468,11 +473,12 @@ k_xfwd(const XFwdArgs a) {
     const bool valid = mreal < a.nm;
     const int m = valid ? mreal : a.nm - 1;
     XchgFull<C> xc;
-    xc.buf = reinterpret_cast<cplx*>(MLV_SMEM_BASE());
+    cplx* const xbase = reinterpret_cast<cplx*>(MLV_SMEM_BASE());
+    xc.buf = xbase;
     xc.c = c;
     const double sz = a.symz[m + a.sh.m_off];
     const int rpc = 1 << a.sh.fwd_rshift;             // rows per block of the forward buffers
-    wait_arrivals(a.wait_counter, a.wait_value);
+    wait_arrivals(a.wait_counter, a.wait_expect);
     {   // L2 prefetch: the other fields' blocks, the next CTA's first block, and the
         // state / history columns the epilogue will read
         constexpr unsigned CHUNK = 16384;
@@ -502,14 +508,14 @@ k_xfwd(const XFwdArgs a) {
     // the x stencil reads every element of operand 0 twice (rows x-1, x+1): its block of this
     // column tile is brought into the (still idle) exchange buffer by the copy engine -- one
     // request for the whole block instead of four dependent groups of loads per thread
-    unsigned long long* bar = reinterpret_cast<unsigned long long*>(xc.buf + (size_t)F::XSLOTS * C);
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(xbase + (size_t)F::XSLOTS * C);
     if (SPLIT == 1 && a.stage) {
         if (threadIdx.x == 0) mbar_init(bar, 1);
         __syncthreads();
         if (threadIdx.x == 0) {
             mbar_expect_tx(bar, (unsigned)(NF * C * sizeof(cplx)));
             for (int x0 = 0; x0 < NF; x0 += rpc)
-                bulk_load(xc.buf + (size_t)x0 * C,
+                bulk_load(xbase + (size_t)x0 * C,
                           a.src[0] + (size_t)(x0 >> a.sh.fwd_rshift) * a.sh.fwd_chunk + (size_t)blockIdx.x * rpc * C,
                           (unsigned)(rpc * C * sizeof(cplx)), bar);
         }
@@ -560,8 +566,8 @@ k_xfwd(const XFwdArgs a) {
                     MLV_UNROLL
                     for (int j = 0; j < 16; ++j) {
                         const int x = tau + F::T * j;
-                        const cplx p = xc.buf[(size_t)((x + 1) & (NF - 1)) * C + c];
-                        const cplx q = xc.buf[(size_t)((x - 1) & (NF - 1)) * C + c];
+                        const cplx p = xbase[(size_t)((x + 1) & (NF - 1)) * C + c];
+                        const cplx q = xbase[(size_t)((x - 1) & (NF - 1)) * C + c];
                         v[j] = mk(fma(cw, p.x - q.x, v[j].x), fma(cw, p.y - q.y, v[j].y));
                     }
                     ++f;
@@ -923,9 +929,8 @@ struct ZAdvArgs {
     const cplx* Iuz;
     const cplx* Iq;
     PeerBlocks out;                // destination block per tile owner; IA/IB given as offsets
-    PeerSignals sig;               // peer stores: arrival counters of the forward exchange
     const unsigned long long* wait_counter;   // peer stores: inverse blocks of all ranks have arrived
-    unsigned long long wait_value;
+    const unsigned long long* wait_expect;
     long long outoff[2];
     cplx* IA;                      // out: z-spectrum of ux q   (tile layout)
     cplx* IB;                      // out: z-spectrum of uz q
@@ -954,7 +959,7 @@ k_z_advect(const ZAdvArgs a) {
     const size_t rowoff = (size_t)(2 * rp) * a.ipitch;
     const int cts = log2_pow2(a.ct);                 // tile width is a power of two
     const bool sharded = a.sh.fwd_chunk != 0;
-    wait_arrivals(a.wait_counter, a.wait_value);
+    wait_arrivals(a.wait_counter, a.wait_expect);
 
     // announce the rows of the two velocity components (needed one and two transforms
     // from now) and the scalar rows of the CTA that will follow this one on the SM
@@ -1052,7 +1057,6 @@ k_z_advect(const ZAdvArgs a) {
         }
         if (w < 4 && g == 0) a.red[(size_t)blockIdx.x * 4 + w] = rbuf[w * NT];
     }
-    signal_peers(a.sig);
 }
 
 }  // namespace mlv

@@ -88,7 +88,6 @@ k_xinv_split(const XInvArgs a) {
             }
         }
     }
-    signal_peers(a.sig);
 }
 
 // ===================================================================== z stage, real rows
@@ -261,7 +260,7 @@ k_zr_advect(const ZAdvArgs a) {
     const size_t rowoff = (size_t)x * a.ipitch;
     const int cts = log2_pow2(a.ct);
     const bool sharded = a.sh.fwd_chunk != 0;
-    wait_arrivals(a.wait_counter, a.wait_value);
+    wait_arrivals(a.wait_counter, a.wait_expect);
 
     cplx v[16];
     zreal_load_line<LOG2H>(v, a.Iq + rowoff, a.tws, tau, a.nm, a.sh);
@@ -311,7 +310,6 @@ k_zr_advect(const ZAdvArgs a) {
         }
         if (w < 4 && g == 0) a.red[(size_t)blockIdx.x * 4 + w] = rbuf[w * NT];
     }
-    signal_peers(a.sig);
 }
 
 }  // namespace mlv

@@ -425,6 +425,29 @@ class Integrator:
         return self._dt / 24 * (9 * dvar.get() + 19 * dvar.get(-1)
                                 - 5 * dvar.get(-2) + dvar.get(-3))
 
+    def predictor_corrector(self, var, dvar, rhs, diffusion_term=None):
+        """One PECE step of the Adams-Bashforth / Adams-Moulton pair the reference advertises
+        (README.md:55) but never wires up (`corrector` has no call site):
+
+            predict   y* = y_n + AB(f_n, f_n-1, ...)            (Integrator.py:5-18)
+            evaluate  f* = rhs(y*)                               (the script's right-hand side)
+            correct   y_n+1 = y_n + AM(f*, f_n, f_n-1, ...)      (Integrator.py:20-33)
+
+        `dvar` holds f_n in its current level on entry (as for `integrate`) and f* on exit,
+        `rhs` is a callable returning the right-hand side for the state now in `var`
+        (explicit treatment of every term; `diffusion_term`, if given, is added to f_n first as
+        `_explicit` does).  An extension without a reference implementation: parity is
+        unpinned, its order of accuracy is verified by convergence tests."""
+        dvar._flush()
+        if diffusion_term is not None:
+            dvar[:] = dvar[:] + _dev(diffusion_term, np.complex128)
+        y_n = _dev(var[:], np.complex128).copy()
+        var[:] = y_n + self.predictor(dvar)                      # P
+        dvar.advance()
+        dvar[:] = rhs()                                          # E (at the predicted state)
+        dvar._flush()
+        var[:] = y_n + self.corrector(dvar)                      # C
+
     def set_dt(self, ux, uz):
         """Sets dt based on CFL limit (Integrator.py:35-44; signed max)."""
         mx = ux._cached_reduction(1) if hasattr(ux, "_cached_reduction") else None

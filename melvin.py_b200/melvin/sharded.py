@@ -145,6 +145,10 @@ class ShardedScalarStepper:
         self.fwd_block = self.fwd_field // self.nchunks      # one row block of one peer and field
         self.cur = 0
         self.hidx = 0
+        # CUDA graphs of the step (scalar stepper; peer-store exchange ordered on the device, or one GPU)
+        graphable = (type(self) is ShardedScalarStepper and _backend.is_cuda()
+                     and (self.world == 1 or (self.p2p and self._flags)))
+        self._graphs = {} if graphable and os.environ.get("MLV_GRAPH", "1") != "0" else None
         self.red4 = _backend.zeros((4,), np.float64)
         self._alloc_state()
         self.t = 0.0
@@ -376,6 +380,32 @@ class ShardedScalarStepper:
         return self._cfl_counter < self.loop + 1 or self._trk_counter < self.loop + 1
 
     def step(self):
+        # peer-store exchange (and the single-GPU stepper): nothing in a step depends on the host
+        # -- the kernels of a step are ordered across ranks on the device -- so a step is replayed
+        # as a CUDA graph: one launch instead of five, no Python or ctypes latency in between
+        if self._graphs is not None:
+            key = (self.cur, self.hidx, self.dt, self._tickers_due())
+            g = self._graphs.get(key)
+            if g is None and self.loop >= 2 * self.order:       # after the eager warm-up steps
+                if len(self._graphs) > 4 * self.order:          # dt changed: drop the stale graphs
+                    self._graphs.clear()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._launch_step()
+                self._graphs[key] = g
+            if g is not None:
+                g.replay()
+                self._advance()
+                return
+        self._launch_step()
+        self._advance()
+
+    def _advance(self):
+        self.cur = 1 - self.cur
+        self.hidx = (self.hidx + 1) % self.order
+        self.end_loop()
+
+    def _launch_step(self):
         ctx = self.ctx
         w_in, w_out = self.w[self.cur], self.w[1 - self.cur]
         wp = w_in.data_ptr()
@@ -433,9 +463,6 @@ class ShardedScalarStepper:
         if self.order == 4:
             g.fm2, g.fm3 = lv[2], lv[3]
         ctx.call("mlv_x_forward", ctypes.byref(d))
-        self.cur = 1 - self.cur
-        self.hidx = (self.hidx + 1) % self.order
-        self.end_loop()
 
     # ------------------------------------------------- tickers (Simulation.end_loop)
     def _global_reductions(self):

@@ -261,3 +261,13 @@ def test_adams_moulton_corrector_formulas(order):
     import host_cases as hc
     got_c, want_c, got_p, want_p = hc.corrector_formulas(order)
     assert rel(got_c, want_c) < 1e-14 and rel(got_p, want_p) < 1e-14
+
+
+@pytest.mark.parametrize("order", [2, 4])
+def test_predictor_corrector_converges_at_its_order(order):
+    """SURVEY 8f-3 (parity unpinned: no reference implementation): AB/AM PECE step"""
+    import host_cases as hc
+    res = hc.predictor_corrector_convergence(order)
+    rates = [np.log2(res[i][1] / res[i + 1][1]) for i in range(len(res) - 1)]
+    assert all(r > order - 0.35 for r in rates), (res, rates)
+    assert res[-1][1] < (1e-4 if order == 2 else 1e-8)

@@ -448,3 +448,14 @@ def test_async_frame_output_is_a_snapshot():
         assert xp._output is not None and xp._output.frames_written == 6
         for k in range(6):
             assert np.array_equal(np.load(f"w{k:04d}.npy"), frames[k]), k
+
+
+@pytest.mark.parametrize("order", [2, 4])
+def test_predictor_corrector_converges_at_its_order(order):
+    """SURVEY 8f-3 (parity unpinned: the reference never calls its correctors): AB/AM PECE step,
+    observed order of accuracy on a problem with a known solution"""
+    import host_cases as hc
+    res = hc.predictor_corrector_convergence(order)
+    rates = [np.log2(res[i][1] / res[i + 1][1]) for i in range(len(res) - 1)]
+    assert all(r > order - 0.35 for r in rates), (res, rates)
+    assert res[-1][1] < (1e-4 if order == 2 else 1e-8)
