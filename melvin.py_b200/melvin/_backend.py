@@ -109,14 +109,40 @@ def zeros(shape, dtype):
     return t
 
 
-def from_host(arr, dtype=None):
+def _host_tensor(arr, dtype=None):
     a = np.ascontiguousarray(arr, dtype=dtype)
     if a.dtype not in _TORCH_DTYPE:
         a = a.astype(np.complex128 if np.iscomplexobj(a) else np.float64)
-    t = torch.from_numpy(a)
+    return torch.from_numpy(a)
+
+
+def from_host(arr, dtype=None):
+    """Host array -> new device buffer.  A source in PINNED host memory is copied
+    asynchronously on the current stream (the caller keeps the source unchanged until the
+    stream has passed the copy, as with any pinned-memory transfer); pageable sources are
+    copied synchronously."""
+    t = _host_tensor(arr, dtype)
     if is_cuda():
-        return t.to(device(), non_blocking=False)
+        return t.to(device(), non_blocking=t.is_pinned())
     return t.clone()
+
+
+def copy_from_host(dst, arr):
+    """Host array -> existing device buffer of the same shape (no staging buffer); asynchronous
+    for pinned sources, see from_host."""
+    t = _host_tensor(arr, np.complex128 if dst.is_complex() else np.float64)
+    dst.copy_(t, non_blocking=is_cuda() and t.is_pinned())
+
+
+def copy_to_host(out, t):
+    """Device buffer -> caller-provided host array (numpy array or torch tensor).  Into PINNED
+    memory the copy is asynchronous on the current stream: the data is valid once the stream
+    (or an event recorded after this call) has been synchronised."""
+    h = out if isinstance(out, torch.Tensor) else torch.from_numpy(out)
+    if tuple(h.shape) != tuple(t.shape) or h.dtype != t.dtype or not h.is_contiguous():
+        raise ValueError("on_host(out=...): the host buffer must be contiguous and match the shape and dtype")
+    h.copy_(t.detach(), non_blocking=is_cuda() and h.is_pinned())
+    return out
 
 
 def to_host(t):
@@ -248,8 +274,10 @@ def context_for(params):
         if int(params.nx) % (2 * _dist.world()):
             raise NotImplementedError("slab decomposition needs nx divisible by twice the rank count")
         shard = (_dist.rank(), _dist.world())
+    # one context (plans + scratch pool) per grid AND per stream it is created under: simulations
+    # built under different `torch.cuda.stream(...)` blocks run concurrently (melvin/ensemble.py)
     key = (int(params.nx), int(params.nz), float(params.lx), float(params.lz), fdm_z,
-           int(params.spatial_derivative_order), str(device()), shard)
+           int(params.spatial_derivative_order), str(device()), shard, current_stream_handle())
     ctx = _contexts.get(key)
     if ctx is None:
         ctx = Context(params.nx, params.nz, params.lx, params.lz, fdm_z,

@@ -291,7 +291,15 @@ class Variable:
                 # (FDM-z mode has no params.nm: re-sampling fails there as in the reference, App. A-14)
                 nn, nm = self._params.nn, self._params.nm
                 data = scale_variable(data, (nn, nm), np if isinstance(data, np.ndarray) else self._xp)
-            self.sets(self._dt.from_host(data))
+            if (isinstance(data, np.ndarray) and self._ctx.world == 1
+                    and tuple(data.shape) == tuple(self._s._t.shape)):
+                # host state of the right shape: straight into the state buffer (asynchronous
+                # on the current stream when `data` lives in pinned memory)
+                self._flush_dependants(self._s._t)
+                self._virt = None
+                _backend.copy_from_host(self._s._t, data)
+            else:
+                self.sets(self._dt.from_host(data))
 
     # ------------------------------------------------------ derivatives
     def pddx(self):
@@ -451,7 +459,13 @@ class Variable:
         fname = self._dump_name + f"{dump_counter:04d}.npy"
         self._xp.save(fname, self._p)
 
-    def on_host(self):
+    def on_host(self, out=None):
+        """Host copy of the spectral data (reference melvin/Variable.py: on_host).  With `out`
+        (a host array of the right shape; pinned memory makes the copy asynchronous on the
+        current stream -- synchronise the stream or an event before reading it) no new host
+        array is allocated."""
+        if out is not None and self._ctx.world == 1:
+            return _backend.copy_to_host(out, self.gets()._touch()._t)
         return self._dt.to_host(self.gets())
 
     def get_name(self):

@@ -41,3 +41,35 @@ def test_bench_parity_preflight_single():
     import bench
     res = bench.parity_single_gpu()
     assert res["ok"] and res["cases"][0]["field_rel_l2"] < 1e-12
+
+
+def test_streamed_ensemble_matches_blocking_loop():
+    """melvin/ensemble.py: members stepped round-robin with host-resident states (Variable.load from
+    a host buffer, on_host(out=...)) give the states of the same simulations stepped one by one."""
+    import bench
+    from melvin.ensemble import Ensemble
+    cwd = os.getcwd()
+    try:
+        def build(i):
+            step, o = bench.build_public_loop("kh", 32, 32)
+            return {"step": step, "o": o, "host": o["w"].on_host().copy()}
+        ens = Ensemble(build, members=3)
+        assert len({id(m.payload["o"]["w"]._ctx) for m in ens.members}) == (3 if _backend.is_cuda() else 1)
+        for k in range(9):
+            with ens.turn(k) as m:
+                p = m.payload
+                p["o"]["w"].load(p["host"], is_physical=False)
+                p["step"]()
+                p["o"]["w"].on_host(out=p["host"])
+        ens.drain()
+        step, o = bench.build_public_loop("kh", 32, 32)
+        for _ in range(3):
+            step()
+        want = o["w"].on_host()
+        for m in ens.members:
+            assert m.passes == 3
+            np.testing.assert_allclose(m.payload["host"], want, rtol=0, atol=1e-14 * np.abs(want).max())
+        with pytest.raises(ValueError):
+            o["w"].on_host(out=np.zeros((3, 3), dtype=np.complex128))
+    finally:
+        os.chdir(cwd)

@@ -459,3 +459,40 @@ def test_predictor_corrector_converges_at_its_order(order):
     rates = [np.log2(res[i][1] / res[i + 1][1]) for i in range(len(res) - 1)]
     assert all(r > order - 0.35 for r in rates), (res, rates)
     assert res[-1][1] < (1e-4 if order == 2 else 1e-8)
+
+
+def test_streamed_ensemble_with_pinned_host_states():
+    """melvin/ensemble.py on real streams: three members, each pass = asynchronous upload from
+    pinned memory -> time step -> asynchronous read-back; states equal the blocking loop's and
+    the oracle's (1e-12)."""
+    import os
+    import torch
+    import bench
+    from melvin.ensemble import Ensemble
+    cwd = os.getcwd()
+    try:
+        def build(i):
+            step, o = bench.build_public_loop("kh", 256, 128)
+            return {"step": step, "o": o, "host": torch.from_numpy(o["w"].on_host()).pin_memory()}
+        ens = Ensemble(build, members=3)
+        assert len({id(m.payload["o"]["w"]._ctx) for m in ens.members}) == 3        # one context per stream
+        for k in range(12):
+            with ens.turn(k) as m:
+                p = m.payload
+                p["o"]["w"].load(p["host"].numpy(), is_physical=False)
+                p["step"]()
+                p["o"]["w"].on_host(out=p["host"])
+        ens.drain()
+        step, o = bench.build_public_loop("kh", 256, 128)
+        for _ in range(4):
+            step()
+        want = o["w"].on_host()
+        for m in ens.members:
+            assert rel_l2(m.payload["host"].numpy(), want) < 1e-14
+        pd = bench.run_params("kh", 256, 128)
+        g = mo.Grid(256, 128, pd["lx"], pd["lz"])
+        ic = bench.initial_fields("kh", 256, 128, pd)
+        ref, _, _ = mo.run_single_scalar(g, ic["w"], 1.0 / pd["Re"], pd["initial_dt"], 4)
+        assert rel_l2(want, ref) < FIELD_TOL
+    finally:
+        os.chdir(cwd)
