@@ -149,6 +149,27 @@ typedef struct mlv_ew {             /* out = a (op) b on (rows, cols) views */
     double a_re, a_im, b_re, b_im;
 } mlv_ew;
 
+typedef struct mlv_trig {           /* pruned DFT of period `period` along ONE axis by direct summation */
+    int32_t inverse;                /* 0: samples -> modes (e^{-2 pi i jk/M}); 1: modes -> samples (e^{+...}) */
+    int32_t ext;                    /* how the n_samp samples fill a period: MLV_EXT_* */
+    int32_t period;                 /* M: n_samp (periodic) or 2(n_samp-1) (mirrored) */
+    int32_t n_samp, n_modes;        /* entries stored along the axis on either side */
+    int32_t two_sided;              /* modes k = 0..nn,-nn..-1 (n_modes = 2nn+1); else k = 0..n_modes-1 */
+    int32_t hermitian;              /* inverse of a one-sided spectrum to REAL samples (numpy irfft); real scale only */
+    int32_t samp_complex;           /* samples are complex128 (else float64) */
+    int32_t batch_fastest;          /* adjacent threads take adjacent lines (unit batch stride) */
+    int32_t nbatch;                 /* number of lines */
+    int64_t samp_stride, samp_batch_stride;   /* elements along the axis / between lines */
+    int64_t mode_stride, mode_batch_stride;
+    const void* in;
+    void* out;
+    double scale_re, scale_im;      /* complex factor of the result */
+    double w0;                      /* weight of mode 0 (cosine: forward 1/2, inverse 2; else 1) */
+} mlv_trig;
+#define MLV_EXT_PERIODIC 0
+#define MLV_EXT_EVEN 1              /* x0..x_{n-1}, x_{n-2}..x_1     SpectralTransformer.py:169-172 */
+#define MLV_EXT_ODD 2               /* x0..x_{n-2}, -x_{n-1}..-x_1   SpectralTransformer.py:174-178 */
+
 /* ---- context ------------------------------------------------------------- */
 int mlv_create(const mlv_params* p, mlv_ctx** ctx);
 int mlv_destroy(mlv_ctx* ctx);
@@ -234,6 +255,10 @@ int mlv_reduce_partials(mlv_ctx* ctx, const double* partials, double* red4);
 /* materialised physical operands: out = pddx(ux*q) + pddz(uz*q) */
 int mlv_advect_phys(mlv_ctx* ctx, const double* ux, const double* uz, const double* q,
                     double* out);
+
+/* ---- COSINE / SINE bases (melvin/SpectralTransformer.py:108-125,134-146,169-196): the mirrored
+ * rfft2 / irfft2 of the reference, one axis per call, only the retained modes evaluated. */
+int mlv_trig_axis(mlv_ctx* ctx, const mlv_trig* d);
 
 /* ---- SpatialDifferentiator ------------------------------------------------
  * spectral: sddx/sddz/sd2dx2/sd2dz2/calc_lap (:50-74) through mlv_spec_lincomb;

@@ -3,10 +3,12 @@
 
 #include "mlv_kernels_pw.cuh"
 #include "mlv_kernels_split.cuh"
+#include "mlv_kernels_trig.cuh"
 #include "mlv_rt.h"
 
 #include <stdarg.h>
 #include <new>
+#include <utility>
 #include <vector>
 
 namespace mlv {
@@ -67,6 +69,8 @@ struct mlv_ctx {
     unsigned long long* peer_flags[MLV_MAXPEER] = {};
     bool flags_on = false;
     unsigned long long* expect = nullptr;       // device: arrivals due at this rank so far, [0] inverse, [1] forward
+    // COSINE / SINE bases: roots of unity e^{-2 pi i j/M} per period M (mlv_trig_axis)
+    std::vector<std::pair<int, mlv::cplx*>> trig_tables;
     mlv::stream_t stream = 0;
 };
 
@@ -78,30 +82,40 @@ static int ilog2_exact(int n) {
     return ((1 << l) == n) ? l : -1;
 }
 
+// table of one pass (radix r, remaining length n3): plane b < log2(r) holds exp(-2 pi i n 2^b / (r n3)), n < n3
+static size_t append_table(std::vector<cplx>& host, int r, int n3) {
+    const size_t off = host.size();
+    const long double ncur = (long double)r * n3;
+    int lr = 0;
+    while ((1 << lr) < r) ++lr;
+    for (int b = 0; b < lr; ++b)
+        for (int n = 0; n < n3; ++n) {
+            // argument reduced exactly in integers
+            const long long e = ((long long)n << b) % (long long)ncur;
+            const long double ang = -2.0L * 3.14159265358979323846264338327950288L * (long double)e / ncur;
+            host.push_back(mk((double)cosl(ang), (double)sinl(ang)));
+        }
+    return off;
+}
+
 template <int LOG2N>
-static void build_tables(std::vector<cplx>& host, size_t (&offs)[MLV_MAX_PASS]) {
+static void build_tables(std::vector<cplx>& host, size_t (&offs)[MLV_MAX_PASS + 2]) {
     typedef FftCfg<LOG2N> F;
-    for (int p = 0; p < MLV_MAX_PASS; ++p) offs[p] = (size_t)-1;
+    for (int p = 0; p < MLV_MAX_PASS + 2; ++p) offs[p] = (size_t)-1;
     for (int p = 0; p < F::NPASS; ++p) {
         const int n3 = F::n3(p), r = F::radix(p);
         if (n3 <= 1) continue;
-        offs[p] = host.size();
-        const long double ncur = (long double)r * n3;
-        int lr = 0;
-        while ((1 << lr) < r) ++lr;
-        for (int n = 0; n < n3; ++n)
-            for (int b = 0; b < lr; ++b) {
-                // exp(-2 pi i n 2^b / ncur), argument reduced exactly in integers
-                const long long e = ((long long)n << b) % (long long)ncur;
-                const long double ang = -2.0L * 3.14159265358979323846264338327950288L * (long double)e / ncur;
-                host.push_back(mk((double)cosl(ang), (double)sinl(ang)));
-            }
+        offs[p] = append_table(host, r, n3);
+    }
+    if (F::NPASS == 3) {        // mirrored pass order 16 -> 16 -> R0 (fft_grp2nat)
+        offs[MLV_MAX_PASS] = append_table(host, 16, F::T);
+        offs[MLV_MAX_PASS + 1] = append_table(host, 16, F::R0);
     }
 }
 
 static int make_plan(Plan& plan, int log2n, stream_t s) {
     std::vector<cplx> host;
-    size_t offs[MLV_MAX_PASS];
+    size_t offs[MLV_MAX_PASS + 2];
     switch (log2n) {
 #define MLV_CASE(L) case L: build_tables<L>(host, offs); break;
         MLV_CASE(4) MLV_CASE(5) MLV_CASE(6) MLV_CASE(7) MLV_CASE(8) MLV_CASE(9)
@@ -120,6 +134,8 @@ static int make_plan(Plan& plan, int log2n, stream_t s) {
     }
     for (int p = 0; p < MLV_MAX_PASS; ++p)
         plan.tw.p[p] = (offs[p] == (size_t)-1) ? nullptr : plan.dev + offs[p];
+    for (int p = 0; p < 2; ++p)
+        plan.tw.g[p] = (offs[MLV_MAX_PASS + p] == (size_t)-1) ? nullptr : plan.dev + offs[MLV_MAX_PASS + p];
     return 0;
 }
 
@@ -453,17 +469,30 @@ template <int L>
 static int launch_zadv(mlv_ctx* c, ZAdvArgs& a, unsigned& grid_out) {
     constexpr int LPC = zlines(L);
     typedef FftCfg<L> F;
-    auto kfn = k_z_advect<L, LPC>;
     const size_t smem = (size_t)LPC * (F::XSLOTS * sizeof(double) + (size_t)F::N * sizeof(cplx)) +
                         (size_t)4 * LPC * F::T * sizeof(double);
-    const unsigned grid = (unsigned)((a.nrows / 2 + LPC - 1) / LPC);
+    unsigned grid = (unsigned)((a.nrows / 2 + LPC - 1) / LPC);
+    a.wave = 148 * (smem > 113 * 1024 ? 1 : 2);
+    // three-pass lengths: persistent CTAs (one per resident slot) with grouped transforms
+    const bool grouped = F::NPASS == 3 && !rt_env_flag("MLV_ZADV_CLASSIC");
+    if (grouped && grid > (unsigned)a.wave) grid = (unsigned)a.wave;
+    if (grouped) {                           // test switch: force several row pairs per CTA on small grids
+        const char* g = getenv("MLV_ZADV_GRID");
+        if (g && atoi(g) > 0 && (unsigned)atoi(g) < grid) grid = (unsigned)atoi(g);
+    }
     grid_out = grid;
     // per-CTA partials: the launch over rows [row0, row0 + nrows) owns slots [k grid, (k+1) grid), k = row0 / nrows
     int rc = ensure_red(c, (size_t)(a.nx / a.nrows) * grid * 4);
     if (rc) return rc;
     a.red = (c->red_user ? c->red_user : c->red) + (size_t)(a.row0 / a.nrows) * grid * 4;
-    a.wave = 148 * (smem > 113 * 1024 ? 1 : 2);
-
+    if constexpr (F::NPASS == 3) {
+        if (grouped) {
+            auto kfn = k_z_advect_grouped<L, LPC>;
+            MLV_LAUNCH(kfn, grid, (unsigned)(LPC * F::T), smem, c->stream, a);
+            return 0;
+        }
+    }
+    auto kfn = k_z_advect<L, LPC>;
     MLV_LAUNCH(kfn, grid, (unsigned)(LPC * F::T), smem, c->stream, a);
     return 0;
 }
@@ -654,6 +683,7 @@ int mlv_destroy(mlv_ctx* c) {
     if (c->symx) rt_free(c->symx);
     if (c->red) rt_free(c->red);
     if (c->expect) rt_free(c->expect);
+    for (auto& t : c->trig_tables) rt_free(t.second);
     delete c;
     return MLV_OK;
 }
@@ -1155,6 +1185,47 @@ int mlv_reduce(mlv_ctx* c, int op, int rows, int cols, const mlv_view* av, const
     MLV_LAUNCH(kfn, grid, 256u, 256 * sizeof(double), c->stream, a);
     const int fop = (op == MLV_RED_MAX) ? RED_MAX : (op == MLV_RED_MIN ? RED_MIN : RED_SUM);
     return reduce_final(c, c->red, (int)grid, 1, 0, fop, out_dev);
+}
+
+// ------------------------------------------------ COSINE / SINE bases
+static int trig_table(mlv_ctx* c, int M, const cplx** out) {
+    for (auto& t : c->trig_tables)
+        if (t.first == M) { *out = t.second; return MLV_OK; }
+    std::vector<cplx> host((size_t)M);
+    for (int j = 0; j < M; ++j) {
+        const long double ang = -2.0L * 3.14159265358979323846264338327950288L * (long double)j / (long double)M;
+        host[j] = mk((double)cosl(ang), (double)sinl(ang));
+    }
+    cplx* dev = nullptr;
+    int rc = rt_malloc((void**)&dev, host.size() * sizeof(cplx));
+    if (!rc) rc = rt_h2d(dev, host.data(), host.size() * sizeof(cplx), c->stream);
+    if (rc) return rc;
+    c->trig_tables.push_back(std::make_pair(M, dev));
+    *out = dev;
+    return MLV_OK;
+}
+
+int mlv_trig_axis(mlv_ctx* c, const mlv_trig* d) {
+    if (!c || !d || !d->in || !d->out) { set_error("mlv_trig_axis: null argument"); return MLV_ERR_INVALID; }
+    const int mirrored = d->ext == MLV_EXT_EVEN || d->ext == MLV_EXT_ODD;
+    if (d->ext < MLV_EXT_PERIODIC || d->ext > MLV_EXT_ODD || d->n_samp < 2 || d->n_modes < 1 || d->nbatch < 1 ||
+        d->period != (mirrored ? 2 * (d->n_samp - 1) : d->n_samp) ||
+        (d->two_sided && !(d->n_modes & 1)) || (d->two_sided ? d->n_modes / 2 : d->n_modes - 1) > d->period / 2 ||
+        (d->hermitian && (!d->inverse || d->two_sided || d->scale_im != 0.0))) {
+        set_error("mlv_trig_axis: inconsistent descriptor");
+        return MLV_ERR_INVALID;
+    }
+    TrigArgs a;
+    a.inverse = d->inverse; a.ext = d->ext; a.M = d->period; a.n_samp = d->n_samp; a.n_modes = d->n_modes;
+    a.two_sided = d->two_sided; a.hermitian = d->hermitian; a.samp_complex = d->samp_complex;
+    a.batch_fastest = d->batch_fastest; a.w0 = d->w0; a.nbatch = d->nbatch;
+    a.samp_stride = d->samp_stride; a.samp_batch = d->samp_batch_stride;
+    a.mode_stride = d->mode_stride; a.mode_batch = d->mode_batch_stride;
+    a.in = d->in; a.out = d->out; a.sre = d->scale_re; a.sim = d->scale_im;
+    if (int rc = trig_table(c, a.M, &a.E)) return rc;
+    auto kfn = k_trig_axis;
+    MLV_LAUNCH(kfn, grid1d((size_t)(a.inverse ? a.n_samp : a.n_modes) * a.nbatch), 256u, 0, c->stream, a);
+    return MLV_OK;
 }
 
 }  // extern "C"

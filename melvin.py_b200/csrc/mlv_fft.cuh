@@ -26,10 +26,16 @@ namespace mlv {
 
 #define MLV_MAX_PASS 4
 
-// Per-pass twiddle tables (device pointers).  Table p has N3_p rows of log2(R_p) entries
-//   tw[n*log2(R) + b] = exp(-2 pi i n 2^b / (R_p N3_p));   unused when N3_p == 1.
+// Per-pass twiddle tables (device pointers).  Table p holds log2(R_p) planes of N3_p entries
+//   tw[b*N3 + n] = exp(-2 pi i n 2^b / (R_p N3_p));   unused when N3_p == 1.
+// (Plane-major: the lanes of a warp read consecutive n of one plane, i.e. consecutive 16-byte
+// entries; with the entries of one n side by side every lane touched its own 64-byte stretch and
+// a table load cost 16 LSU wavefronts instead of 4 -- more than the data loads of the z stage.)
 struct FftTw {
     const cplx* p[MLV_MAX_PASS];
+    // three-pass lengths only (N = R0*256): tables of the mirrored pass order 16 -> 16 -> R0
+    // (fft_grp2nat): g[0] = (R 16, N3 N/16), g[1] = (R 16, N3 R0)
+    const cplx* g[2];
 };
 
 template <int LOG2N>
@@ -176,7 +182,7 @@ MLV_DEV void tw_fetch(cplx (&wb)[4], int tau, int u, const cplx* tw) {
     constexpr int LR = Log2R<R>::v;
     const int n = (tau + T * u) & (N3 - 1);
     MLV_UNROLL
-    for (int b = 0; b < LR; ++b) wb[b] = tw[n * LR + b];
+    for (int b = 0; b < LR; ++b) wb[b] = tw[b * N3 + n];
 }
 
 template <bool INV>
@@ -304,6 +310,88 @@ MLV_DEV void fft_line(cplx (&v)[16], const int tau_, const FftTw& tw, X& xc) {
     const int tau = opaque_int(tau_);    // per-transform index arithmetic (see opaque_int)
     fft_pass<C::R0, C::n3(0), C::T, INV>(v, tau, tw.p[0]);
     if constexpr (C::NPASS > 1) fft_later_passes<LOG2N, 1, INV, X>(v, tau, tw, xc);
+}
+
+// ------------------------------------------------ grouped three-pass transforms
+// N = R0 * 256 (three passes).  The last two passes of the standard order R0 -> 16 -> 16 are 256-point
+// sub-transforms that live inside groups of 16 consecutive threads (thread tau = 16 k0 + c): if
+// the result may stay in *grouped order*
+//     thread tau, register j  <->  index (tau >> 4) + R0 (tau & 15) + (N/16) j
+// the exchange before the last pass is a 16x16 transpose inside the group -- half a warp, no
+// CTA barrier, and the warps of a line drift apart instead of meeting at every exchange.
+// Point-wise work (products, maxima, sums) does not care about the order, and the mirrored
+// pass order 16 -> 16 -> R0 takes grouped order back to natural order with its FIRST exchange
+// inside the group.  A physical-space stage  inverse -> product -> forward  therefore needs one
+// CTA-wide exchange per transform instead of two.
+MLV_DEV void warp_sync() {
+#ifdef MLV_EMU
+    const int w = (int)threadIdx.x >> 5;
+    const int left = (int)blockDim.x - 32 * w;
+    emu_bar_sync(16 + w, left < 32 ? left : 32);
+#else
+    __syncwarp();
+#endif
+}
+
+// 16x16 transpose inside a group of 16 threads through the group's 16*17 doubles of the (half-size)
+// exchange buffer: register j of lane c <-> register c of lane j.  Real parts, then imaginary
+// parts.  The region belongs to the group (one half-warp), so warp-level ordering is enough
+// against the group's own previous use; the caller orders it against CTA-wide users of the
+// same buffer with a CTA barrier.
+MLV_DEV void group_transpose(cplx (&v)[16], double* gbuf, const int lane) {
+    warp_sync();
+    MLV_UNROLL
+    for (int j = 0; j < 16; ++j) gbuf[j * 17 + lane] = v[j].x;
+    warp_sync();
+    MLV_UNROLL
+    for (int j = 0; j < 16; ++j) v[j].x = gbuf[lane * 17 + j];
+    warp_sync();
+    MLV_UNROLL
+    for (int j = 0; j < 16; ++j) gbuf[j * 17 + lane] = v[j].y;
+    warp_sync();
+    MLV_UNROLL
+    for (int j = 0; j < 16; ++j) v[j].y = gbuf[lane * 17 + j];
+}
+
+// natural order in -> grouped order out (passes R0, 16, 16).  `buf`: the line's XSLOTS doubles.
+template <int LOG2N, bool INV>
+MLV_DEV void fft_nat2grp(cplx (&v)[16], const int tau_, const FftTw& tw, double* buf) {
+    typedef FftCfg<LOG2N> C;
+    static_assert(C::NPASS == 3, "grouped transforms: N = R0 * 256");
+    const int tau = opaque_int(tau_);
+    fft_pass<C::R0, C::n3(0), C::T, INV>(v, tau, tw.p[0]);
+    XchgSplit xc;
+    xc.buf = buf;
+    const int lo = tau & 15, hi = tau >> 4;
+    xc.exchange(v, [&](int j) { return tau + C::T * j; }, [&](int j) { return lo + 16 * j + 256 * hi; });
+    fft_pass<16, 16, C::T, INV>(v, tau, tw.p[1]);
+    __syncthreads();                       // every CTA-wide read done before the groups reuse the buffer
+    group_transpose(v, buf + 272 * hi, lo);
+    fft_pass<16, 1, C::T, INV>(v, tau, nullptr);
+}
+
+// grouped order in -> natural order out (passes 16, 16, R0).  The caller guarantees that no
+// CTA-wide exchange is still reading `buf` when this is called (a preceding fft_nat2grp is fine).
+template <int LOG2N, bool INV>
+MLV_DEV void fft_grp2nat(cplx (&v)[16], const int tau_, const FftTw& tw, double* buf) {
+    typedef FftCfg<LOG2N> C;
+    static_assert(C::NPASS == 3, "grouped transforms: N = R0 * 256");
+    constexpr int U = 16 / C::R0;
+    const int tau = opaque_int(tau_);
+    const int s = tau & 15, p = tau >> 4;
+    // x[n_lo + T j], n_lo = p + R0 s: radix 16 over j, twiddle W_N^(n_lo k0)
+    fft_pass<16, C::T, C::T, INV>(v, p + C::R0 * s, tw.g[0]);
+    group_transpose(v, buf + 272 * p, s);
+    // thread (p, k0), register s: radix 16 over s, twiddle W_T^(p k1)
+    fft_pass<16, C::R0, C::T, INV>(v, p, tw.g[1]);
+    XchgSplit xc;
+    xc.buf = buf;
+    xc.exchange(v, [&](int j) { return tau + C::T * j; },
+                [&](int j) {
+                    const int m = tau + C::T * (j % U);          // k0 + 16 k1 of the output this register feeds
+                    return 16 * (j / U) + (m & 15) + 16 * C::R0 * (m >> 4);
+                });
+    fft_pass<C::R0, 1, C::T, INV>(v, tau, nullptr);
 }
 
 }  // namespace mlv

@@ -1059,4 +1059,139 @@ k_z_advect(const ZAdvArgs a) {
     }
 }
 
+// ---- persistent form with grouped transforms (line lengths 512 .. 4096: three passes).
+// Same arithmetic as k_z_advect; differences:
+//  * the three inverse transforms leave their result in grouped order and the two forward
+//    transforms start from it (mlv_fft.cuh: fft_nat2grp / fft_grp2nat): one CTA-wide exchange per
+//    transform instead of two, the other one is a 16x16 transpose inside half a warp;
+//  * a CTA walks over row pairs (grid = resident CTAs), keeps the CFL / energy partials in
+//    registers and reduces them once, and announces the rows of its next pair to the L2 while it
+//    works on the current one.
+template <int LOG2N, int LPC>
+__global__ void __launch_bounds__(LPC * FftCfg<LOG2N>::T, (LPC * FftCfg<LOG2N>::T <= 256) ? 2 : 1)
+k_z_advect_grouped(const ZAdvArgs a) {
+    typedef FftCfg<LOG2N> F;
+    constexpr int NT = LPC * F::T;
+    const int l = threadIdx.x / F::T, tau = threadIdx.x % F::T;
+    unsigned char* base = MLV_SMEM_BASE();
+    double* const xbuf = reinterpret_cast<double*>(base) + (size_t)l * F::XSLOTS;
+    cplx* stash = reinterpret_cast<cplx*>(base + (size_t)LPC * F::XSLOTS * sizeof(double)) +
+                  (size_t)l * F::N + tau;
+    double* rbuf = reinterpret_cast<double*>(base + (size_t)LPC * F::XSLOTS * sizeof(double) +
+                                             (size_t)LPC * F::N * sizeof(cplx));
+    const int cts = log2_pow2(a.ct);                 // tile width is a power of two
+    const bool sharded = a.sh.fwd_chunk != 0;
+    const int npairs = a.nrows / 2;
+    const int stride = (int)gridDim.x * LPC;
+    wait_arrivals(a.wait_counter, a.wait_expect);
+
+    double acc_mx[2] = {-INFINITY, -INFINITY}, acc_ss[2] = {0.0, 0.0};
+    for (int rp0 = (int)blockIdx.x * LPC; rp0 < npairs; rp0 += stride) {     // uniform trip count per CTA
+        const int rplocal = rp0 + l;
+        const bool valid = rplocal < npairs;
+        const int rp = a.row0 / 2 + (valid ? rplocal : 0);   // clamp: loads stay unpredicated
+        const size_t rowoff = (size_t)(2 * rp) * a.ipitch;
+        // announce the velocity rows of this pair (needed one and two transforms from now) and the
+        // scalar rows of the pair this line works on next
+        if (tau < 6 && a.sh.nml >= a.nm) {           // rows are contiguous only when unsharded
+            const unsigned rowbytes = (unsigned)a.nm * (unsigned)sizeof(cplx);
+            if (tau < 4) {
+                l2_prefetch_bulk((tau < 2 ? a.Iux : a.Iuz) + rowoff + (size_t)(tau & 1) * a.ipitch, rowbytes);
+            } else if (rplocal + stride < npairs) {
+                l2_prefetch_bulk(a.Iq + (size_t)(2 * (rp + stride) + (tau & 1)) * a.ipitch, rowbytes);
+            }
+        }
+        cplx v[16];
+        {   // q -> physical (grouped order), parked in the thread-private stash
+            const cplx* rowA = a.Iq + rowoff;
+            zpair_load_line<LOG2N>(v, rowA, rowA + a.ipitch, tau, a.nm, a.sh);
+            fft_nat2grp<LOG2N, true>(v, tau, a.tw, xbuf);
+            MLV_UNROLL
+            for (int j = 0; j < 16; ++j) stash[j * F::T] = v[j];
+        }
+        for (int pass = 0; pass < 2; ++pass) {        // pass 0: A = ux q, pass 1: B = uz q
+            MLV_SCHED_FENCE();
+            {
+                const cplx* src = (pass == 0 ? a.Iux : a.Iuz) + rowoff;
+                zpair_load_line<LOG2N>(v, src, src + a.ipitch, tau, a.nm, a.sh);
+            }
+            MLV_SCHED_FENCE();
+            fft_nat2grp<LOG2N, true>(v, tau, a.tw, xbuf);
+            {
+                double mx = -INFINITY, ss = 0.0;
+                MLV_UNROLL
+                for (int j = 0; j < 16; ++j) {
+                    mx = fmax(mx, fmax(v[j].x, v[j].y));
+                    ss += v[j].x * v[j].x + v[j].y * v[j].y;
+                    const cplx q = stash[j * F::T];
+                    v[j] = mk(v[j].x * q.x, v[j].y * q.y);
+                }
+                if (valid) {
+                    acc_mx[pass] = fmax(acc_mx[pass], mx);
+                    acc_ss[pass] += ss;
+                }
+            }
+            fft_grp2nat<LOG2N, false>(v, tau, a.tw, xbuf);
+            cplx* pbuf = reinterpret_cast<cplx*>(xbuf);
+            __syncthreads();
+            zpair_publish<LOG2N>(v, tau, a.nm, pbuf);
+            __syncthreads();
+            if (valid) {
+                const size_t foff = (size_t)a.outoff[pass];
+                MLV_UNROLL
+                for (int j0 = 0; j0 < 6; j0 += 3) {            // retained low modes: j <= 5
+                    cplx P[3];
+                    MLV_UNROLL
+                    for (int u = 0; u < 3; ++u) {              // partner values: unconditional reads
+                        const int kk = tau + F::T * (j0 + u);
+                        P[u] = pbuf[kk < a.nm ? kk : 0];
+                    }
+                    MLV_UNROLL
+                    for (int u = 0; u < 3; ++u) {
+                        const int j = j0 + u;
+                        const int kk = tau + F::T * j;
+                        if (kk < a.nm) {
+                            cplx A, B;
+                            zpair_unpack(v[j], (kk == 0) ? v[j] : P[u], A, B);
+                            const int t = kk >> cts;
+                            int h = 0, tl = t;                                       // tile owner
+                            if (sharded) { h = t / a.sh.tpr; tl = t - h * a.sh.tpr; }
+                            cplx* o = a.out.blk[h] + foff + fwd_store_off(2 * rp, tl, kk & (a.ct - 1), a.ct, a.sh);
+                            o[0] = A;
+                            o[a.ct] = B;                               // row 2rp+1
+                        }
+                    }
+                }
+            }
+        }
+    }
+    // ---- reductions: per-CTA partials (deterministic two-stage reduction).  fmax drops NaNs,
+    // the sum of squares does not: a NaN anywhere makes the maximum NaN too, as numpy.max does
+    // (Integrator.py:41 tests np.isnan(cfl_dt))
+    __syncthreads();
+    MLV_UNROLL
+    for (int pass = 0; pass < 2; ++pass) {
+        rbuf[pass * NT + threadIdx.x] = acc_ss[pass] != acc_ss[pass] ? NAN : acc_mx[pass];
+        rbuf[(2 + pass) * NT + threadIdx.x] = acc_ss[pass];
+    }
+    __syncthreads();
+    {
+        constexpr int G = NT / 4 > 0 ? NT / 4 : 1;          // threads per quantity
+        const int w = threadIdx.x / G, g = threadIdx.x % G;
+        if (w < 4) {
+            double r = rbuf[w * NT + g];
+            for (int i = g + G; i < NT; i += G) r = (w < 2) ? nan_max(r, rbuf[w * NT + i]) : r + rbuf[w * NT + i];
+            rbuf[w * NT + g] = r;
+        }
+        for (int s2 = G / 2; s2 > 0; s2 >>= 1) {
+            __syncthreads();
+            if (w < 4 && g < s2) {
+                const double x = rbuf[w * NT + g], y = rbuf[w * NT + g + s2];
+                rbuf[w * NT + g] = (w < 2) ? nan_max(x, y) : x + y;
+            }
+        }
+        if (w < 4 && g == 0) a.red[(size_t)blockIdx.x * 4 + w] = rbuf[w * NT];
+    }
+}
+
 }  // namespace mlv

@@ -14,6 +14,12 @@ namespace mlv {
 void set_error(const char* fmt, ...);
 extern unsigned long long g_launches;
 
+// development switches (kernel variants kept for A/B measurements): set = non-empty and not "0"
+inline bool rt_env_flag(const char* name) {
+    const char* v = getenv(name);
+    return v && *v && !(v[0] == '0' && v[1] == 0);
+}
+
 #ifdef MLV_EMU
 typedef void* stream_t;
 void emu_launch(unsigned grid, unsigned block, size_t smem, const std::function<void()>& body);

@@ -26,8 +26,9 @@ EXPORTS = [
     "mlv_z_inverse", "mlv_z_forward", "mlv_x_forward", "mlv_advect_z", "mlv_advect_z_rows", "mlv_set_reduction_partials", "mlv_reduce_partials", "mlv_advect_phys",
     "mlv_spec_lincomb", "mlv_lap_array", "mlv_stencil", "mlv_solve_fdm", "mlv_fdm_velocity",
     "mlv_fdm_advect", "mlv_integrate",
-    "mlv_elementwise", "mlv_reduce",
+    "mlv_elementwise", "mlv_reduce", "mlv_trig_axis",
 ]
+EXT_PERIODIC, EXT_EVEN, EXT_ODD = range(3)
 
 
 class MlvError(RuntimeError):
@@ -76,6 +77,17 @@ class Ew(C.Structure):
                 ("out", View), ("a", View), ("b", View),
                 ("a_re", C.c_double), ("a_im", C.c_double),
                 ("b_re", C.c_double), ("b_im", C.c_double)]
+
+
+class Trig(C.Structure):
+    _fields_ = [("inverse", C.c_int32), ("ext", C.c_int32), ("period", C.c_int32),
+                ("n_samp", C.c_int32), ("n_modes", C.c_int32), ("two_sided", C.c_int32),
+                ("hermitian", C.c_int32), ("samp_complex", C.c_int32), ("batch_fastest", C.c_int32),
+                ("nbatch", C.c_int32),
+                ("samp_stride", C.c_int64), ("samp_batch_stride", C.c_int64),
+                ("mode_stride", C.c_int64), ("mode_batch_stride", C.c_int64),
+                ("in_", C.c_void_p), ("out", C.c_void_p),
+                ("scale_re", C.c_double), ("scale_im", C.c_double), ("w0", C.c_double)]
 
 
 def make_lin_terms(terms):
@@ -132,6 +144,7 @@ def declare(lib):
         "mlv_integrate": [vp, C.POINTER(LinTerms), C.POINTER(Integ)],
         "mlv_elementwise": [vp, C.POINTER(Ew)],
         "mlv_reduce": [vp, i32, i32, i32, C.POINTER(View), C.POINTER(View), vp],
+        "mlv_trig_axis": [vp, C.POINTER(Trig)],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)

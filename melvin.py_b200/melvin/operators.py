@@ -15,6 +15,8 @@ from .basis import BasisFunctions
 
 _CE = BasisFunctions.COMPLEX_EXP
 _FDM = BasisFunctions.FDM
+_COS = BasisFunctions.COSINE
+_SIN = BasisFunctions.SINE
 
 
 def _require_device_namespace(xp):
@@ -113,9 +115,94 @@ class SpectralTransformer:
 
     @staticmethod
     def _only_fourier(basis_functions):
-        if not (basis_functions[0] is _CE and basis_functions[1] is _CE):
-            raise NotImplementedError(
-                "COSINE/SINE bases are not implemented on the B200 backend yet (SURVEY 8f-2)")
+        """True for the all-Fourier pair (the register-transform kernels); COSINE / SINE axes go
+        through mlv_trig_axis."""
+        for b in basis_functions:
+            if b not in (_CE, _COS, _SIN):
+                raise NotImplementedError("fully spectral transforms take COMPLEX_EXP, COSINE or SINE bases")
+        return basis_functions[0] is _CE and basis_functions[1] is _CE
+
+    # -- COSINE / SINE axes (SpectralTransformer.py:108-125,134-146,169-196): the reference mirrors
+    #    the field to period 2(n-1) and calls rfft2 / irfft2; mlv_trig_axis evaluates the retained
+    #    modes (or the n samples) of that transform directly, one axis per call, in rfft2's order
+    def _trig_axes(self, basis_functions):
+        p = self._p
+        ax = []
+        for b, n in ((basis_functions[0], p.nx), (basis_functions[1], p.nz)):
+            if b is _CE:
+                ax.append((_capi.EXT_PERIODIC, n, complex(n), 1.0))
+            elif b is _COS:
+                ax.append((_capi.EXT_EVEN, 2 * (n - 1), complex(n - 1), 0.5))
+            else:
+                ax.append((_capi.EXT_ODD, 2 * (n - 1), -1j * (n - 1), 1.0))
+        return ax                     # per axis: (extension, period, factor, forward weight of mode 0)
+
+    def _trig_check(self):
+        if self._ctx.world > 1:
+            raise NotImplementedError("COSINE / SINE bases are not slab-decomposed")
+
+    def _to_spectral_trig(self, in_arr, out, basis_functions):
+        self._trig_check()
+        p, ctx = self._p, self._ctx
+        if out is None:
+            out = self._array_factory.make_spectral()
+        src = _contig(_dev(in_arr, np.float64))
+        if src.is_complex() or tuple(src.shape) != (p.nx, p.nz):
+            raise TypeError("to_spectral expects a real (nx, nz) physical array")
+        if not isinstance(out, DeviceArray) or not out._touch()._t.is_contiguous() \
+                or tuple(out.shape) != tuple(p.spectral_shape):
+            raise TypeError("out must be a contiguous spectral-shaped device array")
+        out._pre_write()
+        (ex, mx, fx, wx), (ez, mz, fz, wz) = self._trig_axes(basis_functions)
+        nm, rows = p.nm, 2 * p.nn + 1
+        tmp = _backend.empty((p.nx, nm), np.complex128)
+        d = _capi.Trig()                     # z axis: rows of the physical field -> one-sided modes
+        d.inverse, d.ext, d.period, d.n_samp, d.n_modes = 0, ez, mz, p.nz, nm
+        d.two_sided, d.hermitian, d.samp_complex, d.batch_fastest, d.nbatch = 0, 0, 0, 0, p.nx
+        d.samp_stride, d.samp_batch_stride, d.mode_stride, d.mode_batch_stride = 1, p.nz, 1, nm
+        d.in_, d.out, d.scale_re, d.scale_im, d.w0 = src.data_ptr(), tmp.data_ptr(), 1.0, 0.0, wz
+        ctx.call("mlv_trig_axis", ctypes.byref(d))
+        scale = 1.0 / (fx * fz)              # SpectralTransformer.py:191
+        d = _capi.Trig()                     # x axis: columns -> modes 0..nn,-nn..-1
+        d.inverse, d.ext, d.period, d.n_samp, d.n_modes = 0, ex, mx, p.nx, rows
+        d.two_sided, d.hermitian, d.samp_complex, d.batch_fastest, d.nbatch = 1, 0, 1, 1, nm
+        d.samp_stride, d.samp_batch_stride, d.mode_stride, d.mode_batch_stride = nm, 1, nm, 1
+        d.in_, d.out, d.scale_re, d.scale_im, d.w0 = tmp.data_ptr(), out._t.data_ptr(), scale.real, scale.imag, wx
+        ctx.call("mlv_trig_axis", ctypes.byref(d))
+        return out
+
+    def _to_physical_trig(self, in_arr, out, basis_functions):
+        """The reference doubles the mean mode of a cosine axis inside the caller's array
+        (SpectralTransformer.py:123-126, so a second call sees doubled data); here the weight is
+        applied on the fly and `in_arr` is left untouched."""
+        self._trig_check()
+        p, ctx = self._p, self._ctx
+        if out is None:
+            out = self._array_factory.make_physical()
+        src = _contig(_dev(in_arr, np.complex128))
+        if tuple(src.shape) != tuple(p.spectral_shape):
+            raise TypeError("to_physical expects a spectral-shaped array")
+        dst = out._t if isinstance(out, DeviceArray) else None
+        if dst is None or not dst.is_contiguous() or dst.is_complex() or tuple(dst.shape) != (p.nx, p.nz):
+            raise TypeError("out must be a contiguous real (nx, nz) device array")
+        out._pre_write()
+        (ex, mx, fx, wx), (ez, mz, fz, wz) = self._trig_axes(basis_functions)
+        nm, rows = p.nm, 2 * p.nn + 1
+        tmp = _backend.empty((p.nx, nm), np.complex128)
+        scale = fx * fz / (mx * mz)          # :131 and the 1/(Mx Mz) of irfft2
+        d = _capi.Trig()                     # x axis: modes -> the first nx samples of the period
+        d.inverse, d.ext, d.period, d.n_samp, d.n_modes = 1, ex, mx, p.nx, rows
+        d.two_sided, d.hermitian, d.samp_complex, d.batch_fastest, d.nbatch = 1, 0, 1, 1, nm
+        d.samp_stride, d.samp_batch_stride, d.mode_stride, d.mode_batch_stride = nm, 1, nm, 1
+        d.in_, d.out, d.scale_re, d.scale_im, d.w0 = src.data_ptr(), tmp.data_ptr(), scale.real, scale.imag, 1.0 / wx
+        ctx.call("mlv_trig_axis", ctypes.byref(d))
+        d = _capi.Trig()                     # z axis: one-sided modes -> real samples (irfft)
+        d.inverse, d.ext, d.period, d.n_samp, d.n_modes = 1, ez, mz, p.nz, nm
+        d.two_sided, d.hermitian, d.samp_complex, d.batch_fastest, d.nbatch = 0, 1, 0, 0, p.nx
+        d.samp_stride, d.samp_batch_stride, d.mode_stride, d.mode_batch_stride = 1, p.nz, 1, nm
+        d.in_, d.out, d.scale_re, d.scale_im, d.w0 = tmp.data_ptr(), dst.data_ptr(), 1.0, 0.0, 1.0 / wz
+        ctx.call("mlv_trig_axis", ctypes.byref(d))
+        return out
 
     @staticmethod
     def _fdm_axis(basis_functions):
@@ -126,7 +213,8 @@ class SpectralTransformer:
 
     def __to_physical_2d(self, in_arr, out=None, basis_functions=_DEFAULT):
         """SpectralTransformer.py:90-150"""
-        self._only_fourier(basis_functions)
+        if not self._only_fourier(basis_functions):
+            return self._to_physical_trig(in_arr, out, basis_functions)
         if out is None:
             out = self._array_factory.make_physical()
         ctx = self._ctx
@@ -167,7 +255,8 @@ class SpectralTransformer:
 
     def __to_spectral_2d(self, in_arr, out=None, basis_functions=_DEFAULT):
         """SpectralTransformer.py:152-199"""
-        self._only_fourier(basis_functions)
+        if not self._only_fourier(basis_functions):
+            return self._to_spectral_trig(in_arr, out, basis_functions)
         if out is None:
             out = self._array_factory.make_spectral()
         ctx = self._ctx
@@ -246,7 +335,12 @@ class SpatialDifferentiator:
         if basis_fn is _FDM:
             return 0.0 * _dev(var)          # diff factor of FDM is 0 (BasisFunctions.py:26-36)
         if basis_fn is not _CE:
-            raise NotImplementedError("COSINE/SINE bases are not implemented on the B200 backend yet")
+            # diff factors of the trigonometric bases (BasisFunctions.py:26-48): -pi/L (COSINE),
+            # +pi/L (SINE), second derivative -pi^2/L^2 -- exact multiples (powers of two, times
+            # +-i) of the Fourier symbols i 2pi/L and -(2pi/L)^2 the kernels evaluate
+            first = op in (_capi.OP_DDX, _capi.OP_DDZ)
+            c = (0.5j if basis_fn is _COS else -0.5j) if first else 0.25
+            return c * self._term(var, _CE, op)
         if isinstance(var, SpecExpr) and not var.nls and len(var.terms) == 1 \
                 and var.terms[0][1] == _capi.OP_IDENT:
             c, _, a = var.terms[0]

@@ -129,6 +129,80 @@ def to_spectral(g: Grid, phys: np.ndarray) -> np.ndarray:
     return out
 
 
+# COSINE / SINE bases.  Basis codes as in melvin/BasisFunctions.py:5-9.
+COMPLEX_EXP, COSINE, SINE = 0, 1, 2
+
+
+def to_spectral_basis(g: Grid, phys: np.ndarray, bx: int, bz: int) -> np.ndarray:
+    """Physical -> truncated spectral for any pair of spectral bases
+    (melvin/SpectralTransformer.py:152-199): even / odd mirror image, rfft2, scaling,
+    halved mean mode of a cosine axis, 2/3-rule truncation (_scale_2d :21-24)."""
+    arr = np.asarray(phys)
+    xf, zf = g.nx, g.nz
+    if bx == COSINE:
+        arr = np.concatenate((arr[:-1], arr[:0:-1]))                   # :169-172
+        xf = g.nx - 1
+    elif bx == SINE:
+        arr = np.concatenate((arr[:-1], -arr[:0:-1]))                  # :174-178
+        xf = -1j * (g.nx - 1)
+    if bz == COSINE:
+        arr = np.concatenate((arr[:, :-1], arr[:, :0:-1]), axis=1)     # :180-184
+        zf = g.nz - 1
+    elif bz == SINE:
+        arr = np.concatenate((arr[:, :-1], -arr[:, :0:-1]), axis=1)    # :185-189
+        zf = -1j * (g.nz - 1)
+    full = np.fft.rfft2(arr) / (xf * zf)                               # :191
+    if bx == COSINE:
+        full[0] /= 2                                                   # :193-194
+    if bz == COSINE:
+        full[:, 0] /= 2                                                # :195-196
+    out = np.zeros(g.spectral_shape, dtype=np.complex128)
+    out[: g.nn + 1, : g.nm] = full[: g.nn + 1, : g.nm]
+    out[-g.nn:, : g.nm] = full[-g.nn:, : g.nm]
+    return out
+
+
+def to_physical_basis(g: Grid, spec: np.ndarray, bx: int, bz: int) -> np.ndarray:
+    """Spectral -> physical for any pair of spectral bases (melvin/SpectralTransformer.py:90-150).
+    The reference doubles the mean mode of a cosine axis IN the caller's array (:123-126); this
+    restatement works on a copy (same output, no side effect)."""
+    spec = np.array(spec, dtype=np.complex128, copy=True)
+    xf, zf = g.nx, g.nz
+    size = [g.nx, g.nz // 2 + 1]
+    if bx == COSINE:
+        size[0], xf = 2 * (g.nx - 1), g.nx - 1                         # :108-110
+    elif bx == SINE:
+        size[0], xf = 2 * (g.nx - 1), -1j * (g.nx - 1)                 # :111-113
+    if bz == COSINE:
+        size[1], zf = 2 * (g.nz - 1) // 2 + 1, g.nz - 1                # :115-117
+    elif bz == SINE:
+        size[1], zf = 2 * (g.nz - 1) // 2 + 1, -1j * (g.nz - 1)        # :118-120
+    if bx == COSINE:
+        spec[0] *= 2
+    if bz == COSINE:
+        spec[:, 0] *= 2
+    padded = np.zeros(size, dtype=np.complex128)
+    padded[: g.nn + 1, : g.nm] = spec[: g.nn + 1, : g.nm]
+    padded[-g.nn:, : g.nm] = spec[-g.nn:, : g.nm]
+    padded *= xf * zf                                                  # :131
+    out = np.fft.irfft2(padded)                                        # :132
+    if bx in (COSINE, SINE):
+        out = out[: g.nx]                                              # :134-138
+    if bz in (COSINE, SINE):
+        out = out[:, : g.nz]                                           # :140-146
+    return out
+
+
+def diff_factor(basis: int, length: float):
+    """melvin/BasisFunctions.py:26-48"""
+    return {COMPLEX_EXP: 1j * 2 * np.pi, SINE: np.pi, COSINE: -np.pi}[basis] / length
+
+
+def diff2_factor(basis: int, length: float):
+    """melvin/BasisFunctions.py:39-42,57-61"""
+    return -np.abs({COMPLEX_EXP: 1j * 2 * np.pi, SINE: np.pi, COSINE: -np.pi}[basis]) ** 2 / length ** 2
+
+
 # --------------------------------------------------------------------------
 # spectral derivative symbols  (melvin/SpatialDifferentiator.py:50-74,
 #                               melvin/BasisFunctions.py:26-59)

@@ -39,7 +39,7 @@ void trampoline() {
 
 // ---- barriers: counting, generation based (bar.sync / bar.arrive semantics)
 namespace {
-constexpr int kMaxBar = 16;
+constexpr int kMaxBar = 64;     // 0..15 named barriers, 16.. one per warp (warp_sync)
 int g_bar_cnt[kMaxBar];
 unsigned g_bar_gen[kMaxBar];
 void yield_fiber() { swapcontext(&g_fibers[g_cur].ctx, &g_sched); }

@@ -40,6 +40,17 @@ def test_fused_advection_step(nx, nz, order):
     ac.case_fused_advection_step(H, nx, nz, order)
 
 
+@pytest.mark.parametrize("nx,nz,grid", [(64, 512, 3), (32, 2048, 5), (16, 4096, 0), (16, 4096, 3)])
+def test_fused_advection_persistent_grouped(nx, nz, grid, monkeypatch):
+    """three-pass line lengths: persistent CTAs over several row pairs (grid forced small) with
+    grouped-order transforms, incl. a trip count that leaves lines of the last trip idle"""
+    if grid:
+        monkeypatch.setenv("MLV_ZADV_GRID", str(grid))
+    ac.case_fused_advection_step(H, nx, nz, 2)
+    monkeypatch.setenv("MLV_ZADV_CLASSIC", "1")
+    ac.case_fused_advection_step(H, nx, nz, 2)
+
+
 @pytest.mark.parametrize("order", [2, 4])
 @pytest.mark.parametrize("nx,nz,bits", ac.SIZES_SPLIT)
 def test_split_lines(nx, nz, bits, order):

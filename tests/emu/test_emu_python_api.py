@@ -271,3 +271,8 @@ def test_predictor_corrector_converges_at_its_order(order):
     rates = [np.log2(res[i][1] / res[i + 1][1]) for i in range(len(res) - 1)]
     assert all(r > order - 0.35 for r in rates), (res, rates)
     assert res[-1][1] < (1e-4 if order == 2 else 1e-8)
+
+
+def test_cosine_and_sine_bases():
+    import host_cases as hc
+    hc.trig_bases()

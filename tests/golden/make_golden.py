@@ -18,7 +18,7 @@ from functools import partial
 
 import numpy as np
 
-REF = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
+REF = next((a for a in sys.argv[1:] if not a.startswith("--")), "/root/reference")
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.dont_write_bytecode = True
 sys.path.insert(0, REF)
@@ -444,9 +444,45 @@ def loop_rbc(nx, nz, order, int_order, nsteps, snaps):
          int_order=int_order, nsteps=nsteps, **out)
 
 
+def ops_trig_bases(nx, nz, lx, lz):
+    """COSINE / SINE bases (SpectralTransformer.py:90-199, SpatialDifferentiator.py:50-74):
+    every pair of spectral bases except the all-Fourier one, on random data."""
+    out = {}
+    rng = np.random.default_rng(4321)
+    p = Parameters(base_params(nx, nz, lx, lz), validate=False)
+    af = ArrayFactory(p, np)
+    st = SpectralTransformer(p, np, af)
+    sd = SpatialDifferentiator(p, np, af)
+    phys = rng.standard_normal((nx, nz))
+    spec_in = (rng.standard_normal(p.spectral_shape) + 1j * rng.standard_normal(p.spectral_shape))
+    out["phys_in"], out["spec_in"] = phys, spec_in
+    for bx in (BasisFunctions.COMPLEX_EXP, BasisFunctions.COSINE, BasisFunctions.SINE):
+        for bz in (BasisFunctions.COMPLEX_EXP, BasisFunctions.COSINE, BasisFunctions.SINE):
+            if bx is CE and bz is CE:
+                continue
+            tag = f"b{int(bx)}{int(bz)}"
+            spec = st.to_spectral(phys.copy(), basis_functions=[bx, bz])
+            out[f"{tag}_to_spectral"] = spec.copy()
+            # to_physical doubles the mean mode of a cosine axis inside its argument (:123-126):
+            # hand it copies, store what it returns
+            out[f"{tag}_roundtrip"] = st.to_physical(spec.copy(), basis_functions=[bx, bz]).copy()
+            out[f"{tag}_to_physical"] = st.to_physical(spec_in.copy(), basis_functions=[bx, bz]).copy()
+            out[f"{tag}_lap"] = np.asarray(sd.calc_lap([bx, bz]), dtype=np.float64)
+    for b in (BasisFunctions.COSINE, BasisFunctions.SINE):
+        out[f"sddx_b{int(b)}"] = sd.sddx(spec_in, b)
+        out[f"sddz_b{int(b)}"] = sd.sddz(spec_in, b)
+        out[f"sd2dx2_b{int(b)}"] = sd.sd2dx2(spec_in, b)
+        out[f"sd2dz2_b{int(b)}"] = sd.sd2dz2(spec_in, b)
+    save(f"ops_trig_{nx}x{nz}.npz", lx=lx, lz=lz, **out)
+
+
 def main():
+    if "--only-trig" in sys.argv:
+        ops_trig_bases(64, 32, 1.5, 1.0)
+        return
     with tempfile.TemporaryDirectory() as scratch:
         os.chdir(scratch)   # params.json / tracker files land here
+        ops_trig_bases(64, 32, 1.5, 1.0)
         ops_fully_spectral(64, 32, 1.5, 1.0)
         ops_fdm(64, 32, 2.44, 1.0)
         integrator_vectors(32, 32)

@@ -137,3 +137,82 @@ def predictor_corrector_convergence(order):
         want = q0_s * np.exp(lam * T)
         res.append((dt, float(np.linalg.norm(got - want) / np.linalg.norm(want))))
     return res
+
+
+def trig_bases(tol=1e-12):
+    """COSINE / SINE bases: every basis pair against vectors of the unmodified
+    reference (tests/golden/ops_trig_64x32.npz) and the oracle restatement, the spectral
+    derivative factors, and the reference's analytic known-answer tests
+    (test/SpectralTransformer_test.py:64-310, restated for this grid)."""
+    import os
+    from melvin import ArrayFactory, BasisFunctions, Parameters, SpatialDifferentiator, SpectralTransformer
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ops_trig_64x32.npz"))
+    nx, nz = g["phys_in"].shape
+    p = Parameters({"nx": nx, "nz": nz, "lx": float(g["lx"]), "lz": float(g["lz"]), "final_time": 1.0},
+                   validate=False)
+    G = mo.Grid(nx, nz, p.lx, p.lz)
+    af = ArrayFactory(p, xp)
+    st = SpectralTransformer(p, xp, af)
+    sd = SpatialDifferentiator(p, xp, af)
+    B = BasisFunctions
+    worst = 0.0
+    for bx in (B.COMPLEX_EXP, B.COSINE, B.SINE):
+        for bz in (B.COMPLEX_EXP, B.COSINE, B.SINE):
+            if bx is B.COMPLEX_EXP and bz is B.COMPLEX_EXP:
+                continue
+            tag = f"b{int(bx)}{int(bz)}"
+            spec = st.to_spectral(xp.array(g["phys_in"]), basis_functions=[bx, bz])
+            e = [mo.relative_l2(spec.get(), g[f"{tag}_to_spectral"]),
+                 mo.relative_l2(spec.get(), mo.to_spectral_basis(G, g["phys_in"], int(bx), int(bz)))]
+            held = xp.array(g["spec_in"])
+            phys = st.to_physical(held, af.make_physical(), basis_functions=[bx, bz])
+            e.append(mo.relative_l2(phys.get(), g[f"{tag}_to_physical"]))
+            assert np.array_equal(held.get(), g["spec_in"])          # the argument is left untouched
+            back = st.to_physical(spec, basis_functions=[bx, bz])
+            e.append(mo.relative_l2(back.get(), g[f"{tag}_roundtrip"]))
+            e.append(mo.relative_l2(np.asarray(sd.calc_lap([bx, bz])), g[f"{tag}_lap"]))
+            assert max(e) < tol, (tag, e)
+            worst = max(worst, max(e))
+    sin_ = xp.array(g["spec_in"])
+    for b in (B.COSINE, B.SINE):
+        for name, fn in (("sddx", sd.sddx), ("sddz", sd.sddz), ("sd2dx2", sd.sd2dx2), ("sd2dz2", sd.sd2dz2)):
+            got = fn(sin_, b)
+            got = got.materialize().get() if hasattr(got, "materialize") else np.asarray(got)
+            assert mo.relative_l2(got, g[f"{name}_b{int(b)}"]) < 1e-14, (name, int(b))
+    # analytic known answers (reference test/SpectralTransformer_test.py)
+    xe, ze = np.linspace(0, 1.0, nx), np.linspace(0, 1.0, nz)                    # end points included
+    xo, zo = np.linspace(0, 1.0, nx, endpoint=False), np.linspace(0, 1.0, nz, endpoint=False)
+
+    def check(bases, X, Z, fn, entries):
+        Xg, Zg = np.meshgrid(X, Z, indexing="ij")
+        true_physical = fn(Xg, Zg)
+        spectral, physical = af.make_spectral(), af.make_physical()
+        st.to_spectral(xp.array(true_physical), spectral, basis_functions=bases)
+        true_spectral = np.zeros(spectral.shape, complex)
+        for idx, val in entries.items():
+            true_spectral[idx] = val
+        np.testing.assert_array_almost_equal(spectral.get(), true_spectral)
+        st.to_physical(spectral, physical, basis_functions=bases)
+        np.testing.assert_array_almost_equal(physical.get(), true_physical)
+
+    pi = np.pi
+    check([B.COSINE, B.COMPLEX_EXP], xe, zo, lambda X, Z: np.cos(pi * X) + 2.0 * np.cos(2 * pi * X),
+          {(1, 0): 1.0, (2, 0): 2.0, (-1, 0): 1.0, (-2, 0): 2.0})                         # :64-92
+    check([B.COMPLEX_EXP, B.COSINE], xo, ze, lambda X, Z: np.cos(pi * Z) + 2.0 * np.cos(2 * pi * Z),
+          {(0, 1): 1.0, (0, 2): 2.0})                                                     # :95-121
+    check([B.COSINE, B.COSINE], xe, ze,
+          lambda X, Z: np.cos(pi * Z) + 2.0 * np.cos(2 * pi * Z) + np.cos(pi * X)
+          + 2.0 * np.cos(2 * pi * X) * np.cos(pi * Z),
+          {(0, 1): 1.0, (0, 2): 2.0, (1, 0): 1.0, (2, 1): 2.0, (-1, 0): 1.0, (-2, 1): 2.0})   # :124-160
+    check([B.SINE, B.SINE], xe, ze,
+          lambda X, Z: np.sin(pi * Z) * np.sin(pi * X) + 2.0 * np.sin(2 * pi * Z) * np.sin(3 * pi * X),
+          {(1, 1): 1.0, (-1, 1): -1.0, (3, 2): 2.0, (-3, 2): -2.0})                       # :162-186
+    check([B.SINE, B.COMPLEX_EXP], xe, zo, lambda X, Z: np.sin(pi * X) + 2.0 * np.sin(2 * pi * X),
+          {(1, 0): 1.0, (-1, 0): -1.0, (2, 0): 2.0, (-2, 0): -2.0})                       # :188-210
+    check([B.SINE, B.COSINE], xe, ze, lambda X, Z: np.sin(pi * X) + 2.0 * np.sin(2 * pi * X),
+          {(1, 0): 1.0, (-1, 0): -1.0, (2, 0): 2.0, (-2, 0): -2.0})                       # :212-234
+    check([B.COSINE, B.SINE], xe, ze,
+          lambda X, Z: np.cos(pi * X) * np.sin(pi * Z) + 2.0 * np.cos(3 * pi * X) * np.sin(2 * pi * Z)
+          + 3.0 * np.sin(2 * pi * Z),
+          {(1, 1): 1.0, (-1, 1): 1.0, (0, 2): 3.0, (3, 2): 2.0, (-3, 2): 2.0})            # :236-262
+    return worst

@@ -38,6 +38,18 @@ def test_fused_advection_step(H, nx, nz, order):
     ac.case_fused_advection_step(H, nx, nz, order)
 
 
+@pytest.mark.parametrize("nx,nz,grid", [(64, 512, 3), (32, 2048, 5), (16, 4096, 0), (16, 4096, 3), (1024, 4096, 0),
+                                        (2048, 1024, 0)])
+def test_fused_advection_persistent_grouped(H, nx, nz, grid, monkeypatch):
+    """three-pass line lengths: persistent CTAs (several row pairs per CTA, also forced on small
+    grids) with grouped-order transforms, and the classic one-pair-per-CTA kernel, vs the oracle"""
+    if grid:
+        monkeypatch.setenv("MLV_ZADV_GRID", str(grid))
+    ac.case_fused_advection_step(H, nx, nz, 2)
+    monkeypatch.setenv("MLV_ZADV_CLASSIC", "1")
+    ac.case_fused_advection_step(H, nx, nz, 2)
+
+
 @pytest.mark.parametrize("order", [2, 4])
 @pytest.mark.parametrize("nx,nz,bits", ac.SIZES_SPLIT)
 def test_split_lines_forced(H, nx, nz, bits, order):

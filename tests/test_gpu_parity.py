@@ -496,3 +496,10 @@ def test_streamed_ensemble_with_pinned_host_states():
         assert rel_l2(want, ref) < FIELD_TOL
     finally:
         os.chdir(cwd)
+
+
+def test_cosine_and_sine_bases():
+    """SURVEY 8f-2 on the device: all eight non-Fourier basis pairs vs the unmodified reference's
+    vectors (1e-12), derivative factors, the reference's seven analytic transform tests."""
+    import host_cases as hc
+    assert hc.trig_bases(FIELD_TOL) < FIELD_TOL

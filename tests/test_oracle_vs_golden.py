@@ -251,3 +251,29 @@ def test_loop_rbc(order, ab):
             for nm, arr in zip(("w", "tmp", "psi"), state):
                 assert rel_l2(arr, gl[f"{nm}_step{run.loop}"]) < 1e-10, (nm, run.loop)
     np.testing.assert_allclose(run.ke, gl["ke"], rtol=1e-9)
+
+
+def test_cosine_sine_bases_vs_reference_vectors():
+    """oracle restatement of the mirrored rfft2 / irfft2 (SpectralTransformer.py:90-199) and of the
+    basis diff factors (BasisFunctions.py:26-61) against vectors of the unmodified reference"""
+    g = golden("ops_trig_64x32.npz")
+    G = mo.Grid(64, 32, float(g["lx"]), float(g["lz"]))
+    n, m = mo.mode_numbers(G) if hasattr(mo, "mode_numbers") else (None, None)
+    for bx in range(3):
+        for bz in range(3):
+            if bx == 0 and bz == 0:
+                continue
+            tag = f"b{bx}{bz}"
+            spec = mo.to_spectral_basis(G, g["phys_in"], bx, bz)
+            assert mo.relative_l2(spec, g[f"{tag}_to_spectral"]) < 1e-15
+            assert mo.relative_l2(mo.to_physical_basis(G, g["spec_in"], bx, bz), g[f"{tag}_to_physical"]) < 1e-15
+            assert mo.relative_l2(mo.to_physical_basis(G, spec, bx, bz), g[f"{tag}_roundtrip"]) < 1e-15
+    nn_ = np.concatenate((np.arange(0, G.nn + 1), np.arange(-G.nn, 0)))[:, None]
+    mm_ = np.arange(0, G.nm)[None, :]
+    for b in (1, 2):
+        assert mo.relative_l2(mo.diff_factor(b, G.lx) * nn_ * g["spec_in"], g[f"sddx_b{b}"]) < 1e-15
+        assert mo.relative_l2(mo.diff_factor(b, G.lz) * mm_ * g["spec_in"], g[f"sddz_b{b}"]) < 1e-15
+        assert mo.relative_l2(mo.diff2_factor(b, G.lx) * nn_ ** 2 * g["spec_in"], g[f"sd2dx2_b{b}"]) < 1e-15
+        assert mo.relative_l2(mo.diff2_factor(b, G.lz) * mm_ ** 2 * g["spec_in"], g[f"sd2dz2_b{b}"]) < 1e-15
+        assert mo.relative_l2(mo.diff2_factor(b, G.lx) * nn_ ** 2 + mo.diff2_factor(3 - b, G.lz) * mm_ ** 2,
+                              g[f"b{b}{3 - b}_lap"]) < 1e-15
