@@ -690,7 +690,7 @@ def gpu_arm(args, rank, world):
     blocking_s = time.perf_counter() - t0
 
     from melvin.ensemble import Ensemble
-    n_members = 3
+    n_members = int(os.environ.get("MLV_E2E_MEMBERS", "4"))
     e2e_passes = max(3 * n_members, min(4 * args.steps, 120))
 
     def build_member(i):

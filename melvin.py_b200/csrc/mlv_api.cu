@@ -324,8 +324,44 @@ static int check_integ(const mlv_ctx* c, const mlv_integ* g, const char* fn) {
 }
 
 // ----------------------------------------------------------- launch helpers
+// 4096-point lines, unsharded, tensor maps available: column-serial persistent kernel, two CTAs per SM
+template <int L>
+static int launch_xinv_cols(mlv_ctx* c, XInvArgs& a, bool& done) {
+    typedef FftCfg<L> F;
+    done = false;
+    if constexpr (L == 12) {
+        // measured slower than the two-column kernel (0.215 vs 0.168 ms at 4096^2): 16-byte-wide tensor
+        // boxes move one row per ~3 cycles whatever their width, so a column-at-a-time kernel is
+        // bound by the copy engine (profiles/r02_experiments.md); kept as a selectable variant
+        if (c->nranks != 1 || !rt_tma_enabled() || !rt_env_flag("MLV_XINV_COLS")) return 0;
+        const int rows = 2 * a.nn + 1;
+        const int h = rows < 256 ? rows : 256, nb = (rows + h - 1) / h;
+        const size_t smem = ((size_t)F::N + (size_t)h * nb) * sizeof(cplx) + 16;
+        if (smem > 113 * 1024) return 0;
+        a.load_tma = 1; a.ld_rows = h; a.ld_boxes = nb;
+        a.use_tma = 1; a.tma_rows = 256;
+        for (int f = 0; f < a.nf; ++f) {
+            if (!rt_make_tmap(&a.smap[f], const_cast<cplx*>(a.src[f]), 2ull * a.spitch, (unsigned long long)rows,
+                              16ull * a.spitch, 2u, (unsigned)h)) return 0;
+            if (!rt_make_tmap(&a.tmap[f], a.dst[f], 2ull * a.ipitch, (unsigned long long)F::N,
+                              16ull * a.ipitch, 2u, 256u)) return 0;
+        }
+        unsigned grid = (unsigned)a.nm < 296u ? (unsigned)a.nm : 296u;
+        if (const char* g = getenv("MLV_XINV_GRID")) if (atoi(g) > 0 && (unsigned)atoi(g) < grid) grid = (unsigned)atoi(g);
+        auto kfn = k_xinv_cols<L>;
+        MLV_LAUNCH(kfn, grid, (unsigned)F::T, smem, c->stream, a);
+        done = true;
+    }
+    return 0;
+}
+
 template <int L>
 static int launch_xinv(mlv_ctx* c, XInvArgs& a) {
+    {
+        bool done = false;
+        if (int rc = launch_xinv_cols<L>(c, a, done)) return rc;
+        if (done) return 0;
+    }
     constexpr int C = xcols(L);
     typedef FftCfg<L> F;
     auto kfn = k_xinv<L, C>;
@@ -334,7 +370,6 @@ static int launch_xinv(mlv_ctx* c, XInvArgs& a) {
     const unsigned grid = (unsigned)((a.nm + C - 1) / C);
     a.use_tma = 0;
     a.load_tma = 0; a.ld_rows = rows; a.ld_boxes = 1;
-#ifndef MLV_EMU
     if (rt_tma_enabled()) {
         // source tiles through tensor loads: boxes of ld_rows rows; the stash is rounded up to whole
         // boxes, so pick the largest box height whose padding still fits the shared memory
@@ -352,9 +387,11 @@ static int launch_xinv(mlv_ctx* c, XInvArgs& a) {
             else { a.ld_rows = rows; a.ld_boxes = 1; break; }
         }
     }
-#endif
     a.wave = 148 * (smem > 113 * 1024 ? 1 : 2);
-#ifndef MLV_EMU
+    unsigned launch_grid = grid;
+    // tensor loads on: resident CTAs only, each walks over tiles and requests its next source tile early
+    if (a.load_tma && !rt_env_flag("MLV_XINV_ONESHOT") && grid > (unsigned)a.wave) launch_grid = (unsigned)a.wave;
+    if (a.load_tma) if (const char* g = getenv("MLV_XINV_GRID")) if (atoi(g) > 0 && (unsigned)atoi(g) < launch_grid) launch_grid = (unsigned)atoi(g);
     if (c->nranks == 1 && rt_tma_enabled()) {
         // column tiles leave through tensor stores: one (rows x 2C doubles) box per 256 rows
         a.tma_rows = F::N < 256 ? F::N : 256;
@@ -364,8 +401,7 @@ static int launch_xinv(mlv_ctx* c, XInvArgs& a) {
                               16ull * a.ipitch, 2u * C, (unsigned)a.tma_rows))
                 a.use_tma = 0;
     }
-#endif
-    MLV_LAUNCH(kfn, grid, (unsigned)(C * F::T), smem, c->stream, a);
+    MLV_LAUNCH(kfn, launch_grid, (unsigned)(C * F::T), smem, c->stream, a);
     return 0;
 }
 

@@ -18,6 +18,8 @@
 #include <cstring>
 #define __grid_constant__
 struct alignas(64) CUtensorMap { unsigned long long opaque[16]; };
+// emulated 2-D tensor map of doubles (filled by rt_make_tmap, mlv_rt.h): copies happen at once
+struct EmuTmap { void* base; unsigned long long inner, rows, row_bytes; unsigned box_inner, box_rows; };
 #include <functional>
 #include <vector>
 #define __global__
@@ -39,6 +41,7 @@ extern unsigned char* emu_smem_base;
 void __syncthreads();
 void emu_bar_sync(int id, int count);
 void emu_bar_arrive(int id, int count);
+void emu_yield();
 #define MLV_SMEM_BASE() (emu_smem_base)
 static inline double __ldg(const double* p) { return *p; }
 static inline double2 __ldg(const double2* p) { return *p; }
@@ -167,7 +170,13 @@ MLV_DEV void tma_store_2d(const CUtensorMap* map, const void* smem, int c0, int 
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                  ::"l"((unsigned long long)map), "r"(s), "r"(c0), "r"(c1) : "memory");
 #else
-    (void)map; (void)smem; (void)c0; (void)c1;
+    const EmuTmap* m = reinterpret_cast<const EmuTmap*>(map);     // elements outside the tensor are clipped
+    const size_t w = (unsigned long long)c0 >= m->inner ? 0 :
+                     ((unsigned long long)c0 + m->box_inner <= m->inner ? m->box_inner : (size_t)(m->inner - c0));
+    for (unsigned r = 0; r < m->box_rows; ++r)
+        if ((unsigned long long)c1 + r < m->rows)
+            memcpy((char*)m->base + ((unsigned long long)c1 + r) * m->row_bytes + (size_t)c0 * 8,
+                   (const char*)smem + (size_t)r * m->box_inner * 8, w * 8);
 #endif
 }
 MLV_DEV void tma_commit() {
@@ -190,7 +199,8 @@ MLV_DEV void mbar_init(unsigned long long* bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 #else
-    (void)bar; (void)count;
+    (void)count;
+    *bar = 0;                  // emulation: low 32 bits = bytes still expected, bit 32 = phase parity
 #endif
 }
 MLV_DEV void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
@@ -198,7 +208,7 @@ MLV_DEV void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
     const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
 #else
-    (void)bar; (void)bytes;
+    *bar += bytes;
 #endif
 }
 MLV_DEV void mbar_wait(unsigned long long* bar, unsigned parity) {
@@ -212,9 +222,16 @@ MLV_DEV void mbar_wait(unsigned long long* bar, unsigned parity) {
         "bra MLV_WAIT_%=;\n\t"
         "MLV_DONE_%=:\n\t}" ::"r"(a), "r"(parity) : "memory");
 #else
-    (void)bar; (void)parity;
+    while (((*(volatile unsigned long long*)bar >> 32) & 1ull) == parity) emu_yield();
 #endif
 }
+#ifdef MLV_EMU
+// emulated copies are complete on return: take their bytes off the barrier, flip the phase at 0
+inline void emu_mbar_complete(unsigned long long* bar, unsigned bytes) {
+    *bar -= bytes;
+    if ((*bar & 0xffffffffull) == 0) *bar ^= (1ull << 32);
+}
+#endif
 // contiguous global -> shared (multiple of 16 bytes, 16-byte aligned on both sides)
 MLV_DEV void bulk_load(void* smem, const void* gmem, unsigned bytes, unsigned long long* bar) {
 #ifndef MLV_EMU
@@ -223,7 +240,8 @@ MLV_DEV void bulk_load(void* smem, const void* gmem, unsigned bytes, unsigned lo
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(s), "l"(gmem), "r"(bytes), "r"(b) : "memory");
 #else
-    (void)smem; (void)gmem; (void)bytes; (void)bar;
+    memcpy(smem, gmem, bytes);
+    emu_mbar_complete(bar, bytes);
 #endif
 }
 // one box of a 2-D tensor map, global -> shared
@@ -234,7 +252,16 @@ MLV_DEV void tma_load_2d(void* smem, const CUtensorMap* map, int c0, int c1, uns
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(s), "l"((unsigned long long)map), "r"(b), "r"(c0), "r"(c1) : "memory");
 #else
-    (void)smem; (void)map; (void)c0; (void)c1; (void)bar;
+    const EmuTmap* m = reinterpret_cast<const EmuTmap*>(map);
+    const size_t w = (unsigned long long)c0 >= m->inner ? 0 :
+                     ((unsigned long long)c0 + m->box_inner <= m->inner ? m->box_inner : (size_t)(m->inner - c0));
+    for (unsigned r = 0; r < m->box_rows; ++r) {
+        char* d = (char*)smem + (size_t)r * m->box_inner * 8;
+        memset(d, 0, (size_t)m->box_inner * 8);
+        if ((unsigned long long)c1 + r < m->rows)
+            memcpy(d, (const char*)m->base + ((unsigned long long)c1 + r) * m->row_bytes + (size_t)c0 * 8, w * 8);
+    }
+    emu_mbar_complete(bar, (unsigned)((size_t)m->box_inner * m->box_rows * 8));
 #endif
 }
 

@@ -247,41 +247,71 @@ MLV_DEV void fft_pass(cplx (&v)[16], int tau, const cplx* tw) {
 }
 
 // ------------------------------------------------------ exchange policies
+// Order in which the 16 registers of a thread go through an exchange: 0,4,8,12, 1,5,9,13, ...
+// The radix-16 butterfly starts with radix-4 butterflies over registers {n, n+4, n+8, n+12} and
+// ends with results that land in the same groups, so the first butterflies can start while the
+// other loads are still in flight, and the first stores can leave before the last results exist.
+#ifndef MLV_NO_XORDER
+#define MLV_XORDER(i) ((((i) & 3) << 2) | ((i) >> 2))
+#else
+#define MLV_XORDER(i) (i)
+#endif
+
 // Full complex128 exchange buffer shared by C interleaved lines (x passes):
 // slot L of line c lives at buf[L*C + c].  Two barriers per exchange.
 template <int C>
 struct XchgFull {
+    static constexpr bool SWIZZLE = false;
     cplx* buf;
     int c;
     template <class WI, class RI>
     MLV_DEV void exchange(cplx (&v)[16], WI wi, RI ri) {
         __syncthreads();
         MLV_UNROLL
-        for (int j = 0; j < 16; ++j) buf[wi(j) * C + c] = v[j];
+        for (int i = 0; i < 16; ++i) { const int j = MLV_XORDER(i); buf[wi(j) * C + c] = v[j]; }
         __syncthreads();
         MLV_UNROLL
-        for (int j = 0; j < 16; ++j) v[j] = buf[ri(j) * C + c];
+        for (int i = 0; i < 16; ++i) { const int j = MLV_XORDER(i); v[j] = buf[ri(j) * C + c]; }
     }
 };
 
 // Half-size exchange buffer (N+N/16 doubles per line): real parts, then
 // imaginary parts.  Four barriers per exchange, half the shared memory.
 struct XchgSplit {
+    static constexpr bool SWIZZLE = false;
     double* buf;
     template <class WI, class RI>
     MLV_DEV void exchange(cplx (&v)[16], WI wi, RI ri) {
         __syncthreads();
         MLV_UNROLL
-        for (int j = 0; j < 16; ++j) buf[wi(j)] = v[j].x;
+        for (int i = 0; i < 16; ++i) { const int j = MLV_XORDER(i); buf[wi(j)] = v[j].x; }
         __syncthreads();
         MLV_UNROLL
-        for (int j = 0; j < 16; ++j) v[j].x = buf[ri(j)];
+        for (int i = 0; i < 16; ++i) { const int j = MLV_XORDER(i); v[j].x = buf[ri(j)]; }
         __syncthreads();
         MLV_UNROLL
-        for (int j = 0; j < 16; ++j) buf[wi(j)] = v[j].y;
+        for (int i = 0; i < 16; ++i) { const int j = MLV_XORDER(i); buf[wi(j)] = v[j].y; }
         __syncthreads();
         MLV_UNROLL
-        for (int j = 0; j < 16; ++j) v[j].y = buf[ri(j)];
+        for (int i = 0; i < 16; ++i) { const int j = MLV_XORDER(i); v[j].y = buf[ri(j)]; }
+    }
+};
+
+// One line, full complex128 slots, exactly N of them: the stride-16 gather of the last exchange is
+// made conflict-free by XOR-ing the slot with bits of its own row (L ^ ((L >> 4) & 7)) instead of
+// padding one slot per 16 -- 64 KB for a 4096-point line, which lets two such CTAs (plus a
+// 44 KB column stash each) share an SM.
+struct XchgLineSwz {
+    static constexpr bool SWIZZLE = true;
+    cplx* buf;
+    template <class WI, class RI>
+    MLV_DEV void exchange(cplx (&v)[16], WI wi, RI ri) {
+        __syncthreads();
+        MLV_UNROLL
+        for (int j = 0; j < 16; ++j) buf[wi(j)] = v[j];
+        __syncthreads();
+        MLV_UNROLL
+        for (int j = 0; j < 16; ++j) v[j] = buf[ri(j)];
     }
 };
 
@@ -295,8 +325,11 @@ MLV_DEV void fft_later_passes(cplx (&v)[16], const int tau, const FftTw& tw, X& 
     const int hi = tau / N3;
     xc.exchange(
         v,
-        [&](int j) { const int L = tau + C::T * j; return PAD ? L + (L >> 4) : L; },
-        [&](int j) { const int L = lo + N3 * j + 16 * N3 * hi; return PAD ? L + (L >> 4) : L; });
+        [&](int j) { const int L = tau + C::T * j; return PAD ? (X::SWIZZLE ? (L ^ ((L >> 4) & 7)) : L + (L >> 4)) : L; },
+        [&](int j) {
+            const int L = lo + N3 * j + 16 * N3 * hi;
+            return PAD ? (X::SWIZZLE ? (L ^ ((L >> 4) & 7)) : L + (L >> 4)) : L;
+        });
     fft_pass<16, N3, C::T, INV>(v, tau, tw.p[P]);
     if constexpr (N3 > 1) fft_later_passes<LOG2N, P + 1, INV, X>(v, tau, tw, xc);
 }
@@ -341,16 +374,16 @@ MLV_DEV void warp_sync() {
 MLV_DEV void group_transpose(cplx (&v)[16], double* gbuf, const int lane) {
     warp_sync();
     MLV_UNROLL
-    for (int j = 0; j < 16; ++j) gbuf[j * 17 + lane] = v[j].x;
+    for (int i = 0; i < 16; ++i) { const int j = MLV_XORDER(i); gbuf[j * 17 + lane] = v[j].x; }
     warp_sync();
     MLV_UNROLL
-    for (int j = 0; j < 16; ++j) v[j].x = gbuf[lane * 17 + j];
+    for (int i = 0; i < 16; ++i) { const int j = MLV_XORDER(i); v[j].x = gbuf[lane * 17 + j]; }
     warp_sync();
     MLV_UNROLL
-    for (int j = 0; j < 16; ++j) gbuf[j * 17 + lane] = v[j].y;
+    for (int i = 0; i < 16; ++i) { const int j = MLV_XORDER(i); gbuf[j * 17 + lane] = v[j].y; }
     warp_sync();
     MLV_UNROLL
-    for (int j = 0; j < 16; ++j) v[j].y = gbuf[lane * 17 + j];
+    for (int i = 0; i < 16; ++i) { const int j = MLV_XORDER(i); v[j].y = gbuf[lane * 17 + j]; }
 }
 
 // natural order in -> grouped order out (passes R0, 16, 16).  `buf`: the line's XSLOTS doubles.

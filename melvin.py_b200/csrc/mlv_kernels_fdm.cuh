@@ -249,6 +249,7 @@ __global__ void __launch_bounds__(512) k_fdm_solve(const FdmSolveArgs a) {
 // (four barriers per exchange; leaves room for the physical-space stash of q).
 template <int C>
 struct XchgSplitC {
+    static constexpr bool SWIZZLE = false;
     double* buf;
     int c;
     template <class WI, class RI>

@@ -284,9 +284,6 @@ __global__ void __launch_bounds__(C * FftCfg<LOG2N>::T, (C * FftCfg<LOG2N>::T <=
 k_xinv(const __grid_constant__ XInvArgs a) {
     typedef FftCfg<LOG2N> F;
     const int c = threadIdx.x % C, tau = threadIdx.x / C;
-    const int mreal = blockIdx.x * C + c;
-    const bool valid = mreal < a.nm;
-    const int m = valid ? mreal : a.nm - 1;          // clamp: loads stay unpredicated
     XchgFull<C> xc;
     cplx* const xbase = reinterpret_cast<cplx*>(MLV_SMEM_BASE());
     xc.buf = xbase;
@@ -296,28 +293,37 @@ k_xinv(const __grid_constant__ XInvArgs a) {
     // the stash: one tensor load per ld_rows rows instead of a scattered load per row and warp
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(stash + (size_t)a.ld_rows * a.ld_boxes * C);
     unsigned ld_phase = 0;
-    auto stash_fetch = [&](int f) {
+    auto stash_fetch = [&](int f, int tile) {
         if (threadIdx.x == 0) {
             mbar_expect_tx(bar, (unsigned)((size_t)a.ld_rows * a.ld_boxes * C * sizeof(cplx)));
             for (int b = 0; b < a.ld_boxes; ++b)
-                tma_load_2d(stash + (size_t)b * a.ld_rows * C, &a.smap[f], 2 * C * (int)blockIdx.x, b * a.ld_rows, bar);
+                tma_load_2d(stash + (size_t)b * a.ld_rows * C, &a.smap[f], 2 * C * tile, b * a.ld_rows, bar);
         }
     };
+    const int ntiles = (a.nm + C - 1) / C;
     if (a.load_tma) {
         if (threadIdx.x == 0) mbar_init(bar, 1);
         __syncthreads();
-        stash_fetch(0);                              // flies during the prefetch announcements below
+        stash_fetch(0, (int)blockIdx.x);             // flies during the prefetch announcements below
     }
+    const int rmask = (1 << a.sh.rpc_shift) - 1;
+    bool tma_pending = false;
+    bool prefetched = a.load_tma != 0;          // the stash (being) filled belongs to field 0 of this tile
+    // the CTA walks over column tiles (grid = ntiles unless the launch asks for resident CTAs only):
+    // the source tile of the next trip is requested as soon as the last field of this one has left
+    // the stash, so that its ~2700 tensor-load rows travel during that field's transform
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int mreal = tile * C + c;
+    const bool valid = mreal < a.nm;
+    const int m = valid ? mreal : a.nm - 1;          // clamp: loads stay unpredicated
     // announce the columns of the CTA that follows this one on the SM
-    if ((int)(blockIdx.x + a.wave) < (int)gridDim.x) {
+    if (tile + a.wave < ntiles && gridDim.x == (unsigned)ntiles) {
         const int rows = 2 * a.nn + 1;
         for (int r = threadIdx.x; r < rows; r += C * F::T)
-            l2_prefetch_line(a.src[0] + (size_t)r * a.spitch + (size_t)(blockIdx.x + a.wave) * C);
+            l2_prefetch_line(a.src[0] + (size_t)r * a.spitch + (size_t)(tile + a.wave) * C);
     }
     const int mg = m + a.sh.m_off;                   // global column (spectral symbols)
-    const int rmask = (1 << a.sh.rpc_shift) - 1;
     bool stash_psi = false;     // stash holds psi = -src/lap instead of the raw column
-    bool tma_pending = false;
     for (int f = 0; f < a.nf; ++f) {
         cplx v[16];
         const cplx* __restrict__ src = a.src[f];
@@ -332,13 +338,14 @@ k_xinv(const __grid_constant__ XInvArgs a) {
         // branch-free loads (all issued before the first is consumed); truncated rows read 0
         const bool via_tma = !reuse && a.load_tma;
         if (via_tma) {
-            if (f > 0) {                             // the stash still held the previous source
+            if (!(f == 0 && prefetched)) {           // the stash still held the previous source
                 __syncthreads();
-                stash_fetch(f);
+                stash_fetch(f, tile);
             }
             mbar_wait(bar, ld_phase);
             ld_phase ^= 1;
         }
+        prefetched = false;
         if (reuse || via_tma) {
             MLV_UNROLL
             for (int j = 0; j < 16; ++j) {
@@ -401,6 +408,12 @@ k_xinv(const __grid_constant__ XInvArgs a) {
                 v[j] = spectral_op(op, v[j], n, mg, a.k);      // truncated rows: 0 stays 0
             }
         }
+        if (a.load_tma && f == a.nf - 1 && tile + (int)gridDim.x < ntiles) {
+            // last field of the tile: nobody reads the stash any more -> request the next tile now
+            __syncthreads();
+            stash_fetch(0, tile + (int)gridDim.x);
+            prefetched = true;
+        }
         if (tma_pending && threadIdx.x == 0) tma_wait_read();   // previous tile has left the buffer
         fft_line<LOG2N, true>(v, tau, a.tw, xc);
         if (a.use_tma) {
@@ -413,7 +426,7 @@ k_xinv(const __grid_constant__ XInvArgs a) {
             __syncthreads();
             if (threadIdx.x == 0) {
                 for (int r0 = 0; r0 < F::N; r0 += a.tma_rows)
-                    tma_store_2d(&a.tmap[f], xbase + (size_t)r0 * C, 2 * C * (int)blockIdx.x, r0);
+                    tma_store_2d(&a.tmap[f], xbase + (size_t)r0 * C, 2 * C * tile, r0);
                 tma_commit();
             }
             tma_pending = true;
@@ -424,6 +437,113 @@ k_xinv(const __grid_constant__ XInvArgs a) {
                 const int x = tau + F::T * j;          // global row -> block of its owner
                 a.out.blk[x >> a.sh.rpc_shift][off + (size_t)(x & rmask) * a.ipitch] = v[j];
             }
+        }
+    }
+    }
+    if (tma_pending && threadIdx.x == 0) tma_wait_read();       // shared memory must outlive the reads
+}
+
+// ---- column-serial form of the inverse x pass (4096-point lines, unsharded, TMA both ways).
+// k_xinv runs ONE 512-thread CTA per SM (two columns side by side): its 16 warps meet at every
+// barrier of every exchange, so the shared-memory phases and the fp64 phases of the SM never
+// overlap.  Here a CTA is one 256-thread line (like the z stage) and two of them share an SM
+// and drift apart: one is in an exchange while the other is in its butterflies.  What makes two
+// CTAs fit: one column at a time (stash of 2nn+1 cplx = 44 KB instead of 87 KB) and an exchange
+// buffer of exactly N slots that is also the parking area of the result (XchgLineSwz, 64 KB).
+// A CTA walks over columns (persistent); the column enters through 16-byte-wide tensor loads and
+// each result leaves through 16-byte-wide tensor stores (the neighbouring column's halves of the
+// sectors follow within microseconds and meet them in the L2).
+template <int LOG2N>
+__global__ void __launch_bounds__(FftCfg<LOG2N>::T, 2)
+k_xinv_cols(const __grid_constant__ XInvArgs a) {
+    typedef FftCfg<LOG2N> F;
+    const int tau = threadIdx.x;
+    XchgLineSwz xc;
+    cplx* const xbase = reinterpret_cast<cplx*>(MLV_SMEM_BASE());
+    xc.buf = xbase;
+    cplx* const stash = xbase + F::N;
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(stash + (size_t)a.ld_rows * a.ld_boxes);
+    unsigned ld_phase = 0;
+    if (threadIdx.x == 0) mbar_init(bar, 1);
+    __syncthreads();
+    bool tma_pending = false;
+    for (int m = blockIdx.x; m < a.nm; m += gridDim.x) {
+        const int mg = m + a.sh.m_off;                   // global column (spectral symbols)
+        bool stash_psi = false;     // stash holds psi = -src/lap instead of the raw column
+        for (int f = 0; f < a.nf; ++f) {
+            cplx v[16];
+            const int op = a.op[f];
+            const bool wants_psi = (op == XOP_PSI || op == XOP_UX || op == XOP_UZ);
+            const bool same_prev = f > 0 && a.src[f] == a.src[f - 1];
+            const bool reuse = same_prev && (!stash_psi || wants_psi);
+            if (!reuse) stash_psi = false;
+            const bool keep = f + 1 < a.nf && a.src[f + 1] == a.src[f];
+            const int opn = keep ? a.op[f + 1] : -1;
+            const bool next_wants_psi = (opn == XOP_PSI || opn == XOP_UX || opn == XOP_UZ);
+            if (!reuse) {
+                __syncthreads();                         // every thread is done with the old stash
+                if (threadIdx.x == 0) {
+                    mbar_expect_tx(bar, (unsigned)((size_t)a.ld_rows * a.ld_boxes * sizeof(cplx)));
+                    for (int b = 0; b < a.ld_boxes; ++b)
+                        tma_load_2d(stash + (size_t)b * a.ld_rows, &a.smap[f], 2 * m, b * a.ld_rows, bar);
+                }
+                mbar_wait(bar, ld_phase);
+                ld_phase ^= 1;
+            }
+            MLV_UNROLL
+            for (int j = 0; j < 16; ++j) {
+                if (MLV_MID(j)) { v[j] = mk(0.0, 0.0); continue; }
+                int r = 0, n = 0;
+                const bool ok = xrow_static<F::N>(j, tau + F::T * j, a.nn, r, n);
+                const cplx t = stash[ok ? r : 0];
+                v[j] = ok ? t : mk(0.0, 0.0);
+            }
+            if (wants_psi) {
+                const bool have_psi = reuse && stash_psi;
+                const bool park_psi = keep && next_wants_psi && !have_psi;
+                const double bz = a.k.kz0 * mg;
+                MLV_UNROLL
+                for (int j = 0; j < 16; ++j) {
+                    if (MLV_MID(j)) continue;
+                    int r, n;
+                    const bool ok = xrow_static<F::N>(j, tau + F::T * j, a.nn, r, n);
+                    cplx psi = v[j];
+                    if (!have_psi) {
+                        double lap = lap_symbol(n, mg, a.k);
+                        if (n == 0 && mg == 0) lap = 1.0;
+                        const double rl = -fast_rcp(lap);             // psi = (-w)/lap
+                        psi = mk(v[j].x * rl, v[j].y * rl);
+                        if (park_psi && ok) stash[r] = psi;           // thread-private slot
+                    }
+                    if (op == XOP_UX) v[j] = mk(bz * psi.y, -bz * psi.x);
+                    else if (op == XOP_UZ) { const double b = a.k.kx0 * n; v[j] = mk(-b * psi.y, b * psi.x); }
+                    else v[j] = psi;
+                }
+                if (park_psi) stash_psi = true;
+            } else if (op != XOP_IDENT) {
+                MLV_UNROLL
+                for (int j = 0; j < 16; ++j) {
+                    if (MLV_MID(j)) continue;
+                    int r, n;
+                    xrow_static<F::N>(j, tau + F::T * j, a.nn, r, n);
+                    v[j] = spectral_op(op, v[j], n, mg, a.k);      // truncated rows: 0 stays 0
+                }
+            }
+            if (tma_pending && threadIdx.x == 0) tma_wait_read();   // previous column has left the buffer
+            fft_line<LOG2N, true>(v, tau, a.tw, xc);
+            // park the column in the exchange buffer (dense) and hand it to the copy engine; the
+            // stores overlap the next field's prologue and first butterflies
+            __syncthreads();
+            MLV_UNROLL
+            for (int j = 0; j < 16; ++j) xbase[tau + F::T * j] = v[j];
+            tma_fence_smem();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                for (int r0 = 0; r0 < F::N; r0 += a.tma_rows)
+                    tma_store_2d(&a.tmap[f], xbase + r0, 2 * m, r0);
+                tma_commit();
+            }
+            tma_pending = true;
         }
     }
     if (tma_pending && threadIdx.x == 0) tma_wait_read();       // shared memory must outlive the reads
@@ -700,18 +820,31 @@ MLV_DEV void zpair_load_line_(cplx (&v)[16], const cplx* __restrict__ rowA,
                               const cplx* __restrict__ rowB, int tau_, int nm, const Shard& sh) {
     typedef FftCfg<LOG2N> F;
     const int tau = opaque_int(tau_);
-    // branch-free: the loads are all issued before the first one is consumed
+    // branch-free: the loads are all issued before the first one is consumed.  By the 2/3-rule
+    // invariant (MLV_MID) registers j <= 5 can only hold low modes (A + iB) and j >= 10 only the
+    // mirrored high ones (conj A + i conj B): which form applies is known at compile time.
     MLV_UNROLL
     for (int j = 0; j < 16; ++j) {
         if (MLV_MID(j)) { v[j] = mk(0.0, 0.0); continue; }
         const int idx = tau + F::T * j;
-        const bool lo = idx < nm, hi = idx > F::N - nm;
-        const int mm = lo ? idx : (hi ? F::N - idx : 0);
-        const size_t off = SHARDED ? inv_col_off(mm, sh) : (size_t)mm;
-        const cplx A = ldg_pred(rowA + off, lo || hi), B = ldg_pred(rowB + off, lo || hi);
-        const double s = lo ? 1.0 : -1.0;            // hi: conj(A) + i conj(B)
-        const double ay = idx == 0 ? 0.0 : A.y, by = idx == 0 ? 0.0 : B.y;   // F4: Im of bin 0 dropped
-        v[j] = mk(A.x - s * by, s * ay + B.x);
+        if (j <= 5) {
+            const bool ok = idx < nm;
+            const int mm = ok ? idx : 0;
+            const size_t off = SHARDED ? inv_col_off(mm, sh) : (size_t)mm;
+            const cplx A = ldg_pred(rowA + off, ok), B = ldg_pred(rowB + off, ok);
+            if (j == 0) {                                  // F4: Im of bin 0 dropped
+                const bool z = idx == 0;
+                v[j] = mk(A.x - (z ? 0.0 : B.y), (z ? 0.0 : A.y) + B.x);
+            } else {
+                v[j] = mk(A.x - B.y, A.y + B.x);
+            }
+        } else {
+            const bool ok = idx > F::N - nm;
+            const int mm = ok ? F::N - idx : 0;
+            const size_t off = SHARDED ? inv_col_off(mm, sh) : (size_t)mm;
+            const cplx A = ldg_pred(rowA + off, ok), B = ldg_pred(rowB + off, ok);
+            v[j] = mk(A.x + B.y, B.x - A.y);
+        }
     }
 }
 template <int LOG2N>

@@ -27,6 +27,20 @@ inline int rt_malloc(void** p, size_t n) { *p = malloc(n ? n : 1); return *p ? 0
 inline void rt_free(void* p) { free(p); }
 inline int rt_h2d(void* d, const void* h, size_t n, stream_t) { memcpy(d, h, n); return 0; }
 inline size_t rt_max_smem() { return 232448; }
+// tensor maps are emulated (mlv_common.cuh: EmuTmap): the TMA paths of the kernels run on the host too
+inline bool rt_tma_enabled() {
+    static int on = -1;
+    if (on < 0) on = getenv("MLV_NO_TMA") ? 0 : 1;
+    return on == 1;
+}
+inline bool rt_make_tmap(CUtensorMap* m, void* base, unsigned long long inner, unsigned long long rows,
+                         unsigned long long row_bytes, unsigned box_inner, unsigned box_rows) {
+    if (((uintptr_t)base & 15) || (row_bytes & 15) || box_inner > 256 || box_rows > 256) return false;
+    EmuTmap* e = reinterpret_cast<EmuTmap*>(m);
+    e->base = base; e->inner = inner; e->rows = rows; e->row_bytes = row_bytes;
+    e->box_inner = box_inner; e->box_rows = box_rows;
+    return true;
+}
 #define MLV_LAUNCH(kfn, grid, block, smem, stream, ...)                                   \
     do {                                                                                  \
         if ((size_t)(smem) > mlv::rt_max_smem()) {                                        \

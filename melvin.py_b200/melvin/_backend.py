@@ -18,7 +18,8 @@ import torch
 from . import _capi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libmelvin_b200.so")
+# MLV_LIB: development switch to A/B-measure another build of the same sources (tools/build_variant.sh)
+LIB_PATH = os.environ.get("MLV_LIB") or os.path.join(_HERE, "_lib", "libmelvin_b200.so")
 
 _state = {"lib": None, "device": None, "launches": 0, "calls": {}}
 

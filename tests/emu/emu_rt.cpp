@@ -45,6 +45,8 @@ unsigned g_bar_gen[kMaxBar];
 void yield_fiber() { swapcontext(&g_fibers[g_cur].ctx, &g_sched); }
 }  // namespace
 
+void emu_yield() { yield_fiber(); }
+
 void emu_bar_arrive(int id, int count) {
     if (++g_bar_cnt[id] == count) { g_bar_cnt[id] = 0; ++g_bar_gen[id]; }
 }

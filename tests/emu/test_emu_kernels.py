@@ -74,3 +74,19 @@ def test_fdm_fused_step(nx, nz, order):
     """batched scan solver (one and several unknowns per thread, 256 and 512 threads), fused
     1-D advection and the row-wise right-hand side / update"""
     ac.case_fdm_fused_step(H, nx, nz, order)
+
+
+@pytest.mark.parametrize("nx,nz,grid", [(4096, 16, 0), (4096, 64, 3)])
+def test_inverse_x_pass_column_serial(nx, nz, grid, monkeypatch):
+    """4096-point x lines: column-serial persistent inverse x pass (two 256-thread CTAs per SM,
+    16-byte-wide tensor loads / stores, swizzled exchange buffer), several columns per CTA when the
+    grid is forced small, and the classic two-column kernel, vs the oracle"""
+    if grid:
+        monkeypatch.setenv("MLV_XINV_GRID", str(grid))
+    ac.case_transforms_2d(H, nx, nz)
+    if nz <= 1024:
+        ac.case_fused_advection_step(H, nx, nz, 2)
+    monkeypatch.setenv("MLV_XINV_COLS", "1")
+    ac.case_transforms_2d(H, nx, nz)
+    if nz <= 1024:
+        ac.case_fused_advection_step(H, nx, nz, 2)

@@ -111,3 +111,19 @@ def test_full_size_4096_transforms_and_properties(H):
     ctx.call("mlv_to_spectral", H.ptr(mix), H.ptr(I), H.ptr(comb))
     assert rel_l2(comb, 0.3 * spec - 1.7 * so) < 1e-13       # linearity
     ctx.close()
+
+
+@pytest.mark.parametrize("nx,nz,grid", [(4096, 16, 0), (4096, 64, 3), (4096, 1024, 0), (4096, 4096, 0)])
+def test_inverse_x_pass_column_serial(H, nx, nz, grid, monkeypatch):
+    """4096-point x lines: column-serial persistent inverse x pass (two 256-thread CTAs per SM,
+    16-byte-wide tensor loads / stores, swizzled exchange buffer), several columns per CTA when the
+    grid is forced small, and the classic two-column kernel, vs the oracle"""
+    if grid:
+        monkeypatch.setenv("MLV_XINV_GRID", str(grid))
+    ac.case_transforms_2d(H, nx, nz)
+    if nz <= 1024:
+        ac.case_fused_advection_step(H, nx, nz, 2)
+    monkeypatch.setenv("MLV_XINV_COLS", "1")
+    ac.case_transforms_2d(H, nx, nz)
+    if nz <= 1024:
+        ac.case_fused_advection_step(H, nx, nz, 2)
