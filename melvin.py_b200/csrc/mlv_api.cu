@@ -509,8 +509,10 @@ static int launch_zadv(mlv_ctx* c, ZAdvArgs& a, unsigned& grid_out) {
                         (size_t)4 * LPC * F::T * sizeof(double);
     unsigned grid = (unsigned)((a.nrows / 2 + LPC - 1) / LPC);
     a.wave = 148 * (smem > 113 * 1024 ? 1 : 2);
-    // three-pass lengths: persistent CTAs (one per resident slot) with grouped transforms
-    const bool grouped = F::NPASS == 3 && !rt_env_flag("MLV_ZADV_CLASSIC");
+    // three-pass lengths: persistent CTAs (one per resident slot) with grouped transforms -- measured
+    // 2 % slower than one row pair per CTA with natural-order transforms (profiles/r02_experiments.md),
+    // kept as a selectable, parity-tested variant
+    const bool grouped = F::NPASS == 3 && rt_env_flag("MLV_ZADV_GROUPED");
     if (grouped && grid > (unsigned)a.wave) grid = (unsigned)a.wave;
     if (grouped) {                           // test switch: force several row pairs per CTA on small grids
         const char* g = getenv("MLV_ZADV_GRID");

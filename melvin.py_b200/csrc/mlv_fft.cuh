@@ -251,10 +251,10 @@ MLV_DEV void fft_pass(cplx (&v)[16], int tau, const cplx* tw) {
 // The radix-16 butterfly starts with radix-4 butterflies over registers {n, n+4, n+8, n+12} and
 // ends with results that land in the same groups, so the first butterflies can start while the
 // other loads are still in flight, and the first stores can leave before the last results exist.
-#ifndef MLV_NO_XORDER
+#ifdef MLV_USE_XORDER
 #define MLV_XORDER(i) ((((i) & 3) << 2) | ((i) >> 2))
 #else
-#define MLV_XORDER(i) (i)
+#define MLV_XORDER(i) (i)          // measured: no gain (profiles/r02_experiments.md)
 #endif
 
 // Full complex128 exchange buffer shared by C interleaved lines (x passes):

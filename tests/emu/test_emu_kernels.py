@@ -44,10 +44,11 @@ def test_fused_advection_step(nx, nz, order):
 def test_fused_advection_persistent_grouped(nx, nz, grid, monkeypatch):
     """three-pass line lengths: persistent CTAs over several row pairs (grid forced small) with
     grouped-order transforms, incl. a trip count that leaves lines of the last trip idle"""
+    monkeypatch.setenv("MLV_ZADV_GROUPED", "1")
     if grid:
         monkeypatch.setenv("MLV_ZADV_GRID", str(grid))
     ac.case_fused_advection_step(H, nx, nz, 2)
-    monkeypatch.setenv("MLV_ZADV_CLASSIC", "1")
+    monkeypatch.delenv("MLV_ZADV_GROUPED")
     ac.case_fused_advection_step(H, nx, nz, 2)
 
 

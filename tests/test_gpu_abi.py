@@ -43,10 +43,11 @@ def test_fused_advection_step(H, nx, nz, order):
 def test_fused_advection_persistent_grouped(H, nx, nz, grid, monkeypatch):
     """three-pass line lengths: persistent CTAs (several row pairs per CTA, also forced on small
     grids) with grouped-order transforms, and the classic one-pair-per-CTA kernel, vs the oracle"""
+    monkeypatch.setenv("MLV_ZADV_GROUPED", "1")
     if grid:
         monkeypatch.setenv("MLV_ZADV_GRID", str(grid))
     ac.case_fused_advection_step(H, nx, nz, 2)
-    monkeypatch.setenv("MLV_ZADV_CLASSIC", "1")
+    monkeypatch.delenv("MLV_ZADV_GROUPED")
     ac.case_fused_advection_step(H, nx, nz, 2)
 
 
