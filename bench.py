@@ -680,6 +680,7 @@ def gpu_arm(args, rank, world):
         torch.cuda.current_stream().synchronize()
         return float(calc_kinetic_energy(ux, uz, xp, params))      # D2H (4 doubles)
 
+    sim.reductions = "always"          # this loop reads the kinetic energy after every step
     for _ in range(2):
         e2e_step()
     torch.cuda.synchronize()
@@ -695,6 +696,7 @@ def gpu_arm(args, rank, world):
 
     def build_member(i):
         mstep, mo = build_public_loop(config, nx, nz)
+        mo["sim"].reductions = "always"
         return {"step": mstep, "o": mo, "ke": None,
                 "hosts": {n: torch.from_numpy(mo[n].on_host()).pin_memory() for n in names}}
 

@@ -251,6 +251,10 @@ int mlv_advect_z_rows(mlv_ctx* ctx, const void* iux, const void* iuz, const void
  * mlv_info.red_doubles doubles registered with mlv_set_reduction_partials (NULL = scratch again)
  * -- and mlv_reduce_partials combines them into red4 whenever somebody asks. */
 int mlv_set_reduction_partials(mlv_ctx* ctx, double* partials);
+/* on = 0: the fused z stage skips its CFL / kinetic-energy partials (Integrator.py:35-44, utility.py:42-59
+ * are ticker-cadence work: melvin/simulation.py asks for them only for steps a ticker will read);
+ * mlv_reduce_partials then fails until a launch with reductions on has run.  Default: on. */
+int mlv_set_reductions(mlv_ctx* ctx, int on);
 int mlv_reduce_partials(mlv_ctx* ctx, const double* partials, double* red4);
 /* materialised physical operands: out = pddx(ux*q) + pddz(uz*q) */
 int mlv_advect_phys(mlv_ctx* ctx, const double* ux, const double* uz, const double* q,

@@ -52,6 +52,7 @@ struct mlv_ctx {
     size_t red_cap = 0;
     double* red_user = nullptr; // caller-owned partials of the fused z stage (mlv_set_reduction_partials)
     int red_count = 0;          // per-CTA partials written by the latest fused z stage over all local rows
+    bool red_on = true;         // mlv_set_reductions: the fused z stage computes its CFL / energy partials
     // slab decomposition (mlv_set_sharding); defaults describe the unsharded case
     int rank = 0, nranks = 1;
     int nml = 0;                // local column pitch of spectral arrays / inverse buffers
@@ -447,15 +448,20 @@ static int launch_zreal(mlv_ctx* c, ZRealArgs& a, bool inverse) {
 template <int L>
 static int launch_zadv_real(mlv_ctx* c, ZAdvArgs& a, unsigned& grid_out) {
     typedef FftCfg<L> F;
-    auto kfn = k_zr_advect<L>;
     const size_t smem = F::XSLOTS * sizeof(double) + (size_t)F::N * sizeof(cplx) + (size_t)4 * F::T * sizeof(double);
     const unsigned grid = (unsigned)a.nrows;
     grid_out = grid;
     int rc = ensure_red(c, (size_t)(a.nx / a.nrows) * grid * 4);
     if (rc) return rc;
-    a.red = (c->red_user ? c->red_user : c->red) + (size_t)(a.row0 / a.nrows) * grid * 4;
+    a.red = c->red_on ? (c->red_user ? c->red_user : c->red) + (size_t)(a.row0 / a.nrows) * grid * 4 : nullptr;
     a.wave = 148;
-    MLV_LAUNCH(kfn, grid, (unsigned)F::T, smem, c->stream, a);
+    if (a.red) {
+        auto kfn = k_zr_advect<L, true>;
+        MLV_LAUNCH(kfn, grid, (unsigned)F::T, smem, c->stream, a);
+    } else {
+        auto kfn = k_zr_advect<L, false>;
+        MLV_LAUNCH(kfn, grid, (unsigned)F::T, smem, c->stream, a);
+    }
     return 0;
 }
 
@@ -523,6 +529,7 @@ static int launch_zadv(mlv_ctx* c, ZAdvArgs& a, unsigned& grid_out) {
     int rc = ensure_red(c, (size_t)(a.nx / a.nrows) * grid * 4);
     if (rc) return rc;
     a.red = (c->red_user ? c->red_user : c->red) + (size_t)(a.row0 / a.nrows) * grid * 4;
+    if (!c->red_on && !grouped) a.red = nullptr;          // no ticker reads the reductions of this step
     if constexpr (F::NPASS == 3) {
         if (grouped) {
             auto kfn = k_z_advect_grouped<L, LPC>;
@@ -530,8 +537,13 @@ static int launch_zadv(mlv_ctx* c, ZAdvArgs& a, unsigned& grid_out) {
             return 0;
         }
     }
-    auto kfn = k_z_advect<L, LPC>;
-    MLV_LAUNCH(kfn, grid, (unsigned)(LPC * F::T), smem, c->stream, a);
+    if (a.red) {
+        auto kfn = k_z_advect<L, LPC, true>;
+        MLV_LAUNCH(kfn, grid, (unsigned)(LPC * F::T), smem, c->stream, a);
+    } else {
+        auto kfn = k_z_advect<L, LPC, false>;
+        MLV_LAUNCH(kfn, grid, (unsigned)(LPC * F::T), smem, c->stream, a);
+    }
     return 0;
 }
 
@@ -1065,8 +1077,14 @@ int mlv_advect_z_rows(mlv_ctx* c, const void* iux, const void* iuz, const void* 
     if (c->p2p_fwd && c->flags_on)         // every rank bumps the forward counter of every rank once per launch
         if (int rs = signal_arrival(c, 1, true, c->nranks)) return rs;
     // per-CTA partials of the rows [0, row0 + nrows) launched so far
-    c->red_count = (int)((long long)grid * (row0 + nrows) / nrows);
+    c->red_count = a.red ? (int)((long long)grid * (row0 + nrows) / nrows) : 0;
     if (red4) return mlv_reduce_partials(c, nullptr, red4);
+    return MLV_OK;
+}
+
+int mlv_set_reductions(mlv_ctx* c, int on) {
+    if (!c) { set_error("mlv_set_reductions: null context"); return MLV_ERR_INVALID; }
+    c->red_on = on != 0;
     return MLV_OK;
 }
 

@@ -1072,7 +1072,10 @@ struct ZAdvArgs {
     const cplx* tws;               // real-row lines: e^{-2 pi i k/nz}, k < nz/2
 };
 
-template <int LOG2N, int LPC>
+// RED = false: no ticker reads the reductions of this step (mlv_set_reductions): the maxima / sums
+// and their shared-memory tree are compiled out (a run-time test instead costs registers this
+// kernel does not have: spills 88 -> 324 bytes, 0.255 -> 0.270 ms)
+template <int LOG2N, int LPC, bool RED>
 __global__ void __launch_bounds__(LPC * FftCfg<LOG2N>::T, (LPC * FftCfg<LOG2N>::T <= 256) ? 2 : 1)
 k_z_advect(const ZAdvArgs a) {
     typedef FftCfg<LOG2N> F;
@@ -1123,7 +1126,7 @@ k_z_advect(const ZAdvArgs a) {
         }
         MLV_SCHED_FENCE();
         fft_line<LOG2N, true>(v, tau, a.tw, xc);
-        {
+        if constexpr (RED) {
             double mx = -INFINITY, ss = 0.0;
             MLV_UNROLL
             for (int j = 0; j < 16; ++j) {
@@ -1136,6 +1139,12 @@ k_z_advect(const ZAdvArgs a) {
             // maximum NaN too, as numpy.max does (Integrator.py:41 tests np.isnan(cfl_dt))
             rbuf[pass * NT + threadIdx.x] = valid ? (ss != ss ? NAN : mx) : -INFINITY;
             rbuf[(2 + pass) * NT + threadIdx.x] = valid ? ss : 0.0;
+        } else {                                 // no ticker reads the reductions of this step
+            MLV_UNROLL
+            for (int j = 0; j < 16; ++j) {
+                const cplx q = stash[j * F::T];
+                v[j] = mk(v[j].x * q.x, v[j].y * q.y);
+            }
         }
         fft_line<LOG2N, false>(v, tau, a.tw, xc);
         cplx* pbuf = reinterpret_cast<cplx*>(xc.buf);
@@ -1171,6 +1180,7 @@ k_z_advect(const ZAdvArgs a) {
         }
     }
     // ---- reductions: per-CTA partials (deterministic two-stage reduction)
+    if constexpr (RED) {
     __syncthreads();
     // tree over the 4 x NT table: thread t reduces column block of quantity w = t / (NT/4)
     {
@@ -1189,6 +1199,7 @@ k_z_advect(const ZAdvArgs a) {
             }
         }
         if (w < 4 && g == 0) a.red[(size_t)blockIdx.x * 4 + w] = rbuf[w * NT];
+    }
     }
 }
 

@@ -244,7 +244,7 @@ k_zr_r2c(const ZRealArgs a) {
 
 // fused physical-space stage of Variable.vec_dot_nabla (see k_z_advect), one real row per CTA.
 // Shared memory: [ XSLOTS doubles exchange | H cplx thread-private stash | 4*T doubles ].
-template <int LOG2H>
+template <int LOG2H, bool RED>
 __global__ void __launch_bounds__(FftCfg<LOG2H>::T, (FftCfg<LOG2H>::T <= 256) ? 2 : 1)
 k_zr_advect(const ZAdvArgs a) {
     typedef FftCfg<LOG2H> F;
@@ -270,7 +270,7 @@ k_zr_advect(const ZAdvArgs a) {
     for (int pass = 0; pass < 2; ++pass) {        // pass 0: A = ux q, pass 1: B = uz q
         zreal_load_line<LOG2H>(v, (pass == 0 ? a.Iux : a.Iuz) + rowoff, a.tws, tau, a.nm, a.sh);
         fft_line<LOG2H, true>(v, tau, a.tw, xc);
-        {
+        if constexpr (RED) {
             double mx = -INFINITY, ss = 0.0;
             MLV_UNROLL
             for (int j = 0; j < 16; ++j) {
@@ -281,6 +281,12 @@ k_zr_advect(const ZAdvArgs a) {
             }
             rbuf[pass * NT + tau] = ss != ss ? NAN : mx;      // NaN-propagating, see k_z_advect
             rbuf[(2 + pass) * NT + tau] = ss;
+        } else {
+            MLV_UNROLL
+            for (int j = 0; j < 16; ++j) {
+                const cplx q = stash[j * F::T];
+                v[j] = mk(v[j].x * q.x, v[j].y * q.y);
+            }
         }
         fft_line<LOG2H, false>(v, tau, a.tw, xc);
         const size_t foff = (size_t)a.outoff[pass];
@@ -292,6 +298,7 @@ k_zr_advect(const ZAdvArgs a) {
         });
     }
     // ---- reductions: per-CTA partials (deterministic two-stage reduction)
+    if constexpr (RED) {
     __syncthreads();
     {
         constexpr int G = NT / 4 > 0 ? NT / 4 : 1;          // threads per quantity
@@ -309,6 +316,7 @@ k_zr_advect(const ZAdvArgs a) {
             }
         }
         if (w < 4 && g == 0) a.red[(size_t)blockIdx.x * 4 + w] = rbuf[w * NT];
+    }
     }
 }
 

@@ -197,6 +197,10 @@ class Context:
         self._scratch_i = None
         self._red4 = None
         self._lazy_exprs = weakref.WeakSet()     # live deferred expressions (b200.SpecExpr)
+        # CFL / kinetic-energy partials of the fused z stage: Simulation.end_loop clears this for
+        # steps no ticker will read (melvin/simulation.py); readers fall back to explicit reductions
+        self.want_reductions = True
+        self._reductions_on = True
         self._stream = None
         self.set_stream(current_stream_handle())
 
@@ -214,6 +218,14 @@ class Context:
             _state["launches"] += 1
             calls = _state["calls"]
             calls[name] = calls.get(name, 0) + 1
+
+    def sync_reduction_mode(self):
+        """Tell the library whether the next fused z stage computes its reduction partials."""
+        on = bool(self.want_reductions)
+        if on != self._reductions_on:
+            _capi.check(self.lib, self.lib.mlv_set_reductions(self.handle, int(on)))
+            self._reductions_on = on
+        return on
 
     # pool of x-transformed intermediates: (nx, ipitch) complex128, FDM-z mode: (nn, nz) x spectra
     def take_i(self):

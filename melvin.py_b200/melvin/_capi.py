@@ -23,7 +23,7 @@ EXPORTS = [
     "mlv_create", "mlv_destroy", "mlv_set_stream", "mlv_get_info", "mlv_long_lines", "mlv_set_sharding", "mlv_set_forward_blocks", "mlv_p2p_alloc", "mlv_p2p_copy", "mlv_p2p_open",
     "mlv_p2p_close", "mlv_set_peer_buffers", "mlv_set_peer_flags", "mlv_last_error",
     "mlv_abi_version", "mlv_launch_count", "mlv_to_physical", "mlv_to_spectral", "mlv_x_inverse",
-    "mlv_z_inverse", "mlv_z_forward", "mlv_x_forward", "mlv_advect_z", "mlv_advect_z_rows", "mlv_set_reduction_partials", "mlv_reduce_partials", "mlv_advect_phys",
+    "mlv_z_inverse", "mlv_z_forward", "mlv_x_forward", "mlv_advect_z", "mlv_advect_z_rows", "mlv_set_reduction_partials", "mlv_set_reductions", "mlv_reduce_partials", "mlv_advect_phys",
     "mlv_spec_lincomb", "mlv_lap_array", "mlv_stencil", "mlv_solve_fdm", "mlv_fdm_velocity",
     "mlv_fdm_advect", "mlv_integrate",
     "mlv_elementwise", "mlv_reduce", "mlv_trig_axis",
@@ -133,6 +133,7 @@ def declare(lib):
         "mlv_advect_z": [vp, vp, vp, vp, vp, vp, vp],
         "mlv_advect_z_rows": [vp, vp, vp, vp, vp, vp, i32, i32, vp],
         "mlv_set_reduction_partials": [vp, vp],
+        "mlv_set_reductions": [vp, i32],
         "mlv_reduce_partials": [vp, vp, vp],
         "mlv_advect_phys": [vp, vp, vp, vp, vp],
         "mlv_spec_lincomb": [vp, C.POINTER(LinTerms), vp],

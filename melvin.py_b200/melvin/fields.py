@@ -380,6 +380,7 @@ class Variable:
         # them when (and if) somebody asks
         if uxo._red_part is None:
             uxo._red_part = _backend.empty((ctx.red_doubles,), np.float64)
+        reduced = ctx.sync_reduction_mode()
         ctx.call("mlv_set_reduction_partials", ctypes.c_void_p(uxo._red_part.data_ptr()), count=False)
         ctx.call("mlv_advect_z", ctypes.c_void_p(uxo._i.data_ptr()), ctypes.c_void_p(uzo._i.data_ptr()),
                  ctypes.c_void_p(self._i.data_ptr()), ctypes.c_void_p(ia.data_ptr()),
@@ -390,9 +391,12 @@ class Variable:
             ia, ib = ctx.exchange(sa, True), ctx.exchange(sb, True)
             ctx.give_i(sa)
             ctx.give_i(sb)
-        shared = {"part": uxo._red_part, "host": None}
-        uxo._red = (shared, 0, 2)
-        uzo._red = (shared, 1, 3)
+        if reduced:
+            shared = {"part": uxo._red_part, "host": None}
+            uxo._red = (shared, 0, 2)
+            uzo._red = (shared, 1, 3)
+        else:                       # nobody asked: a reader falls back to an explicit reduction
+            uxo._red = uzo._red = None
         return SpecExpr(ctx, [], [(1.0, NLTerm(ctx, ia, ib))])
 
     def _vec_dot_nabla_fdm(self, uxo, uzo):

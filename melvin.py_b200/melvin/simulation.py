@@ -115,6 +115,8 @@ class Simulation:
         self._spectral_trans = SpectralTransformer(params, xp, self._array_factory)
         self._t = 0
         self._loop_counter = 0
+        self.reductions = "auto"             # see end_loop
+        self._ctx = _backend.context_for(params)
         self._dump_vars = []
         self._dump_dvars = []
         self._dump_idx = 0
@@ -234,6 +236,16 @@ class Simulation:
         self._t += self._integrator._dt
         for ticker in self._tickers:
             ticker.tick(self._t, self._loop_counter)
+        # the fused z stage produces the CFL maxima and energy sums the tickers read; it only has to
+        # for a step whose end_loop will fire one (every cfl_cadence / tracker_cadence loops).
+        # `reductions = "always"` keeps them on for loops that read them outside the tickers
+        # (a reader that finds none falls back to an explicit reduction: same numbers, two more kernels)
+        if self.reductions == "always":
+            want = True
+        else:
+            dt = self._integrator._dt
+            want = any(t.due(self._t + dt, self._loop_counter + 1) for t in self._tickers)
+        self._ctx.want_reductions = want
 
     def calc_time_remaining(self, ticker):
         self._timer.split()

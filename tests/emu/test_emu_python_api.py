@@ -276,3 +276,36 @@ def test_predictor_corrector_converges_at_its_order(order):
 def test_cosine_and_sine_bases():
     import host_cases as hc
     hc.trig_bases()
+
+
+def test_reductions_follow_the_tickers():
+    """The fused z stage computes the CFL / energy partials only for steps whose end_loop fires a
+    ticker (Simulation.end_loop); a reader on any other step falls back to an explicit reduction
+    and gets the same numbers."""
+    import bench
+    from melvin.utility import calc_kinetic_energy
+    import melvin.b200 as xp
+    cwd = os.getcwd()
+    try:
+        step, o = bench.build_public_loop("kh", 32, 32)
+        sim, ctx, ux, uz = o["sim"], o["sim"]._ctx, o["ux"], o["uz"]
+        on = []
+        for _ in range(23):
+            on.append(ctx.want_reductions)
+            step()
+        # loop 1 fires every ticker; then the CFL ticker every 10 loops (11, 21), tracker every 100
+        assert [i for i, f in enumerate(on) if f] == [0, 10, 20]
+        assert ux._red is None                              # the last step skipped them
+        ke_fallback = float(calc_kinetic_energy(ux, uz, xp, o["params"]))
+        sim.reductions = "always"
+        sim.end_loop.__self__._ctx.want_reductions = True
+        step2, o2 = bench.build_public_loop("kh", 32, 32)
+        o2["sim"].reductions = "always"
+        for _ in range(23):
+            step2()
+        assert o2["ux"]._red is not None
+        ke_fused = float(calc_kinetic_energy(o2["ux"], o2["uz"], xp, o2["params"]))
+        assert abs(ke_fallback / ke_fused - 1) < 1e-13
+        assert np.array_equal(o["w"].on_host(), o2["w"].on_host())       # same trajectory, same dt history
+    finally:
+        os.chdir(cwd)
