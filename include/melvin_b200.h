@@ -275,6 +275,11 @@ int mlv_stencil(mlv_ctx* ctx, const void* in, void* out, int rows, int cols, int
 /* ---- LaplacianSolver.solve (melvin/LaplacianSolver.py:58-79) --------------
  * fully spectral: mlv_spec_lincomb with MLV_OP_INVLAP; FDM-z: batched tridiagonal */
 int mlv_solve_fdm(mlv_ctx* ctx, const void* rhs, void* out);
+/* 4th-order variant (EXTENSION, no reference code path: BASELINE names the pentadiagonal case, the
+ * reference's FDM Laplacian is always the tridiagonal one): the 4th-order central second difference of
+ * SpatialDifferentiator.py:121-130 on rows 2..nz-3, the 2nd-order one on rows 1 and nz-2, identity
+ * boundary rows as in LaplacianSolver.py:46-51.  Parity unpinned; own accuracy / convergence tests. */
+int mlv_solve_fdm_o4(mlv_ctx* ctx, const void* rhs, void* out);
 
 /* ---- fused Fourier-x / FDM-z step (examples/rayleigh_benard_convection.py:95-145) ---------
  * mlv_fdm_velocity: utility.calc_velocity_from_vorticity, FDM branch (utility.py:62-79) in one

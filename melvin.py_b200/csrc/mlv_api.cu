@@ -47,6 +47,7 @@ struct mlv_ctx {
     mlv::Plan planx, planz;
     double* symz = nullptr;     // [nm]
     double* tri_inv = nullptr;  // FDM-z: (nn, nz) pivots of the Thomas factorisation
+    double* penta = nullptr;    // FDM-z, 4th-order solve: 5 x (nn, nz) LU coefficients (built on first use)
     double* symx = nullptr;     // FDM-z: [nn] Fourier symbol of the periodic central x stencil
     double* red = nullptr;      // reduction partials
     size_t red_cap = 0;
@@ -730,6 +731,7 @@ int mlv_destroy(mlv_ctx* c) {
     if (c->tws_z) rt_free(c->tws_z);
     if (c->symz) rt_free(c->symz);
     if (c->tri_inv) rt_free(c->tri_inv);
+    if (c->penta) rt_free(c->penta);
     if (c->symx) rt_free(c->symx);
     if (c->red) rt_free(c->red);
     if (c->expect) rt_free(c->expect);
@@ -1158,6 +1160,68 @@ int mlv_solve_fdm(mlv_ctx* c, const void* rhs, void* out) {
     if (!c || !rhs || !out) { set_error("mlv_solve_fdm: null argument"); return MLV_ERR_INVALID; }
     if (!c->p.fdm_z) { set_error("mlv_solve_fdm: context is fully spectral"); return MLV_ERR_INVALID; }
     return launch_fdm_solve(c, rhs, 1.0, out, nullptr, nullptr);
+}
+
+// LU factors (no pivoting) of the nn pentadiagonal systems of the 4th-order solve, in extended
+// precision on the host; stored as the coefficients of the two substitution recurrences.
+static int build_penta(mlv_ctx* c) {
+    const int nz = c->p.nz, nn = c->nn;
+    const size_t tot = (size_t)nn * nz;
+    std::vector<double> co(5 * tot);
+    double *fa = co.data(), *fb = fa + tot, *dinv = fb + tot, *ba = dinv + tot, *bb = ba + tot;
+    const long double h2 = (long double)c->dz * (long double)c->dz;
+    std::vector<long double> e(nz), cc(nz), d(nz), f(nz), g(nz), du(nz), fu(nz);
+    for (int n = 0; n < nn; ++n) {
+        const long double k2 = ((long double)n * (long double)c->p.kx0) * ((long double)n * (long double)c->p.kx0);
+        for (int i = 0; i < nz; ++i) {
+            e[i] = cc[i] = f[i] = g[i] = 0.0L;
+            if (i == 0 || i == nz - 1) { d[i] = 1.0L; continue; }             // solution = right-hand side
+            if (i == 1 || i == nz - 2) {                                        // 2nd-order closure
+                cc[i] = f[i] = 1.0L / h2; d[i] = -2.0L / h2 - k2;
+                continue;
+            }
+            e[i] = g[i] = -1.0L / (12.0L * h2);                                 // SpatialDifferentiator.py:121-130
+            cc[i] = f[i] = 4.0L / (3.0L * h2);
+            d[i] = -5.0L / (2.0L * h2) - k2;
+        }
+        double* FA = fa + (size_t)n * nz; double* FB = fb + (size_t)n * nz; double* DI = dinv + (size_t)n * nz;
+        double* BA = ba + (size_t)n * nz; double* BB = bb + (size_t)n * nz;
+        for (int i = 0; i < nz; ++i) {
+            long double l2 = 0.0L, l1 = 0.0L, ci = cc[i], di = d[i], fi = f[i];
+            if (i >= 2) { l2 = e[i] / du[i - 2]; ci -= l2 * fu[i - 2]; di -= l2 * g[i - 2]; }
+            if (i >= 1) { l1 = ci / du[i - 1]; di -= l1 * fu[i - 1]; fi -= l1 * g[i - 1]; }
+            du[i] = di; fu[i] = fi;
+            FA[i] = (double)(-l1); FB[i] = (double)(-l2);
+            DI[i] = (double)(1.0L / di);
+            BA[i] = (double)(-fi / di); BB[i] = (double)(-g[i] / di);
+        }
+    }
+    int rc = rt_malloc((void**)&c->penta, co.size() * sizeof(double));
+    if (!rc) rc = rt_h2d(c->penta, co.data(), co.size() * sizeof(double), c->stream);
+    return rc;
+}
+
+int mlv_solve_fdm_o4(mlv_ctx* c, const void* rhs, void* out) {
+    if (!c || !rhs || !out) { set_error("mlv_solve_fdm_o4: null argument"); return MLV_ERR_INVALID; }
+    if (!c->p.fdm_z) { set_error("mlv_solve_fdm_o4: context is fully spectral"); return MLV_ERR_INVALID; }
+    if (c->p.nz < 6) { set_error("mlv_solve_fdm_o4: nz >= 6"); return MLV_ERR_UNSUPPORTED; }
+    if (!c->penta) if (int rc = build_penta(c)) return rc;
+    FdmSolve5Args a;
+    const size_t tot = (size_t)c->nn * c->p.nz;
+    a.rhs = (const cplx*)rhs; a.out = (cplx*)out; a.nn = c->nn; a.nz = c->p.nz;
+    a.fa = c->penta; a.fb = c->penta + tot; a.dinv = c->penta + 2 * tot; a.ba = c->penta + 3 * tot; a.bb = c->penta + 4 * tot;
+    const unsigned nt = a.nz <= 256 * MLV_FDM_PER ? 256u : 512u;
+    if ((long long)nt * MLV_FDM_PER < a.nz) {
+        set_error("FDM-z solve: nz=%d unsupported (at most %d)", a.nz, 512 * MLV_FDM_PER);
+        return MLV_ERR_UNSUPPORTED;
+    }
+    size_t smem = (size_t)(a.nz + (a.nz >> 3) + 1) * sizeof(cplx) + 256 * sizeof(double);
+#ifdef MLV_EMU
+    smem += 8 * (size_t)nt * sizeof(double);
+#endif
+    auto kfn = k_fdm_solve5;
+    MLV_LAUNCH(kfn, (unsigned)a.nn, nt, smem, c->stream, a);
+    return MLV_OK;
 }
 
 int mlv_fdm_velocity(mlv_ctx* c, const void* w, void* psi, void* uxh, void* uzh) {

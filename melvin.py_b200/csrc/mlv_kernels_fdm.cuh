@@ -244,6 +244,186 @@ __global__ void __launch_bounds__(512) k_fdm_solve(const FdmSolveArgs a) {
     }
 }
 
+// ===================================================================== 4th-order (pentadiagonal) solve
+// An extension with no counterpart in the reference (its finite-difference Laplacian is always the
+// 2nd-order tridiagonal one, LaplacianSolver.py:22-45; BASELINE's north star names the pentadiagonal
+// case): per x mode n the system  (D4 - (kx n)^2) psi = rhs  with D4 the 4th-order central second
+// difference the reference uses for derivatives (SpatialDifferentiator.py:121-130) on rows
+// 2..nz-3, the 2nd-order one on rows 1 and nz-2, and identity rows 0 and nz-1 (the reference's
+// "solution matches the right-hand side on the boundary" convention, LaplacianSolver.py:46-51).
+// The context holds the LU factors (no pivoting: the operator is negative definite); both
+// substitutions are SECOND-order linear recurrences
+//     z_i = g_i + a_i z_(i-1) + b_i z_(i-2)
+// evaluated as a parallel scan of affine maps on the pair (z_i, z_(i-1)): PER consecutive unknowns
+// per thread composed in registers, warp shuffles inside a warp, one exchange between warps.
+struct Aff2 {              // (z_i, z_(i-1)) = M (z_s, z_(s-1)) + G,  M = [[m00, m01], [m10, m11]] real
+    double m00, m01, m10, m11;
+    cplx g0, g1;
+};
+MLV_DEV Aff2 aff2_identity() { Aff2 r; r.m00 = 1; r.m01 = 0; r.m10 = 0; r.m11 = 1; r.g0 = mk(0, 0); r.g1 = mk(0, 0); return r; }
+// one more element on top of `p`:  z_new = g + a z_i + b z_(i-1)
+MLV_DEV Aff2 aff2_push(const Aff2& p, double a, double b, cplx g) {
+    Aff2 r;
+    r.m00 = a * p.m00 + b * p.m10; r.m01 = a * p.m01 + b * p.m11;
+    r.m10 = p.m00; r.m11 = p.m01;
+    r.g0 = mk(g.x + a * p.g0.x + b * p.g1.x, g.y + a * p.g0.y + b * p.g1.y);
+    r.g1 = p.g0;
+    return r;
+}
+// later o earlier
+MLV_DEV Aff2 aff2_compose(const Aff2& l, const Aff2& e) {
+    Aff2 r;
+    r.m00 = l.m00 * e.m00 + l.m01 * e.m10; r.m01 = l.m00 * e.m01 + l.m01 * e.m11;
+    r.m10 = l.m10 * e.m00 + l.m11 * e.m10; r.m11 = l.m10 * e.m01 + l.m11 * e.m11;
+    r.g0 = mk(l.g0.x + l.m00 * e.g0.x + l.m01 * e.g1.x, l.g0.y + l.m00 * e.g0.y + l.m01 * e.g1.y);
+    r.g1 = mk(l.g1.x + l.m10 * e.g0.x + l.m11 * e.g1.x, l.g1.y + l.m10 * e.g0.y + l.m11 * e.g1.y);
+    return r;
+}
+
+// carry-in pair of every thread: exclusive scan of the maps in thread order (REV: reverse order),
+// applied to the zero start pair.  wbuf: 8 * 32 doubles of shared memory (+ 8 * blockDim.x in the
+// emulation build).
+template <bool REV>
+MLV_DEV void aff2_scan_carry(Aff2 t, double* wbuf, cplx& c0, cplx& c1) {
+#ifdef MLV_EMU
+    double* sm = wbuf + 256;                      // [8][blockDim.x]
+    const int nt = blockDim.x, id = threadIdx.x;
+    sm[id] = t.m00; sm[nt + id] = t.m01; sm[2 * nt + id] = t.m10; sm[3 * nt + id] = t.m11;
+    sm[4 * nt + id] = t.g0.x; sm[5 * nt + id] = t.g0.y; sm[6 * nt + id] = t.g1.x; sm[7 * nt + id] = t.g1.y;
+    __syncthreads();
+    if (id == 0) {
+        cplx a = mk(0.0, 0.0), b = mk(0.0, 0.0);
+        for (int q = 0; q < nt; ++q) {
+            const int u = REV ? nt - 1 - q : q;
+            const double m00 = sm[u], m01 = sm[nt + u], m10 = sm[2 * nt + u], m11 = sm[3 * nt + u];
+            const cplx g0 = mk(sm[4 * nt + u], sm[5 * nt + u]), g1 = mk(sm[6 * nt + u], sm[7 * nt + u]);
+            sm[4 * nt + u] = a.x; sm[5 * nt + u] = a.y; sm[6 * nt + u] = b.x; sm[7 * nt + u] = b.y;
+            const cplx na = mk(g0.x + m00 * a.x + m01 * b.x, g0.y + m00 * a.y + m01 * b.y);
+            const cplx nb = mk(g1.x + m10 * a.x + m11 * b.x, g1.y + m10 * a.y + m11 * b.y);
+            a = na; b = nb;
+        }
+    }
+    __syncthreads();
+    c0 = mk(sm[4 * nt + id], sm[5 * nt + id]);
+    c1 = mk(sm[6 * nt + id], sm[7 * nt + id]);
+    __syncthreads();
+#else
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    auto shfl = [&](double v, int d) { return REV ? __shfl_down_sync(full, v, d) : __shfl_up_sync(full, v, d); };
+    auto fetch = [&](const Aff2& s, int d) {
+        Aff2 o;
+        o.m00 = shfl(s.m00, d); o.m01 = shfl(s.m01, d); o.m10 = shfl(s.m10, d); o.m11 = shfl(s.m11, d);
+        o.g0 = mk(shfl(s.g0.x, d), shfl(s.g0.y, d)); o.g1 = mk(shfl(s.g1.x, d), shfl(s.g1.y, d));
+        return o;
+    };
+    MLV_UNROLL
+    for (int d = 1; d < 32; d <<= 1) {             // inclusive scan inside the warp
+        const Aff2 o = fetch(t, d);
+        const bool has = REV ? (lane + d < 32) : (lane >= d);
+        if (has) t = aff2_compose(t, o);
+    }
+    if (lane == (REV ? 0 : 31)) {
+        double* w = wbuf + 8 * warp;
+        w[0] = t.m00; w[1] = t.m01; w[2] = t.m10; w[3] = t.m11;
+        w[4] = t.g0.x; w[5] = t.g0.y; w[6] = t.g1.x; w[7] = t.g1.y;
+    }
+    Aff2 prev = fetch(t, 1);                       // exclusive value inside the warp
+    if (lane == (REV ? 31 : 0)) prev = aff2_identity();
+    __syncthreads();
+    cplx a = mk(0.0, 0.0), b = mk(0.0, 0.0);       // carry into this warp (at most 32 warps: replayed)
+    auto step = [&](int w) {
+        const double* q = wbuf + 8 * w;
+        const cplx na = mk(q[4] + q[0] * a.x + q[1] * b.x, q[5] + q[0] * a.y + q[1] * b.y);
+        const cplx nb = mk(q[6] + q[2] * a.x + q[3] * b.x, q[7] + q[2] * a.y + q[3] * b.y);
+        a = na; b = nb;
+    };
+    if (REV) { for (int w = nw - 1; w > warp; --w) step(w); }
+    else { for (int w = 0; w < warp; ++w) step(w); }
+    __syncthreads();                               // wbuf is reused by the next scan
+    c0 = mk(prev.g0.x + prev.m00 * a.x + prev.m01 * b.x, prev.g0.y + prev.m00 * a.y + prev.m01 * b.y);
+    c1 = mk(prev.g1.x + prev.m10 * a.x + prev.m11 * b.x, prev.g1.y + prev.m10 * a.y + prev.m11 * b.y);
+#endif
+}
+
+struct FdmSolve5Args {
+    const cplx* rhs;      // (nn, nz)
+    cplx* out;
+    const double* fa;     // forward:  y_i = r_i + fa_i y_(i-1) + fb_i y_(i-2)
+    const double* fb;
+    const double* dinv;   // backward: x_i = dinv_i y_i + ba_i x_(i+1) + bb_i x_(i+2)
+    const double* ba;
+    const double* bb;
+    int nn, nz;
+};
+
+__global__ void __launch_bounds__(512) k_fdm_solve5(const FdmSolve5Args a) {
+    constexpr int PER = MLV_FDM_PER;
+    cplx* row = reinterpret_cast<cplx*>(MLV_SMEM_BASE());            // padded: slot e + (e >> 3)
+    const int padded = a.nz + (a.nz >> 3) + 1;
+    double* wbuf = reinterpret_cast<double*>(row + padded);
+    const int n = blockIdx.x, nt = blockDim.x, t = threadIdx.x;
+    const size_t base = (size_t)n * a.nz;
+    for (int e = t; e < a.nz; e += nt) row[e + (e >> 3)] = a.rhs[base + e];
+    __syncthreads();
+    const int e0 = t * PER;
+    cplx g[PER];
+    // ---- forward substitution
+    {
+        double ca[PER], cb[PER];
+        Aff2 m = aff2_identity();
+        MLV_UNROLL
+        for (int k = 0; k < PER; ++k) {
+            const int i = e0 + k;
+            ca[k] = 0.0; cb[k] = 0.0; g[k] = mk(0.0, 0.0);
+            if (i < a.nz) {
+                ca[k] = a.fa[base + i]; cb[k] = a.fb[base + i];
+                g[k] = row[i + (i >> 3)];
+                m = aff2_push(m, ca[k], cb[k], g[k]);
+            }
+        }
+        cplx z1, z2;                                 // y_(e0-1), y_(e0-2)
+        aff2_scan_carry<false>(m, wbuf, z1, z2);
+        MLV_UNROLL
+        for (int k = 0; k < PER; ++k)
+            if (e0 + k < a.nz) {
+                const cplx y = mk(g[k].x + ca[k] * z1.x + cb[k] * z2.x, g[k].y + ca[k] * z1.y + cb[k] * z2.y);
+                z2 = z1; z1 = y; g[k] = y;
+            }
+    }
+    // ---- back substitution (unknowns and threads in reverse order)
+    {
+        double ca[PER], cb[PER];
+        Aff2 m = aff2_identity();
+        MLV_UNROLL
+        for (int k = PER - 1; k >= 0; --k) {
+            const int i = e0 + k;
+            ca[k] = 0.0; cb[k] = 0.0;
+            if (i < a.nz) {
+                const double dv = a.dinv[base + i];
+                ca[k] = a.ba[base + i]; cb[k] = a.bb[base + i];
+                g[k] = mk(dv * g[k].x, dv * g[k].y);
+                m = aff2_push(m, ca[k], cb[k], g[k]);
+            }
+        }
+        cplx z1, z2;                                 // x_(e0+PER), x_(e0+PER+1)
+        aff2_scan_carry<true>(m, wbuf, z1, z2);
+        MLV_UNROLL
+        for (int k = PER - 1; k >= 0; --k)
+            if (e0 + k < a.nz) {
+                const cplx x = mk(g[k].x + ca[k] * z1.x + cb[k] * z2.x, g[k].y + ca[k] * z1.y + cb[k] * z2.y);
+                z2 = z1; z1 = x; g[k] = x;
+            }
+    }
+    MLV_UNROLL
+    for (int k = 0; k < PER; ++k) {
+        const int i = e0 + k;
+        if (i < a.nz) row[i + (i >> 3)] = g[k];
+    }
+    __syncthreads();
+    for (int e = t; e < a.nz; e += nt) a.out[base + e] = row[e + (e >> 3)];     // unit stride
+}
+
 // ===================================================================== K2: fused 1-D advection
 // Half-size exchange buffer shared by C interleaved lines: real parts, then imaginary parts
 // (four barriers per exchange; leaves room for the physical-space stash of q).

@@ -24,7 +24,7 @@ EXPORTS = [
     "mlv_p2p_close", "mlv_set_peer_buffers", "mlv_set_peer_flags", "mlv_last_error",
     "mlv_abi_version", "mlv_launch_count", "mlv_to_physical", "mlv_to_spectral", "mlv_x_inverse",
     "mlv_z_inverse", "mlv_z_forward", "mlv_x_forward", "mlv_advect_z", "mlv_advect_z_rows", "mlv_set_reduction_partials", "mlv_set_reductions", "mlv_reduce_partials", "mlv_advect_phys",
-    "mlv_spec_lincomb", "mlv_lap_array", "mlv_stencil", "mlv_solve_fdm", "mlv_fdm_velocity",
+    "mlv_spec_lincomb", "mlv_lap_array", "mlv_stencil", "mlv_solve_fdm", "mlv_solve_fdm_o4", "mlv_fdm_velocity",
     "mlv_fdm_advect", "mlv_integrate",
     "mlv_elementwise", "mlv_reduce", "mlv_trig_axis",
 ]
@@ -140,6 +140,7 @@ def declare(lib):
         "mlv_lap_array": [vp, f64, vp],
         "mlv_stencil": [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, f64],
         "mlv_solve_fdm": [vp, vp, vp],
+        "mlv_solve_fdm_o4": [vp, vp, vp],
         "mlv_fdm_velocity": [vp, vp, vp, vp, vp],
         "mlv_fdm_advect": [vp, vp, vp, vp, vp, vp, vp],
         "mlv_integrate": [vp, C.POINTER(LinTerms), C.POINTER(Integ)],

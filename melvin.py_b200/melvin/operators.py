@@ -432,6 +432,11 @@ class LaplacianSolver:
             print("WARNING: Laplacian solver only implemented for boundary conditions "
                   "where soln matches value of rhs")
             self.solve = self._solve_fdm
+            # EXTENSION (no reference code path): `laplacian_order: 4` in the parameters selects
+            # the pentadiagonal 4th-order operator; the default is the reference's tridiagonal one
+            self._order = int(getattr(params, "laplacian_order", 2))
+            if self._order not in (2, 4):
+                raise NotImplementedError("laplacian_order must be 2 or 4")
 
     @property
     def lap(self):
@@ -445,6 +450,22 @@ class LaplacianSolver:
         p = self._params
         kx0 = abs(1j * 2 * np.pi / p.lx)
         mats = []
+        if getattr(self, "_order", 2) == 4:
+            h2 = p.dz ** 2
+            for n in range(p.nn):
+                k2 = (n * kx0) ** 2
+                m = sp.lil_matrix((p.nz, p.nz), dtype=np.complex128)
+                for i in range(p.nz):
+                    if i in (0, p.nz - 1):
+                        m[i, i] = 1.0
+                    elif i in (1, p.nz - 2):
+                        m[i, i - 1], m[i, i], m[i, i + 1] = 1.0 / h2, -2.0 / h2 - k2, 1.0 / h2
+                    else:
+                        m[i, i - 2] = m[i, i + 2] = -1.0 / (12.0 * h2)
+                        m[i, i - 1] = m[i, i + 1] = 4.0 / (3.0 * h2)
+                        m[i, i] = -5.0 / (2.0 * h2) - k2
+                mats.append(m.tocsr())
+            return mats
         for n in range(p.nn):
             diag = np.full(p.nz, -((n * kx0) ** 2 + 2.0 / p.dz ** 2))
             off = np.full(p.nz, 1.0 / p.dz ** 2)
@@ -472,7 +493,7 @@ class LaplacianSolver:
         src = _contig(_dev(rhs, np.complex128))
         out._touch()
         out._pre_write()
-        self._ctx.call("mlv_solve_fdm", _ptr(src), _ptr(out._t))
+        self._ctx.call("mlv_solve_fdm_o4" if self._order == 4 else "mlv_solve_fdm", _ptr(src), _ptr(out._t))
         return out
 
 

@@ -23,6 +23,7 @@ _DEFAULTS = dict(
     load_from=None,
     discretisation=["spectral", "spectral"],
     precision="double",
+    laplacian_order=2,     # EXTENSION (not a reference key): 4 = pentadiagonal FDM-z Laplacian solve
     nx=None, nz=None, lx=None, lz=None, final_time=None,
 )
 

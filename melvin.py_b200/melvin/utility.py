@@ -66,7 +66,8 @@ def calc_velocity_from_vorticity(vorticity, streamfunction, ux, uz, laplacian_so
         uz._request_physical()
         return
 
-    if all(getattr(v, "_fused_fdm", False) for v in (vorticity, psi, ux, uz)):
+    if (all(getattr(v, "_fused_fdm", False) for v in (vorticity, psi, ux, uz))
+            and getattr(laplacian_solver, "_order", 2) == 2):     # (the 4th-order solve is not fused)
         _velocity_fdm(vorticity, psi, ux, uz)
         return
 

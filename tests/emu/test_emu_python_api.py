@@ -309,3 +309,9 @@ def test_reductions_follow_the_tickers():
         assert np.array_equal(o["w"].on_host(), o2["w"].on_host())       # same trajectory, same dt history
     finally:
         os.chdir(cwd)
+
+
+def test_pentadiagonal_fourth_order_solve():
+    import host_cases as hc
+    worst, r2, r4 = hc.pentadiagonal_solve()
+    assert worst < 1e-12

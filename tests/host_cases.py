@@ -216,3 +216,98 @@ def trig_bases(tol=1e-12):
           + 3.0 * np.sin(2 * pi * Z),
           {(1, 1): 1.0, (-1, 1): 1.0, (0, 2): 3.0, (3, 2): 2.0, (-3, 2): 2.0})            # :236-262
     return worst
+
+
+def pentadiagonal_solve(nx=32, nz=96):
+    """4th-order (pentadiagonal) Laplacian solve, SURVEY 8f-3 (extension, parity unpinned):
+    (1) the device solution of A x = b against a long-double banded solve of the same matrices
+        (LaplacianSolver.laps), random complex right-hand sides;
+    (2) A @ solve(b) == b with the host matrices;
+    (3) convergence: psi'' - k^2 psi = f with a smooth exact solution, the error falls ~16x per halving of dz
+        where the tridiagonal solve falls ~4x."""
+    import contextlib
+    import io
+    from melvin import ArrayFactory, BasisFunctions, LaplacianSolver, Parameters
+    CE, FDM = BasisFunctions.COMPLEX_EXP, BasisFunctions.FDM
+
+    def make(nz_, order):
+        p = Parameters({"nx": nx, "nz": nz_, "lx": 2.0, "lz": 1.0, "final_time": 1.0,
+                        "discretisation": ["spectral", "fdm"], "laplacian_order": order}, validate=False)
+        af = ArrayFactory(p, xp)
+        with contextlib.redirect_stdout(io.StringIO()):
+            return p, LaplacianSolver(p, xp, [CE, FDM], array_factory=af)
+
+    p, solver = make(nz, 4)
+    rng = np.random.default_rng(7)
+    rhs = rng.standard_normal(p.spectral_shape) + 1j * rng.standard_normal(p.spectral_shape)
+    got = solver.solve(xp.array(rhs)).get()
+    laps = solver.laps
+    worst = 0.0
+    for n, A in enumerate(laps):
+        Ad = np.asarray(A.todense()).real.astype(np.longdouble)
+        # Gaussian elimination without pivoting in long double (the operator is negative definite)
+        M = Ad.copy()
+        b = rhs[n].astype(np.clongdouble)
+        for i in range(nz):
+            for r in range(i + 1, min(i + 3, nz)):
+                if M[r, i] != 0:
+                    f = M[r, i] / M[i, i]
+                    M[r, i:i + 3] -= f * M[i, i:i + 3]
+                    b[r] -= f * b[i]
+        x = np.zeros(nz, dtype=np.clongdouble)
+        for i in range(nz - 1, -1, -1):
+            x[i] = (b[i] - sum(M[i, j] * x[j] for j in range(i + 1, min(i + 3, nz)))) / M[i, i]
+        err = np.linalg.norm((got[n] - x).astype(complex)) / np.linalg.norm(x.astype(complex))
+        res = np.linalg.norm(A @ got[n] - rhs[n]) / np.linalg.norm(rhs[n])
+        worst = max(worst, float(err))
+        assert err < 1e-12 and res < 1e-11, (n, float(err), float(res))
+    # convergence on psi = sin(3 pi z) + z^2 (1-z) + 1/2 with Dirichlet values given on the boundary rows
+    errs = {2: [], 4: []}
+    for order in (2, 4):
+        for nzc in (65, 129, 257):
+            pc_, sc = make(nzc, order)
+            z = np.arange(nzc) * pc_.dz                # the grid the stencils assume (dz = lz / nz)
+            kx0 = abs(1j * 2 * np.pi / pc_.lx)
+            psi = np.sin(3 * np.pi * z) + z ** 2 * (1 - z) + 0.5
+            d2 = -(3 * np.pi) ** 2 * np.sin(3 * np.pi * z) + 2 - 6 * z
+            b = np.zeros(pc_.spectral_shape, complex)
+            for n in range(pc_.nn):
+                b[n] = d2 - (n * kx0) ** 2 * psi
+                b[n, 0], b[n, -1] = psi[0], psi[-1]
+            sol = sc.solve(xp.array(b)).get()
+            errs[order].append(np.abs(sol - psi[None, :]).max())
+    rate2 = np.log2(errs[2][0] / errs[2][2]) / 2
+    rate4 = np.log2(errs[4][0] / errs[4][2]) / 2
+    assert 1.8 < rate2 < 2.3, (rate2, errs[2])
+    assert rate4 > 2.9 and errs[4][2] < errs[2][2] / 20, (rate4, errs)
+    return worst, rate2, rate4
+
+
+def pentadiagonal_residual(nx, nz):
+    """Large grids: residual of the pentadiagonal solve on a sample of x modes against a banded
+    product built with numpy (long double), random right-hand sides."""
+    import contextlib
+    import io
+    from melvin import ArrayFactory, BasisFunctions, LaplacianSolver, Parameters
+    CE, FDM = BasisFunctions.COMPLEX_EXP, BasisFunctions.FDM
+    p = Parameters({"nx": nx, "nz": nz, "lx": 2.44, "lz": 1.0, "final_time": 1.0,
+                    "discretisation": ["spectral", "fdm"], "laplacian_order": 4}, validate=False)
+    af = ArrayFactory(p, xp)
+    with contextlib.redirect_stdout(io.StringIO()):
+        solver = LaplacianSolver(p, xp, [CE, FDM], array_factory=af)
+    rng = np.random.default_rng(11)
+    rhs = rng.standard_normal(p.spectral_shape) + 1j * rng.standard_normal(p.spectral_shape)
+    x = solver.solve(xp.array(rhs)).get().astype(np.clongdouble)
+    h2 = np.longdouble(p.dz) ** 2
+    kx0 = np.longdouble(abs(1j * 2 * np.pi / p.lx))
+    for n in sorted(set([0, 1, p.nn // 3, p.nn - 1])):
+        k2 = (n * kx0) ** 2
+        v = x[n]
+        Ax = np.empty(nz, dtype=np.clongdouble)
+        Ax[0], Ax[-1] = v[0], v[-1]
+        Ax[1] = (v[0] - 2 * v[1] + v[2]) / h2 - k2 * v[1]
+        Ax[-2] = (v[-3] - 2 * v[-2] + v[-1]) / h2 - k2 * v[-2]
+        Ax[2:-2] = (-v[4:] / 12 + 4 * v[3:-1] / 3 - 5 * v[2:-2] / 2 + 4 * v[1:-3] / 3 - v[:-4] / 12) / h2 - k2 * v[2:-2]
+        res = np.linalg.norm((Ax - rhs[n]).astype(complex)) / np.linalg.norm(rhs[n])
+        # the solution is rounded to double: A amplifies that by ~ 1/dz^2
+        assert res < 20 * 1.1e-16 * nz ** 2, (n, float(res))

