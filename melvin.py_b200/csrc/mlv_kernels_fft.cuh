@@ -806,6 +806,113 @@ k_xfwd(const XFwdArgs a) {
     }
 }
 
+// ---- specialised forward x pass of the single-scalar step (Kelvin-Helmholtz / Taylor-Green loop,
+// examples/kelvin_helmholtz_instability.py:115-131): one GPU, two operands (d/dx by the order-2
+// stencil, d/dz by its symbol), staged stencil operand, no extra linear terms, AB2 + theta-scheme with
+// the symbolic Laplacian.  Same arithmetic, in the same order, as the generic k_xfwd<.., 1> on that
+// path; everything the generic kernel decides at run time is fixed here, which frees enough
+// registers for UN epilogue outputs per trip (fewer exposed load round trips).
+template <int LOG2N, int C, int UN>
+__global__ void __launch_bounds__(C * FftCfg<LOG2N>::T, (C * FftCfg<LOG2N>::T <= 256) ? 2 : 1)
+k_xfwd_scalar(const XFwdArgs a) {
+    typedef FftCfg<LOG2N> F;
+    constexpr int NF = F::N;
+    const int c = threadIdx.x % C, tau = threadIdx.x / C;
+    const int mreal = blockIdx.x * C + c;
+    const bool valid = mreal < a.nm;
+    const int m = valid ? mreal : a.nm - 1;
+    XchgFull<C> xc;
+    cplx* const xbase = reinterpret_cast<cplx*>(MLV_SMEM_BASE());
+    xc.buf = xbase;
+    xc.c = c;
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(xbase + (size_t)F::XSLOTS * C);
+    if (threadIdx.x == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(bar, (unsigned)(NF * C * sizeof(cplx)));
+        bulk_load(xbase, a.src[0] + (size_t)blockIdx.x * NF * C, (unsigned)(NF * C * sizeof(cplx)), bar);
+    }
+    {   // L2 prefetch: second operand of this tile, first operand of the CTA that follows on the SM,
+        // the state / history columns of the epilogue
+        constexpr unsigned CHUNK = 16384;
+        constexpr unsigned BLOCK = (unsigned)NF * C * (unsigned)sizeof(cplx);
+        constexpr int NCH = (int)(BLOCK / CHUNK) > 0 ? (int)(BLOCK / CHUNK) : 1;
+        const int t = threadIdx.x;
+        if (t < 2 * NCH) {
+            const int f = t / NCH, ch = t % NCH;
+            const unsigned bytes = BLOCK < CHUNK ? BLOCK : CHUNK;
+            if (f > 0)
+                l2_prefetch_bulk(reinterpret_cast<const char*>(a.src[1] + (size_t)blockIdx.x * NF * C) + (size_t)ch * CHUNK, bytes);
+            else if ((int)(blockIdx.x + a.wave) < (int)gridDim.x)
+                l2_prefetch_bulk(reinterpret_cast<const char*>(a.src[0] + (size_t)(blockIdx.x + a.wave) * NF * C) + (size_t)ch * CHUNK, bytes);
+        }
+        const int rows = 2 * a.nn + 1;
+        for (int r = t; r < rows; r += C * F::T) {
+            const size_t idx = (size_t)r * a.spitch + blockIdx.x * C;
+            l2_prefetch_line(a.integ.q_in + idx);
+            l2_prefetch_line(a.integ.fm1 + idx);
+        }
+    }
+    const double w1 = 0.5 * a.rdx;
+    const double ci = a.symz[m] * a.coef[1], cw = a.coef[0] * w1;
+    const cplx* __restrict__ srcb = a.src[1] + (size_t)blockIdx.x * NF * C + c;
+    cplx v[16];
+    MLV_UNROLL
+    for (int j = 0; j < 16; ++j) {
+        const cplx b = srcb[(size_t)(tau + F::T * j) * C];
+        v[j] = mk(fma(-ci, b.y, 0.0), fma(ci, b.x, 0.0));
+    }
+    mbar_wait(bar, 0);
+    MLV_UNROLL
+    for (int j = 0; j < 16; ++j) {
+        const int x = tau + F::T * j;
+        const cplx p = xbase[(size_t)((x + 1) & (NF - 1)) * C + c];
+        const cplx q = xbase[(size_t)((x - 1) & (NF - 1)) * C + c];
+        v[j] = mk(fma(cw, p.x - q.x, v[j].x), fma(cw, p.y - q.y, v[j].y));
+    }
+    MLV_SCHED_FENCE();
+    fft_line<LOG2N, false>(v, tau, a.tw, xc);
+    if (!valid) return;
+    // ---- epilogue from registers (Integrator.py:5-18 AB2, :58-63 theta-scheme with L = lcoef * lap)
+    const double h = a.integ.dt / 2;
+    const double c1 = (1 - a.integ.alpha) * a.integ.dt, c2 = a.integ.alpha * a.integ.dt;
+    // the 12 registers that can hold retained modes: i = 0..11 -> j = 0..5, 10..15
+    MLV_UNROLL
+    for (int i0 = 0; i0 < 12; i0 += UN) {
+        cplx q[UN], f1[UN];
+        size_t idx[UN];
+        int nmode[UN];
+        bool ok[UN];
+        MLV_SCHED_FENCE();
+        const int tq = opaque_int(tau);
+        MLV_UNROLL
+        for (int u = 0; u < UN; ++u) {
+            const int j = (i0 + u) < 6 ? (i0 + u) : (i0 + u) + 4;
+            int r = 0, n = 0;
+            ok[u] = xrow_static<NF>(j, tq + F::T * j, a.nn, r, n);
+            nmode[u] = n;
+            idx[u] = ok[u] ? (size_t)r * a.spitch + m : (size_t)m;
+        }
+        MLV_UNROLL
+        for (int u = 0; u < UN; ++u) {
+            q[u] = a.integ.q_in[idx[u]];
+            f1[u] = a.integ.fm1[idx[u]];
+        }
+        MLV_UNROLL
+        for (int u = 0; u < UN; ++u) {
+            if (!ok[u]) continue;
+            const int j = (i0 + u) < 6 ? (i0 + u) : (i0 + u) + 4;
+            const cplx f0 = cadd(cscale(v[j], a.scale), mk(0.0, 0.0));      // (+ the empty sum of linear terms)
+            a.integ.f0[idx[u]] = f0;
+            const cplx inc = mk(h * (3 * f0.x - f1[u].x), h * (3 * f0.y - f1[u].y));
+            const double L = a.integ.lcoef * lap_symbol(nmode[u], m, a.k);
+            const double aa = 1 + c1 * L;
+            const double rb = fast_rcp(1 - c2 * L);
+            a.integ.q_out[idx[u]] = mk((aa * q[u].x + inc.x) * rb, (aa * q[u].y + inc.y) * rb);
+        }
+    }
+}
+
 // NaN-propagating maximum (numpy.max semantics)
 MLV_DEV double nan_max(double x, double y) { return (x != x || y != y) ? NAN : fmax(x, y); }
 
@@ -1075,7 +1182,8 @@ struct ZAdvArgs {
 // RED = false: no ticker reads the reductions of this step (mlv_set_reductions): the maxima / sums
 // and their shared-memory tree are compiled out (a run-time test instead costs registers this
 // kernel does not have: spills 88 -> 324 bytes, 0.255 -> 0.270 ms)
-template <int LOG2N, int LPC, bool RED>
+// SHARDED = false: one rank, one row block (the single-GPU step): no owner look-ups, contiguous rows
+template <int LOG2N, int LPC, bool RED, bool SHARDED>
 __global__ void __launch_bounds__(LPC * FftCfg<LOG2N>::T, (LPC * FftCfg<LOG2N>::T <= 256) ? 2 : 1)
 k_z_advect(const ZAdvArgs a) {
     typedef FftCfg<LOG2N> F;
@@ -1094,12 +1202,12 @@ k_z_advect(const ZAdvArgs a) {
                                              (size_t)LPC * F::N * sizeof(cplx));
     const size_t rowoff = (size_t)(2 * rp) * a.ipitch;
     const int cts = log2_pow2(a.ct);                 // tile width is a power of two
-    const bool sharded = a.sh.fwd_chunk != 0;
-    wait_arrivals(a.wait_counter, a.wait_expect);
+    constexpr bool sharded = SHARDED;
+    if constexpr (SHARDED) wait_arrivals(a.wait_counter, a.wait_expect);
 
     // announce the rows of the two velocity components (needed one and two transforms
     // from now) and the scalar rows of the CTA that will follow this one on the SM
-    if (tau < 6 && a.sh.nml >= a.nm) {           // rows are contiguous only when unsharded
+    if (tau < 6 && (!SHARDED || a.sh.nml >= a.nm)) {           // rows are contiguous only when unsharded
         const unsigned rowbytes = (unsigned)a.nm * (unsigned)sizeof(cplx);
         if (tau < 4) {
             l2_prefetch_bulk((tau < 2 ? a.Iux : a.Iuz) + rowoff + (size_t)(tau & 1) * a.ipitch, rowbytes);
@@ -1113,7 +1221,7 @@ k_z_advect(const ZAdvArgs a) {
     cplx v[16];
     {   // q -> physical, parked in the thread-private stash
         const cplx* rowA = a.Iq + rowoff;
-        zpair_load_line<LOG2N>(v, rowA, rowA + a.ipitch, tau, a.nm, a.sh);
+        zpair_load_line_<LOG2N, SHARDED>(v, rowA, rowA + a.ipitch, tau, a.nm, a.sh);
         fft_line<LOG2N, true>(v, tau, a.tw, xc);
         MLV_UNROLL
         for (int j = 0; j < 16; ++j) stash[j * F::T] = v[j];
@@ -1122,7 +1230,7 @@ k_z_advect(const ZAdvArgs a) {
         MLV_SCHED_FENCE();
         {
             const cplx* src = (pass == 0 ? a.Iux : a.Iuz) + rowoff;
-            zpair_load_line<LOG2N>(v, src, src + a.ipitch, tau, a.nm, a.sh);
+            zpair_load_line_<LOG2N, SHARDED>(v, src, src + a.ipitch, tau, a.nm, a.sh);
         }
         MLV_SCHED_FENCE();
         fft_line<LOG2N, true>(v, tau, a.tw, xc);
@@ -1169,9 +1277,13 @@ k_z_advect(const ZAdvArgs a) {
                         cplx A, B;
                         zpair_unpack(v[j], (kk == 0) ? v[j] : P[u], A, B);
                         const int t = kk >> cts;
-                        int h = 0, tl = t;                                       // tile owner
-                        if (sharded) { h = t / a.sh.tpr; tl = t - h * a.sh.tpr; }
-                        cplx* o = a.out.blk[h] + foff + fwd_store_off(2 * rp, tl, kk & (a.ct - 1), a.ct, a.sh);
+                        cplx* o;
+                        if constexpr (sharded) {
+                            const int h = t / a.sh.tpr, tl = t - h * a.sh.tpr;       // tile owner
+                            o = a.out.blk[h] + foff + fwd_store_off(2 * rp, tl, kk & (a.ct - 1), a.ct, a.sh);
+                        } else {                                                 // [tile][nx][ct]
+                            o = a.IA + foff + ((((size_t)t) << a.sh.fwd_rshift) + (size_t)(2 * rp)) * a.ct + (kk & (a.ct - 1));
+                        }
                         o[0] = A;
                         o[a.ct] = B;                               // row 2rp+1
                     }
