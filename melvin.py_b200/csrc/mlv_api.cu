@@ -486,7 +486,9 @@ static int launch_xfwd(mlv_ctx* c, XFwdArgs& a) {
 #define MLV_XFWD_GO(UN_)                                                                  \
         do {                                                                              \
             auto kh = k_xfwd_scalar<L, C, UN_>;                                           \
-            MLV_LAUNCH(kh, grid, (unsigned)(C * F::T), smem, c->stream, a);               \
+            unsigned g_ = grid;                                                           \
+            if (rt_env_flag("MLV_XFWD_PERSISTENT") && g_ > (unsigned)a.wave) g_ = (unsigned)a.wave; \
+            MLV_LAUNCH(kh, g_, (unsigned)(C * F::T), smem, c->stream, a);                 \
         } while (0)
         MLV_XFWD_GO(4);        // 2, 3, 4, 6 outputs per trip measure the same (0.1254 .. 0.1259 ms)
 #undef MLV_XFWD_GO

@@ -818,51 +818,61 @@ k_xfwd_scalar(const XFwdArgs a) {
     typedef FftCfg<LOG2N> F;
     constexpr int NF = F::N;
     const int c = threadIdx.x % C, tau = threadIdx.x / C;
-    const int mreal = blockIdx.x * C + c;
-    const bool valid = mreal < a.nm;
-    const int m = valid ? mreal : a.nm - 1;
     XchgFull<C> xc;
     cplx* const xbase = reinterpret_cast<cplx*>(MLV_SMEM_BASE());
     xc.buf = xbase;
     xc.c = c;
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(xbase + (size_t)F::XSLOTS * C);
-    if (threadIdx.x == 0) mbar_init(bar, 1);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        mbar_expect_tx(bar, (unsigned)(NF * C * sizeof(cplx)));
-        bulk_load(xbase, a.src[0] + (size_t)blockIdx.x * NF * C, (unsigned)(NF * C * sizeof(cplx)), bar);
-    }
-    {   // L2 prefetch: second operand of this tile, first operand of the CTA that follows on the SM,
-        // the state / history columns of the epilogue
+    const int ntiles = (a.nm + C - 1) / C;
+    const bool persistent = gridDim.x != (unsigned)ntiles;
+    auto stage_fetch = [&](int tile) {
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(bar, (unsigned)(NF * C * sizeof(cplx)));
+            bulk_load(xbase, a.src[0] + (size_t)tile * NF * C, (unsigned)(NF * C * sizeof(cplx)), bar);
+        }
+    };
+    // L2 prefetch of what tile `tl` needs beyond its staged operand: the second operand (unless
+    // `first_only`) and the state / history columns of its epilogue; `first_only`: the staged operand
+    auto announce = [&](int tl, bool first_only) {
         constexpr unsigned CHUNK = 16384;
         constexpr unsigned BLOCK = (unsigned)NF * C * (unsigned)sizeof(cplx);
         constexpr int NCH = (int)(BLOCK / CHUNK) > 0 ? (int)(BLOCK / CHUNK) : 1;
         const int t = threadIdx.x;
-        if (t < 2 * NCH) {
-            const int f = t / NCH, ch = t % NCH;
-            const unsigned bytes = BLOCK < CHUNK ? BLOCK : CHUNK;
-            if (f > 0)
-                l2_prefetch_bulk(reinterpret_cast<const char*>(a.src[1] + (size_t)blockIdx.x * NF * C) + (size_t)ch * CHUNK, bytes);
-            else if ((int)(blockIdx.x + a.wave) < (int)gridDim.x)
-                l2_prefetch_bulk(reinterpret_cast<const char*>(a.src[0] + (size_t)(blockIdx.x + a.wave) * NF * C) + (size_t)ch * CHUNK, bytes);
-        }
+        const unsigned bytes = BLOCK < CHUNK ? BLOCK : CHUNK;
+        if (t < NCH)
+            l2_prefetch_bulk(reinterpret_cast<const char*>(a.src[first_only ? 0 : 1] + (size_t)tl * NF * C) + (size_t)t * CHUNK, bytes);
+        if (first_only) return;
         const int rows = 2 * a.nn + 1;
         for (int r = t; r < rows; r += C * F::T) {
-            const size_t idx = (size_t)r * a.spitch + blockIdx.x * C;
+            const size_t idx = (size_t)r * a.spitch + (size_t)tl * C;
             l2_prefetch_line(a.integ.q_in + idx);
             l2_prefetch_line(a.integ.fm1 + idx);
         }
+    };
+    if (threadIdx.x == 0) mbar_init(bar, 1);
+    __syncthreads();
+    stage_fetch((int)blockIdx.x);
+    announce((int)blockIdx.x, false);
+    unsigned phase = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int mreal = tile * C + c;
+    const bool valid = mreal < a.nm;
+    const int m = valid ? mreal : a.nm - 1;
+    {
+        const int nxt = persistent ? tile + (int)gridDim.x : tile + a.wave;
+        if (nxt < ntiles) announce(nxt, !persistent);      // resident CTAs: everything of their next tile
     }
     const double w1 = 0.5 * a.rdx;
     const double ci = a.symz[m] * a.coef[1], cw = a.coef[0] * w1;
-    const cplx* __restrict__ srcb = a.src[1] + (size_t)blockIdx.x * NF * C + c;
+    const cplx* __restrict__ srcb = a.src[1] + (size_t)tile * NF * C + c;
     cplx v[16];
     MLV_UNROLL
     for (int j = 0; j < 16; ++j) {
         const cplx b = srcb[(size_t)(tau + F::T * j) * C];
         v[j] = mk(fma(-ci, b.y, 0.0), fma(ci, b.x, 0.0));
     }
-    mbar_wait(bar, 0);
+    mbar_wait(bar, phase);
+    phase ^= 1;
     MLV_UNROLL
     for (int j = 0; j < 16; ++j) {
         const int x = tau + F::T * j;
@@ -872,7 +882,11 @@ k_xfwd_scalar(const XFwdArgs a) {
     }
     MLV_SCHED_FENCE();
     fft_line<LOG2N, false>(v, tau, a.tw, xc);
-    if (!valid) return;
+    if (tile + (int)gridDim.x < ntiles) {
+        __syncthreads();                                  // the transform has left the buffer
+        stage_fetch(tile + (int)gridDim.x);               // travels during the epilogue
+    }
+    if (!valid) continue;
     // ---- epilogue from registers (Integrator.py:5-18 AB2, :58-63 theta-scheme with L = lcoef * lap)
     const double h = a.integ.dt / 2;
     const double c1 = (1 - a.integ.alpha) * a.integ.dt, c2 = a.integ.alpha * a.integ.dt;
@@ -910,6 +924,7 @@ k_xfwd_scalar(const XFwdArgs a) {
             const double rb = fast_rcp(1 - c2 * L);
             a.integ.q_out[idx[u]] = mk((aa * q[u].x + inc.x) * rb, (aa * q[u].y + inc.y) * rb);
         }
+    }
     }
 }
 
