@@ -456,13 +456,16 @@ static int launch_zadv_real(mlv_ctx* c, ZAdvArgs& a, unsigned& grid_out) {
     if (rc) return rc;
     a.red = c->red_on ? (c->red_user ? c->red_user : c->red) + (size_t)(a.row0 / a.nrows) * grid * 4 : nullptr;
     a.wave = 148;
-    if (a.red) {
-        auto kfn = k_zr_advect<L, true>;
-        MLV_LAUNCH(kfn, grid, (unsigned)F::T, smem, c->stream, a);
-    } else {
-        auto kfn = k_zr_advect<L, false>;
-        MLV_LAUNCH(kfn, grid, (unsigned)F::T, smem, c->stream, a);
-    }
+    const bool single = c->nranks == 1 && a.sh.fwd_chunk == 0 && a.sh.inv_chunk == 0 && (1 << a.sh.fwd_rshift) == a.nx &&
+                        !rt_env_flag("MLV_ZADV_GENERIC");
+#define MLV_ZR_GO(RED_, SH_)                                                             \
+    do {                                                                                  \
+        auto kfn = k_zr_advect<L, RED_, SH_>;                                             \
+        MLV_LAUNCH(kfn, grid, (unsigned)F::T, smem, c->stream, a);                        \
+    } while (0)
+    if (a.red) { if (single) MLV_ZR_GO(true, false); else MLV_ZR_GO(true, true); }
+    else { if (single) MLV_ZR_GO(false, false); else MLV_ZR_GO(false, true); }
+#undef MLV_ZR_GO
     return 0;
 }
 

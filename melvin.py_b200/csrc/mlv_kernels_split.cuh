@@ -244,7 +244,7 @@ k_zr_r2c(const ZRealArgs a) {
 
 // fused physical-space stage of Variable.vec_dot_nabla (see k_z_advect), one real row per CTA.
 // Shared memory: [ XSLOTS doubles exchange | H cplx thread-private stash | 4*T doubles ].
-template <int LOG2H, bool RED>
+template <int LOG2H, bool RED, bool SHARDED>
 __global__ void __launch_bounds__(FftCfg<LOG2H>::T, (FftCfg<LOG2H>::T <= 256) ? 2 : 1)
 k_zr_advect(const ZAdvArgs a) {
     typedef FftCfg<LOG2H> F;
@@ -259,16 +259,15 @@ k_zr_advect(const ZAdvArgs a) {
                                              (size_t)F::N * sizeof(cplx));
     const size_t rowoff = (size_t)x * a.ipitch;
     const int cts = log2_pow2(a.ct);
-    const bool sharded = a.sh.fwd_chunk != 0;
-    wait_arrivals(a.wait_counter, a.wait_expect);
+    if constexpr (SHARDED) wait_arrivals(a.wait_counter, a.wait_expect);
 
     cplx v[16];
-    zreal_load_line<LOG2H>(v, a.Iq + rowoff, a.tws, tau, a.nm, a.sh);
+    zreal_load_line_<LOG2H, SHARDED>(v, a.Iq + rowoff, a.tws, tau, a.nm, a.sh);
     fft_line<LOG2H, true>(v, tau, a.tw, xc);
     MLV_UNROLL
     for (int j = 0; j < 16; ++j) stash[j * F::T] = v[j];
     for (int pass = 0; pass < 2; ++pass) {        // pass 0: A = ux q, pass 1: B = uz q
-        zreal_load_line<LOG2H>(v, (pass == 0 ? a.Iux : a.Iuz) + rowoff, a.tws, tau, a.nm, a.sh);
+        zreal_load_line_<LOG2H, SHARDED>(v, (pass == 0 ? a.Iux : a.Iuz) + rowoff, a.tws, tau, a.nm, a.sh);
         fft_line<LOG2H, true>(v, tau, a.tw, xc);
         if constexpr (RED) {
             double mx = -INFINITY, ss = 0.0;
@@ -292,9 +291,12 @@ k_zr_advect(const ZAdvArgs a) {
         const size_t foff = (size_t)a.outoff[pass];
         zreal_unpack<LOG2H>(v, tau, a.nm, a.tws, xc.buf, [&](int k, cplx X) {
             const int t = k >> cts;
-            int h = 0, tl = t;
-            if (sharded) { h = t / a.sh.tpr; tl = t - h * a.sh.tpr; }
-            a.out.blk[h][foff + fwd_store_off(x, tl, k & (a.ct - 1), a.ct, a.sh)] = X;
+            if constexpr (SHARDED) {
+                const int h = t / a.sh.tpr, tl = t - h * a.sh.tpr;
+                a.out.blk[h][foff + fwd_store_off(x, tl, k & (a.ct - 1), a.ct, a.sh)] = X;
+            } else {                                                     // [tile][nx][ct]
+                a.IA[foff + ((((size_t)t) << a.sh.fwd_rshift) + (size_t)x) * a.ct + (k & (a.ct - 1))] = X;
+            }
         });
     }
     // ---- reductions: per-CTA partials (deterministic two-stage reduction)

@@ -311,6 +311,9 @@ class ShardedScalarStepper:
         ctx, vp = self.ctx, ctypes.c_void_p
         chunked = self.mode == "dma" or not (self.world == 1 or self.p2p)
         works = []
+        # the z stage computes its CFL / energy partials only on the steps whose tickers read them
+        ctx.want_reductions = any(job[5] is not None for job in jobs)
+        ctx.sync_reduction_mode()
         for (sux, suz, sq, fa, fb, red) in jobs:
             args = (vp(self._slot(0, True, sux)), vp(self._slot(0, True, suz)), vp(self._slot(0, True, sq)),
                     vp(self._slot(1, False, fa)), vp(self._slot(1, False, fb)))
@@ -417,6 +420,8 @@ class ShardedScalarStepper:
         wp = w_in.data_ptr()
         # the four reductions are combined only on the steps whose tickers read them
         redp = self._redp if self._tickers_due() else None
+        ctx.want_reductions = redp is not None         # (the z stage skips its partials otherwise)
+        ctx.sync_reduction_mode()
         if self.mode == "dma":
             # one launch per field; the copies of field f (row block h -> rank h) run on the copy
             # engines while the x pass of field f+1 runs on the SMs
