@@ -24,7 +24,7 @@ def run_world(n, case, port, **extra_env):
     assert out.returncode == 0 and lines and lines[-1].endswith("OK"), out.stdout[-2000:] + out.stderr[-2000:]
 
 
-@pytest.mark.parametrize("world", [1, 2, 4])
+@pytest.mark.parametrize("world", [2, 4])          # (world 1: test_multi_field_steppers[ddc-1])
 def test_taylor_green_sharded_matches_reference_golden(world):
     subprocess.run(["sh", os.path.join(ROOT, "tests", "emu", "build_emu.sh")], check=True,
                    capture_output=True)
@@ -40,7 +40,7 @@ def test_long_line_kernels_sharded():
     run_world(2, "khlong", 29612)
 
 
-@pytest.mark.parametrize("case", ["kh", "khlong", "tearing"])
+@pytest.mark.parametrize("case", ["khlong", "tearing"])
 def test_forward_exchange_in_row_blocks(case):
     """forward buffers cut into row blocks, z stage launched block by block (the layout the
     copy-engine exchange pipelines on GPUs)"""
@@ -59,8 +59,7 @@ def test_bench_multi_gpu_host_logic():
     run_world(2, "bench", 29631)
 
 
-@pytest.mark.parametrize("case,world", [("api_tg", 2), ("api_tg", 4), ("api_ddc", 2), ("api_tearing", 2),
-                                        ("api_tearing", 4)])
+@pytest.mark.parametrize("case,world", [("api_tg", 4), ("api_ddc", 2), ("api_tearing", 2)])
 def test_public_api_shards_itself(case, world):
     """N4: the UNCHANGED loops of tests/parity_cases.py (Simulation / Variable / Integrator API)
     under a process group: the package decomposes the fields into slabs itself (melvin/_dist.py),
