@@ -321,4 +321,15 @@ __global__ void __launch_bounds__(256) k_reduce_final4(const double* partial, in
     if (threadIdx.x == 0) out[w] = sm[0];
 }
 
+// contiguous block -> (peer-mapped) destination with coalesced 16-byte accesses, four in flight per thread
+__global__ void __launch_bounds__(512) k_peer_copy(cplx* __restrict__ dst, const cplx* __restrict__ src, size_t n) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n; i += 4 * stride) {
+        const cplx a = src[i], b = src[i + stride], c = src[i + 2 * stride], d = src[i + 3 * stride];
+        dst[i] = a; dst[i + stride] = b; dst[i + 2 * stride] = c; dst[i + 3 * stride] = d;
+    }
+    for (; i < n; i += stride) dst[i] = src[i];
+}
+
 }  // namespace mlv

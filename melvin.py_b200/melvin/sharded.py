@@ -125,7 +125,10 @@ class ShardedScalarStepper:
             self._sync = _backend.zeros((1,), np.float64)
             # several copy streams: copies to different peers run on different copy engines
             ncs = int(os.environ.get("MLV_COPY_STREAMS", "4"))
-            self._copy_streams = [torch.cuda.Stream() for _ in range(max(1, min(ncs, self.world)))]
+            # (copies done by CTAs, MLV_COPY_CTAS: high-priority streams, so that they get the next free
+            # SM slot instead of queueing behind a whole transform kernel)
+            prio = -1 if int(os.environ.get("MLV_COPY_CTAS", "0") or 0) > 0 else 0
+            self._copy_streams = [torch.cuda.Stream(priority=prio) for _ in range(max(1, min(ncs, self.world)))]
             self._ev = [torch.cuda.Event() for _ in range(6)]
             self._join_ev = [torch.cuda.Event() for _ in self._copy_streams]
         else:
