@@ -606,15 +606,20 @@ template <int L>
 static int launch_x1d_advect(mlv_ctx* c, X1dAdvArgs& a, unsigned& grid_out) {
     constexpr int C = xcols(L);
     typedef FftCfg<L> F;
-    auto kfn = k_x1d_advect<L, C>;
     const size_t smem = (size_t)F::XSLOTS * C * sizeof(double) + (size_t)F::N * C * sizeof(cplx) +
                         (size_t)4 * C * F::T * sizeof(double);
     const unsigned grid = (unsigned)(((a.nz + 1) / 2 + C - 1) / C);
     grid_out = grid;
     int rc = ensure_red(c, (size_t)grid * 4);
     if (rc) return rc;
-    a.red = c->red_user ? c->red_user : c->red;
-    MLV_LAUNCH(kfn, grid, (unsigned)(C * F::T), smem, c->stream, a);
+    a.red = c->red_on ? (c->red_user ? c->red_user : c->red) : nullptr;
+    if (a.red) {
+        auto kfn = k_x1d_advect<L, C, true>;
+        MLV_LAUNCH(kfn, grid, (unsigned)(C * F::T), smem, c->stream, a);
+    } else {                                        // no ticker reads the reductions of this step
+        auto kfn = k_x1d_advect<L, C, false>;
+        MLV_LAUNCH(kfn, grid, (unsigned)(C * F::T), smem, c->stream, a);
+    }
     return 0;
 }
 
@@ -1275,7 +1280,7 @@ int mlv_fdm_advect(mlv_ctx* c, const void* uxh, const void* uzh, const void* q, 
     MLV_SWITCH_LOG2(c->log2nx, MLV_GO)
 #undef MLV_GO
     if (rc) return rc;
-    c->red_count = (int)grid;
+    c->red_count = a.red ? (int)grid : 0;
     if (red4) return mlv_reduce_partials(c, nullptr, red4);
     return MLV_OK;
 }

@@ -482,7 +482,7 @@ MLV_DEV void x1d_load_line(cplx (&v)[16], const cplx* __restrict__ S, int tau_, 
     }
 }
 
-template <int LOG2N, int C>
+template <int LOG2N, int C, bool RED>
 __global__ void __launch_bounds__(C * FftCfg<LOG2N>::T, (C * FftCfg<LOG2N>::T <= 256) ? 2 : 1)
 k_x1d_advect(const X1dAdvArgs a) {
     typedef FftCfg<LOG2N> F;
@@ -510,7 +510,7 @@ k_x1d_advect(const X1dAdvArgs a) {
         x1d_load_line<LOG2N>(v, pass == 0 ? a.uxh : a.uzh, tau, a.nn, a.nz, zl, valid, has2);
         MLV_SCHED_FENCE();
         fft_line<LOG2N, true>(v, tau, a.tw, xc);
-        {
+        if constexpr (RED) {
             double mx = -INFINITY, ss = 0.0;
             MLV_UNROLL
             for (int j = 0; j < 16; ++j) {
@@ -521,6 +521,12 @@ k_x1d_advect(const X1dAdvArgs a) {
             }
             rbuf[pass * NT + threadIdx.x] = valid ? (ss != ss ? NAN : mx) : -INFINITY;
             rbuf[(2 + pass) * NT + threadIdx.x] = valid ? ss : 0.0;
+        } else {                                 // no ticker reads the reductions of this step
+            MLV_UNROLL
+            for (int j = 0; j < 16; ++j) {
+                const cplx q = stash[j * NT];
+                v[j] = mk(v[j].x * q.x, v[j].y * q.y);
+            }
         }
         fft_line<LOG2N, false>(v, tau, a.tw, xc);
         __syncthreads();
@@ -547,6 +553,7 @@ k_x1d_advect(const X1dAdvArgs a) {
         }
     }
     // ---- reductions: per-CTA partials
+    if constexpr (RED) {
     __syncthreads();
     {
         constexpr int G = NT / 4 > 0 ? NT / 4 : 1;
@@ -564,6 +571,7 @@ k_x1d_advect(const X1dAdvArgs a) {
             }
         }
         if (w < 4 && g == 0) a.red[(size_t)blockIdx.x * 4 + w] = rbuf[w * NT];
+    }
     }
 }
 

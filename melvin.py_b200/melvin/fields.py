@@ -407,13 +407,17 @@ class Variable:
         ia, ib = ctx.take_i(), ctx.take_i()
         if uxo._red_part is None:
             uxo._red_part = _backend.empty((ctx.red_doubles,), np.float64)
+        reduced = ctx.sync_reduction_mode()
         ctx.call("mlv_set_reduction_partials", vp(uxo._red_part.data_ptr()), count=False)
         ctx.call("mlv_fdm_advect", vp(uxo._i_def[1]._t.data_ptr()), vp(uzo._i_def[1]._t.data_ptr()),
                  vp(self._i_def[1]._t.data_ptr()), vp(ia.data_ptr()), vp(ib.data_ptr()), None)
         ctx.call("mlv_set_reduction_partials", None, count=False)
-        shared = {"part": uxo._red_part, "host": None}
-        uxo._red = (shared, 0, 2)
-        uzo._red = (shared, 1, 3)
+        if reduced:
+            shared = {"part": uxo._red_part, "host": None}
+            uxo._red = (shared, 0, 2)
+            uzo._red = (shared, 1, 3)
+        else:
+            uxo._red = uzo._red = None
         return SpecExpr(ctx, [], [(1.0, NLTerm(ctx, ia, ib))])
 
     def _vec_dot_nabla_eager(self, ux, uz, out, convert_to_physical):
