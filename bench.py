@@ -623,8 +623,9 @@ def gpu_arm(args, rank, world):
         nl = w.vec_dot_nabla(ux.getp(), uz.getp())             # leaves valid intermediates behind
         wptr = w.gets()._t.data_ptr()
         srcs = (ctypes.c_void_p * 3)(wptr, wptr, wptr)
-        ops = (ctypes.c_int32 * 3)(_capi.OP_UX, _capi.OP_UZ, _capi.OP_IDENT)
-        dsts = (ctypes.c_void_p * 3)(ux._i.data_ptr(), uz._i.data_ptr(), w._i.data_ptr())
+        # field order of Variable.vec_dot_nabla (the scalar first: one source tile load per column tile)
+        ops = (ctypes.c_int32 * 3)(_capi.OP_IDENT, _capi.OP_UX, _capi.OP_UZ)
+        dsts = (ctypes.c_void_p * 3)(w._i.data_ptr(), ux._i.data_ptr(), uz._i.data_ptr())
         timed("mlv_x_inverse", lambda: ctx.call("mlv_x_inverse", 3, srcs, ops, dsts))
         ia, ib = nl.nls[0][1].ia, nl.nls[0][1].ib
         vp = ctypes.c_void_p

@@ -39,8 +39,13 @@ def timed(name, fn):
 
 
 srcs = (vp * 3)(w.data_ptr(), w.data_ptr(), w.data_ptr())
-ops = (ctypes.c_int32 * 3)(_capi.OP_UX, _capi.OP_UZ, _capi.OP_IDENT)
-dsts = (vp * 3)(iux.data_ptr(), iuz.data_ptr(), iq.data_ptr())
+order = os.environ.get("KBENCH_XINV_ORDER", "api")       # "api": scalar first, as Variable.vec_dot_nabla issues it
+if order == "api":
+    ops = (ctypes.c_int32 * 3)(_capi.OP_IDENT, _capi.OP_UX, _capi.OP_UZ)
+    dsts = (vp * 3)(iq.data_ptr(), iux.data_ptr(), iuz.data_ptr())
+else:
+    ops = (ctypes.c_int32 * 3)(_capi.OP_UX, _capi.OP_UZ, _capi.OP_IDENT)
+    dsts = (vp * 3)(iux.data_ptr(), iuz.data_ptr(), iq.data_ptr())
 timed("x_inverse(3)", lambda: ctx.call("mlv_x_inverse", 3, srcs, ops, dsts))
 timed("advect_z", lambda: ctx.call("mlv_advect_z", vp(iux.data_ptr()), vp(iuz.data_ptr()), vp(iq.data_ptr()),
                                    vp(ia.data_ptr()), vp(ib.data_ptr()), vp(red4.data_ptr())))
