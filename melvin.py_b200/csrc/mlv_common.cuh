@@ -265,6 +265,16 @@ MLV_DEV void tma_load_2d(void* smem, const CUtensorMap* map, int c0, int c1, uns
 #endif
 }
 
+// L2 prefetch of one box of a 2-D tensor map: one instruction for up to 256 rows of a column tile
+MLV_DEV void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+#ifndef MLV_EMU
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
+                 ::"l"((unsigned long long)map), "r"(c0), "r"(c1) : "memory");
+#else
+    (void)map; (void)c0; (void)c1;
+#endif
+}
+
 // ---- cross-GPU ordering of producer and consumer kernels (peer-memory exchange): after a
 // producer kernel a one-warp kernel bumps a 64-bit arrival counter in each consumer rank's
 // memory (release at system scope); consumer CTAs spin on their own rank's counter (acquire at

@@ -571,6 +571,9 @@ struct XFwdArgs {
     int stage;                   // 1: the block of operand 0 is staged in shared memory by bulk copies
     const unsigned long long* wait_counter;   // peer stores: forward blocks of all ranks have arrived
     const unsigned long long* wait_expect;    // when *wait_counter >= *wait_expect
+    int pf_tma;                  // k_xfwd_scalar: 1 = the epilogue's state / history column tiles are announced to
+    int pf_rows, pf_boxes;       //    the L2 by tensor prefetches (boxes of pf_rows rows), not one hint per row
+    CUtensorMap qmap, fmap;      // integ.q_in, integ.fm1: (2nn+1, 2*spitch) float64, box (pf_rows, 2*C)
 };
 
 // I (tile layout) x nf -> spectral: value = scale * FFT_x( sum_f coef_f * D_f[src_f] ), rows
@@ -814,7 +817,7 @@ k_xfwd(const XFwdArgs a) {
 // registers for UN epilogue outputs per trip (fewer exposed load round trips).
 template <int LOG2N, int C, int UN>
 __global__ void __launch_bounds__(C * FftCfg<LOG2N>::T, (C * FftCfg<LOG2N>::T <= 256) ? 2 : 1)
-k_xfwd_scalar(const XFwdArgs a) {
+k_xfwd_scalar(const __grid_constant__ XFwdArgs a) {
     typedef FftCfg<LOG2N> F;
     constexpr int NF = F::N;
     const int c = threadIdx.x % C, tau = threadIdx.x / C;
@@ -842,6 +845,10 @@ k_xfwd_scalar(const XFwdArgs a) {
         if (t < NCH)
             l2_prefetch_bulk(reinterpret_cast<const char*>(a.src[first_only ? 0 : 1] + (size_t)tl * NF * C) + (size_t)t * CHUNK, bytes);
         if (first_only) return;
+        if (a.pf_tma) {
+            if (t < 2 * a.pf_boxes) tma_prefetch_2d(t & 1 ? &a.fmap : &a.qmap, 2 * C * tl, (t >> 1) * a.pf_rows);
+            return;
+        }
         const int rows = 2 * a.nn + 1;
         for (int r = t; r < rows; r += C * F::T) {
             const size_t idx = (size_t)r * a.spitch + (size_t)tl * C;
