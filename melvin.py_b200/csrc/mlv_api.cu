@@ -419,13 +419,28 @@ static int launch_xinv_split(mlv_ctx* c, XInvArgs& a) {
     return 0;
 }
 
+// tensor maps of the epilogue's state / history column tiles (L2 prefetch by box instead of by row)
+template <int C>
+static void xfwd_prefetch_maps(XFwdArgs& a, int nthreads) {
+    a.pf_tma = 0;
+    if (a.mode != 1 || !rt_tma_enabled() || rt_env_flag("MLV_XFWD_LINEPF")) return;
+    const int rows = 2 * a.nn + 1;
+    a.pf_rows = rows < 256 ? rows : 256;
+    a.pf_boxes = (rows + a.pf_rows - 1) / a.pf_rows;
+    if (2 * a.pf_boxes > nthreads) return;                     // one thread per box
+    a.pf_tma = rt_make_tmap(&a.qmap, const_cast<cplx*>(a.integ.q_in), 2ull * a.spitch, (unsigned long long)rows,
+                            16ull * a.spitch, 2u * C, (unsigned)a.pf_rows) &&
+               rt_make_tmap(&a.fmap, const_cast<cplx*>(a.integ.fm1), 2ull * a.spitch, (unsigned long long)rows,
+                            16ull * a.spitch, 2u * C, (unsigned)a.pf_rows) ? 1 : 0;
+}
+
 template <int L>
 static int launch_xfwd_split(mlv_ctx* c, XFwdArgs& a) {
     constexpr int C = xcols(L);
     typedef FftCfg<L> F;
     auto kfn = k_xfwd<L, C, 2>;
     a.stage = 0;
-    a.pf_tma = 0;
+    a.pf_tma = 0;            // (per-row hints: tensor prefetch measured 2-3 % slower on the long-line kernels)
     const size_t smem = (size_t)F::XSLOTS * C * sizeof(cplx) + 16;
     const unsigned grid = (unsigned)((a.nm + C - 1) / C);
     a.wave = 148 * (smem > 113 * 1024 ? 1 : 2);
@@ -484,21 +499,13 @@ static int launch_xfwd(mlv_ctx* c, XFwdArgs& a) {
     if (rt_tma_enabled() && a.nf >= 2 && a.sym[0] == XSYM_FDX && a.sym[1] == XSYM_FDZ && a.order == 2 &&
         ((1u << a.sh.fwd_rshift) * C * sizeof(cplx)) % 16 == 0)
         a.stage = 1;
+    // the epilogue's state / history column tiles: 22 tensor prefetches per CTA instead of 5462 per-row hints
+    // at 4096^2 (which filled the load/store queue: lg_throttle 4.5 warps per issue), 0.1286 -> 0.1161 ms
     a.pf_tma = 0;
     // the single-scalar step on one GPU (KH / TG loops): specialised kernel
     if (a.stage && c->nranks == 1 && (1 << a.sh.fwd_rshift) == F::N && a.sh.fwd_chunk == 0 && a.nf == 2 && a.mode == 1 &&
         a.integ.ab_order == 2 && a.integ.scheme == 0 && a.lin.n == 0 && !rt_env_flag("MLV_XFWD_GENERIC")) {
-        // the epilogue's state / history column tiles: 22 tensor prefetches per CTA instead of 5462 per-row hints
-        // (which filled the load/store queue: lg_throttle 4.5 warps per issue), 0.1286 -> 0.1161 ms
-        if (rt_tma_enabled() && !rt_env_flag("MLV_XFWD_LINEPF")) {
-            const int rows = 2 * a.nn + 1;
-            a.pf_rows = rows < 256 ? rows : 256;
-            a.pf_boxes = (rows + a.pf_rows - 1) / a.pf_rows;
-            a.pf_tma = rt_make_tmap(&a.qmap, const_cast<cplx*>(a.integ.q_in), 2ull * a.spitch, (unsigned long long)rows,
-                                    16ull * a.spitch, 2u * C, (unsigned)a.pf_rows) &&
-                       rt_make_tmap(&a.fmap, const_cast<cplx*>(a.integ.fm1), 2ull * a.spitch, (unsigned long long)rows,
-                                    16ull * a.spitch, 2u * C, (unsigned)a.pf_rows) ? 1 : 0;
-        }
+        xfwd_prefetch_maps<C>(a, C * F::T);
 #define MLV_XFWD_GO(UN_)                                                                  \
         do {                                                                              \
             auto kh = k_xfwd_scalar<L, C, UN_>;                                           \

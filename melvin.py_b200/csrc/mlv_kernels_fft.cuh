@@ -588,7 +588,7 @@ struct XFwdArgs {
 //   X[2q+s] = DFT_N( (x[p] + (-1)^s x[p+N]) e^{-2 pi i s p/2N} )[q],  s = 0, 1.
 template <int LOG2N, int C, int SPLIT>
 __global__ void __launch_bounds__(C * FftCfg<LOG2N>::T, (C * FftCfg<LOG2N>::T <= 256) ? 2 : 1)
-k_xfwd(const XFwdArgs a) {
+k_xfwd(const __grid_constant__ XFwdArgs a) {
     typedef FftCfg<LOG2N> F;
     constexpr int NF = F::N * SPLIT;                  // line length
     const int c = threadIdx.x % C, tau = threadIdx.x / C;
@@ -618,11 +618,16 @@ k_xfwd(const XFwdArgs a) {
             }
         }
         if (a.mode == 1) {
-            const int rows = 2 * a.nn + 1;
-            for (int r = t; r < rows; r += C * F::T) {
-                const size_t idx = (size_t)r * a.spitch + blockIdx.x * C;
-                l2_prefetch_line(a.integ.q_in + idx);
-                l2_prefetch_line(a.integ.fm1 + idx);
+            if (a.pf_tma) {                      // one tensor prefetch per 256 rows and array
+                if (t < 2 * a.pf_boxes)
+                    tma_prefetch_2d(t & 1 ? &a.fmap : &a.qmap, 2 * C * (int)blockIdx.x, (t >> 1) * a.pf_rows);
+            } else {
+                const int rows = 2 * a.nn + 1;
+                for (int r = t; r < rows; r += C * F::T) {
+                    const size_t idx = (size_t)r * a.spitch + blockIdx.x * C;
+                    l2_prefetch_line(a.integ.q_in + idx);
+                    l2_prefetch_line(a.integ.fm1 + idx);
+                }
             }
         }
     }
