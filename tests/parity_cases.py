@@ -121,8 +121,8 @@ def run_ddc(nx, nz, lx, lz, dt, nsteps, Pr, R0, tau, snaps=()):
     return out
 
 
-def run_tearing(nx, nz, lx, lz, dt, nsteps, Re, S, j0_phys, snaps=()):
-    """examples/resistive_tearing_instability.py:125-148"""
+def run_tearing(nx, nz, lx, lz, dt, nsteps, Re, S, j0_phys, snaps=(), w0_phys=None):
+    """examples/resistive_tearing_instability.py:125-148 (w0_phys: optional non-zero initial vorticity)"""
     d = base_params(nx, nz, lx, lz, initial_dt=dt, Re=Re, S=S, spatial_derivative_order=2,
                     integrator_order=2, integrator="semi-implicit")
     p, sim, (w, j), (dw, dj), psi, ux, uz = make_sim(d, ["w", "j"], ["dw", "dj"], [CE, CE])
@@ -131,6 +131,8 @@ def run_tearing(nx, nz, lx, lz, dt, nsteps, Re, S, j0_phys, snaps=()):
     bz = sim.make_variable("bz", [CE, CE])
     sim.config_scalar_trackers({"ke": partial(calc_kinetic_energy, ux, uz, xp, p)})
     j.load(j0_phys, is_physical=True)
+    if w0_phys is not None:
+        w.load(w0_phys, is_physical=True)
     solver = sim.get_laplacian_solver()
     out = {}
     while sim._loop_counter < nsteps:

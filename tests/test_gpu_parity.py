@@ -344,6 +344,44 @@ def test_tearing_with_config5_line_length(nx, nz):
     np.testing.assert_allclose(out["ke"], run.ke, rtol=1e-4, atol=1e-300)
 
 
+def test_one_kelvin_helmholtz_step_on_the_full_8192_grid():
+    """BASELINE config-4 grid size as a full 2-D grid (8192 x 8192, long-line kernels in both
+    directions): one Kelvin-Helmholtz step vs the oracle."""
+    nx = nz = 8192
+    lx, lz = 16.0 / 9.0, 1.0
+    g = mo.Grid(nx, nz, lx, lz)
+    w0 = mo.ic_kelvin_helmholtz(g)
+    dt = 0.05 * lx / nx
+    want, run, snaps = mo.run_single_scalar(g, w0, 1e-5, dt, 1, tracker_cadence=1, snapshots=(1,))
+    with pc.scratch_cwd():
+        out = pc.run_single_scalar(nx, nz, lx, lz, 1e-5, dt, 1, w0, snaps=(1,))
+    assert rel_l2(out["w_step1"], snaps[1]) < FIELD_TOL
+    np.testing.assert_allclose(out["ke"], run.ke, rtol=SERIES_TOL)
+
+
+def test_tearing_steps_at_16384_x_1024_with_the_series_gate():
+    """BASELINE config-5 line length on a 2-D grid (16384 x 1024).  The example starts from zero
+    vorticity, which makes w and the kinetic energy residues of cancelling O(1) terms (see
+    test_tearing_with_config5_line_length); with a non-zero initial vorticity the same kernels
+    meet the full gates: fields 1e-12, kinetic energy 1e-9."""
+    nx, nz = 16384, 1024
+    lx, lz, Re, S = 16.0 / 9.0, 1.0, 1e6, 1e6
+    g = mo.Grid(nx, nz, lx, lz)
+    j0 = mo.ic_tearing_current(g)
+    w0 = mo.ic_kelvin_helmholtz(g)
+    dt = 0.05 * min(lx / nx, lz / nz) * 0.01
+    run = mo.Run(g, dt, tracker_cadence=1)
+    state = (mo.to_spectral(g, w0), mo.to_spectral(g, j0))
+    hists = (mo.History(g), mo.History(g))
+    for _ in range(2):
+        state = mo.step_tearing(g, run, state, hists, Re, S)
+    with pc.scratch_cwd():
+        out = pc.run_tearing(nx, nz, lx, lz, dt, 2, Re, S, j0, snaps=(2,), w0_phys=w0)
+    assert rel_l2(out["j_step2"], state[1]) < FIELD_TOL
+    assert rel_l2(out["w_step2"], state[0]) < FIELD_TOL
+    np.testing.assert_allclose(out["ke"], run.ke, rtol=SERIES_TOL)
+
+
 # --------------------------------------------------------------- edge cases
 def test_edge_cases_and_errors():
     from melvin import Parameters, Simulation
