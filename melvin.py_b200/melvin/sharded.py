@@ -280,24 +280,46 @@ class ShardedScalarStepper:
         dist.all_gather([torch.view_as_real(p) for p in parts], torch.view_as_real(local), group=self.group)
         return np.concatenate([_backend.to_host(p) for p in parts], axis=1)[:, : self.nm]
 
-    def _inverse_round(self, fields):
+    def _mark(self):
+        """Events at the current end of every copy stream (copy-engine exchange)."""
+        evs = []
+        for cs in self._copy_streams:
+            e = torch.cuda.Event()
+            e.record(cs)
+            evs.append(e)
+        return evs
+
+    def _join_mark(self, evs):
+        """Compute stream waits for this rank's copies up to a mark; the all-reduce then tells every
+        rank that the matching blocks of all ranks have landed."""
+        comp = torch.cuda.current_stream()
+        for e in evs:
+            comp.wait_event(e)
+        dist.all_reduce(self._sync, group=self.group)
+
+    def _inverse_round(self, fields, marks_at=None):
         """fields: [(source spectral tensor, MLV_OP_*, inverse slot)].  Inverse x pass of every
-        field on the local columns, then row block h of every field at rank h."""
+        field on the local columns, then row block h of every field at rank h.
+        marks_at (copy-engine exchange only): field counts after which the copy streams are marked;
+        the round then does NOT join -- the caller joins mark by mark (`_join_mark`), so that the
+        first consumers start while the copies of the later fields are still travelling."""
         ctx, vp = self.ctx, ctypes.c_void_p
         if self.mode == "dma" or not (self.world == 1 or self.p2p):
-            works = []
+            works, marks = [], {}
             for i, (src, op, slot) in enumerate(fields):
                 ctx.call("mlv_x_inverse", 1, (vp * 1)(src.data_ptr()), (ctypes.c_int32 * 1)(op),
                          (vp * 1)(self._slot(0, False, slot)))
                 if self.mode == "dma":
                     self._dma(0, slot, self._ev[i % 3])
+                    if marks_at and (i + 1) in marks_at:
+                        marks[i + 1] = self._mark()
                 else:
                     works.append(self._a2a(self.inv_recv, self.inv_send, slot))
-            if self.mode == "dma":
+            if self.mode == "dma" and not marks_at:
                 self._dma_join(self._ev[3])
             for wk in works:
                 wk.wait()
-            return
+            return marks
         # world 1 / peer stores: batches of up to 4 fields share the column stash of their source
         for b in range(0, len(fields), 4):
             grp = fields[b:b + 4]
@@ -308,16 +330,19 @@ class ShardedScalarStepper:
         if self.world > 1 and not self._flags:
             dist.all_reduce(self._sync, group=self.group)
 
-    def _advect_round(self, jobs):
+    def _advect_round(self, jobs, before=None):
         """jobs: [(inverse slots ux, uz, q, forward slots a, b, red4 tensor or None)].  Fused z
-        stage on the local rows, then tile block h of every forward field at rank h."""
+        stage on the local rows, then tile block h of every forward field at rank h.
+        before: {job index: callable} run right before that job is launched (deferred joins)."""
         ctx, vp = self.ctx, ctypes.c_void_p
         chunked = self.mode == "dma" or not (self.world == 1 or self.p2p)
         works = []
         # the z stage computes its CFL / energy partials only on the steps whose tickers read them
         ctx.want_reductions = any(job[5] is not None for job in jobs)
         ctx.sync_reduction_mode()
-        for (sux, suz, sq, fa, fb, red) in jobs:
+        for k, (sux, suz, sq, fa, fb, red) in enumerate(jobs):
+            if before and k in before:
+                before[k]()
             args = (vp(self._slot(0, True, sux)), vp(self._slot(0, True, suz)), vp(self._slot(0, True, sq)),
                     vp(self._slot(1, False, fa)), vp(self._slot(1, False, fb)))
             redp = vp(red.data_ptr()) if red is not None else None
@@ -626,11 +651,21 @@ class ShardedTearingStepper(ShardedScalarStepper):
         w_new, j_new = self.q["w"][n], self.q["j"][n]
         OP = _capi
         # inverse slots: 0 w, 1 ux, 2 uz, 3 j, 4 bx, 5 bz, 6 updated w
-        self._inverse_round([(w, OP.OP_IDENT, 0), (w, OP.OP_UX, 1), (w, OP.OP_UZ, 2),
-                             (j, OP.OP_IDENT, 3), (j, OP.OP_UX, 4), (j, OP.OP_UZ, 5)])
+        fields = [(w, OP.OP_IDENT, 0), (w, OP.OP_UX, 1), (w, OP.OP_UZ, 2),
+                  (j, OP.OP_IDENT, 3), (j, OP.OP_UX, 4), (j, OP.OP_UZ, 5)]
         # forward slots: (0,1) u.grad w, (2,3) b.grad j, (4,5) u.grad j, (6,7) b.grad w_new
         red = self.red4 if self._tickers_due() else None
-        self._advect_round([(1, 2, 0, 0, 1, red), (4, 5, 3, 2, 3, None), (1, 2, 3, 4, 5, None)])
+        jobs = [(1, 2, 0, 0, 1, red), (4, 5, 3, 2, 3, None), (1, 2, 3, 4, 5, None)]
+        if self.mode == "dma" and os.environ.get("MLV_SPLIT_JOIN", "1") != "0":
+            # copy engines lag behind the x passes (443 GB/s vs 154 MB per field every ~0.25 ms at 8 GPUs):
+            # the first z-stage job needs only the three fields derived from w -- start it as soon as
+            # those have landed, the copies of the j fields travel meanwhile
+            marks = self._inverse_round(fields, marks_at=(3, 6))
+            self._join_mark(marks[3])
+            self._advect_round(jobs, before={1: lambda: self._join_mark(marks[6])})
+        else:
+            self._inverse_round(fields)
+            self._advect_round(jobs)
         self._forward((0, 1, 2, 3), (-1.0, -1.0, 1.0, 1.0), [], 1.0 / self.Re, w, w_new, self.h["w"], self.hidx)
         self._inverse_round([(w_new, OP.OP_IDENT, 6)])
         self._advect_round([(4, 5, 6, 6, 7, None)])
