@@ -579,10 +579,20 @@ class ShardedDoubleDiffusiveStepper(ShardedScalarStepper):
         w, tmp, xi = (self.q[k][c] for k in ("w", "tmp", "xi"))
         OP = _capi
         # inverse slots: 0 w, 1 ux, 2 uz (all from the old vorticity), 3 tmp, 4 xi
-        self._inverse_round([(w, OP.OP_IDENT, 0), (w, OP.OP_UX, 1), (w, OP.OP_UZ, 2),
-                             (tmp, OP.OP_IDENT, 3), (xi, OP.OP_IDENT, 4)])
+        fields = [(w, OP.OP_IDENT, 0), (w, OP.OP_UX, 1), (w, OP.OP_UZ, 2),
+                  (tmp, OP.OP_IDENT, 3), (xi, OP.OP_IDENT, 4)]
         red = self.red4 if self._tickers_due() else None
-        self._advect_round([(1, 2, 0, 0, 1, red), (1, 2, 3, 2, 3, None), (1, 2, 4, 4, 5, None)])
+        jobs = [(1, 2, 0, 0, 1, red), (1, 2, 3, 2, 3, None), (1, 2, 4, 4, 5, None)]
+        if self.mode == "dma" and os.environ.get("MLV_SPLIT_JOIN", "1") != "0":
+            # joins by mark (see ShardedTearingStepper.step): every z-stage job starts as soon as
+            # ITS scalar has landed, the later fields travel during the earlier jobs
+            marks = self._inverse_round(fields, marks_at=(3, 4, 5))
+            self._join_mark(marks[3])
+            self._advect_round(jobs, before={1: lambda: self._join_mark(marks[4]),
+                                             2: lambda: self._join_mark(marks[5])})
+        else:
+            self._inverse_round(fields)
+            self._advect_round(jobs)
         Pr, R0, tau = self.Pr, self.R0, self.tau
         self._forward((0, 1), (-1.0, -1.0), [(Pr, OP.OP_DDX, xi), (-Pr, OP.OP_DDX, tmp)], Pr,
                       w, self.q["w"][n], self.h["w"], self.hidx)
