@@ -315,3 +315,8 @@ def test_pentadiagonal_fourth_order_solve():
     import host_cases as hc
     worst, r2, r4 = hc.pentadiagonal_solve()
     assert worst < 1e-12
+
+
+def test_specialised_kernels_match_generic():
+    import host_cases as hc
+    assert hc.specialised_kernels_match_generic()          # bit-identical on the host build

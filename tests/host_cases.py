@@ -311,3 +311,37 @@ def pentadiagonal_residual(nx, nz):
         res = np.linalg.norm((Ax - rhs[n]).astype(complex)) / np.linalg.norm(rhs[n])
         # the solution is rounded to double: A amplifies that by ~ 1/dz^2
         assert res < 20 * 1.1e-16 * nz ** 2, (n, float(res))
+
+
+def specialised_kernels_match_generic(nx=64, nz=64, nsteps=6):
+    """The kernels specialised for the single-GPU single-scalar step (k_xfwd_scalar, the unsharded
+    z stage, reductions compiled out on non-ticker steps) do the same arithmetic in the same order
+    as the generic ones.  Identical bits on the host build; on the device the compiler contracts
+    multiply-adds per kernel, so the states agree to rounding (1e-14 after a few KH steps)."""
+    import os
+    import bench
+    keys = ("MLV_XFWD_GENERIC", "MLV_ZADV_GENERIC")
+    saved = {k: os.environ.pop(k, None) for k in keys}
+    cwd = os.getcwd()
+    try:
+        def run(generic):
+            for k in keys:
+                if generic:
+                    os.environ[k] = "1"
+                else:
+                    os.environ.pop(k, None)
+            step, o = bench.build_public_loop("kh", nx, nz)
+            o["sim"].reductions = "always" if generic else "auto"
+            for _ in range(nsteps):
+                step()
+            return o["w"].on_host()
+        a, b = run(False), run(True)
+        assert mo.relative_l2(a, b) < 1e-14
+        return np.array_equal(a, b)
+    finally:
+        os.chdir(cwd)
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v

@@ -554,3 +554,10 @@ def test_pentadiagonal_fourth_order_solve(nx, nz):
         assert worst < 1e-12
         return
     hc.pentadiagonal_residual(nx, nz)
+
+
+@pytest.mark.parametrize("nx,nz", [(64, 64), (4096, 512)])
+def test_specialised_kernels_match_generic(nx, nz):
+    """k_xfwd_scalar / unsharded z stage / compiled-out reductions vs the generic kernels (rounding level)"""
+    import host_cases as hc
+    hc.specialised_kernels_match_generic(nx, nz, 4)
