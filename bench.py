@@ -616,6 +616,10 @@ def gpu_arm(args, rank, world):
     roofline = {"bound": "hbm", "kernel": "whole step", "unit": "GB/s", "peak": peak, "peak_source": peak_src,
                 "achieved": bm["step"] / (ms_per_step * 1e-3) / 1e9, "traffic": None}
     roofline["frac"] = roofline["achieved"] / peak
+    if config != "kh":
+        traffic, traffic_src = measured_traffic(nx, nz)
+        roofline["traffic"], roofline["traffic_source"] = traffic.get("whole step"), traffic_src
+        roofline["algorithmic_bytes_per_step"] = bm["step"]
     if config == "kh":
         ctx = w._ctx
         psi, dw, solver = o["psi"], o["dw"], sim.get_laplacian_solver()
