@@ -696,7 +696,8 @@ def gpu_arm(args, rank, world):
     blocking_s = time.perf_counter() - t0
 
     from melvin.ensemble import Ensemble
-    n_members = int(os.environ.get("MLV_E2E_MEMBERS", "4"))
+    # measured (tools/gpu_r4d.sh): 2 / 4 / 6 / 8 members -> 2.62 / 1.47 / 1.43 / 1.40 ms per pass (PCIe-bound)
+    n_members = int(os.environ.get("MLV_E2E_MEMBERS", "8"))
     e2e_passes = max(3 * n_members, min(4 * args.steps, 120))
 
     def build_member(i):
