@@ -25,6 +25,11 @@ from . import _backend, _capi
 from .b200 import DeviceArray, Dist, LazyLap, NLTerm, SpecExpr, _frozen
 from .basis import BasisFunctions
 
+
+def _require_device_namespace(xp):
+    from .operators import _require_device_namespace as f      # (operators imports this module)
+    return f(xp)
+
 _I_NONE, _I_PENDING, _I_VALID = 0, 1, 2
 
 
@@ -74,7 +79,7 @@ class Variable:
     def __init__(self, params, xp, sd=None, st=None, dt=None, array_factory=None,
                  dump_name=None, basis_functions=None):
         self._params = params
-        self._xp = xp
+        self._xp = _require_device_namespace(xp)
         self._st = st
         self._sd = sd
         self._dt = dt
@@ -535,7 +540,7 @@ class TimeDerivative:
 
     def __init__(self, params, xp, dump_name="", array_factory=None):
         self._params = params
-        self._xp = xp
+        self._xp = _require_device_namespace(xp)
         self._curr_idx = 0
         ctx = _backend.context_for(params)
         self._store = DeviceArray(_backend.zeros(

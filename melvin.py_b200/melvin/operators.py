@@ -20,10 +20,23 @@ _SIN = BasisFunctions.SINE
 
 
 def _require_device_namespace(xp):
-    if getattr(xp, "__name__", "") == "numpy":
-        raise _backend.BackendUnavailable(
-            "melvin-b200 has no CPU path: pass the device namespace (`from melvin import b200 as xp`, "
-            "or the `cupy` shim) instead of numpy")
+    """The array namespace the package computes with.  There is no CPU path: `numpy` raises --
+    unless MELVIN_B200_NUMPY_IS_DEVICE=1, the switch for running scripts that hard-code `xp = np`
+    (examples/resistive_tearing_instability.py:19-20) unchanged: the NumPy namespace is then
+    replaced by `melvin.b200` (with a warning) and everything still runs on the device."""
+    if getattr(xp, "__name__", "") != "numpy":
+        return xp
+    import os
+    if os.environ.get("MELVIN_B200_NUMPY_IS_DEVICE", "") not in ("", "0"):
+        import warnings
+        from . import b200
+        warnings.warn("melvin-b200: xp = numpy requested, computing on the device (melvin.b200); "
+                      "there is no CPU path", UserWarning, stacklevel=3)
+        return b200
+    raise _backend.BackendUnavailable(
+        "melvin-b200 has no CPU path: pass the device namespace (`from melvin import b200 as xp`, "
+        "or the `cupy` shim) instead of numpy (or set MELVIN_B200_NUMPY_IS_DEVICE=1 to run an "
+        "`xp = np` script on the device)")
 
 
 def _ptr(t):
@@ -53,7 +66,7 @@ class ArrayFactory:
     """Creates arrays of the correct size and shape (reference melvin/ArrayFactory.py)."""
 
     def __init__(self, params, xp):
-        _require_device_namespace(xp)
+        xp = _require_device_namespace(xp)
         self._p = params
         self._xp = xp
 
@@ -99,7 +112,7 @@ class SpectralTransformer:
     (reference melvin/SpectralTransformer.py)."""
 
     def __init__(self, params, xp, array_factory):
-        _require_device_namespace(xp)
+        xp = _require_device_namespace(xp)
         self._p = params
         self._xp = xp
         self._array_factory = array_factory
@@ -309,7 +322,7 @@ class SpatialDifferentiator:
     (reference melvin/SpatialDifferentiator.py)."""
 
     def __init__(self, params, xp, array_factory=None):
-        _require_device_namespace(xp)
+        xp = _require_device_namespace(xp)
         self._xp = xp
         self._params = params
         self._ctx = _backend.context_for(params)
@@ -420,7 +433,7 @@ class LaplacianSolver:
     """Solves lap(psi) = rhs (reference melvin/LaplacianSolver.py)."""
 
     def __init__(self, params, xp, basis_fns, spatial_diff=None, array_factory=None):
-        _require_device_namespace(xp)
+        xp = _require_device_namespace(xp)
         self._params = params
         self._xp = xp
         self._array_factory = array_factory
@@ -502,7 +515,7 @@ class Integrator:
     treatment of the linear term (reference melvin/Integrator.py)."""
 
     def __init__(self, params, xp):
-        _require_device_namespace(xp)
+        xp = _require_device_namespace(xp)
         self._dt = params.initial_dt
         self._dx = params.dx
         self._dz = params.dz

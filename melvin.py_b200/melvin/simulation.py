@@ -69,7 +69,7 @@ class ScalarTracker:
     """Tracks a scalar through time (reference melvin/ScalarTracker.py)."""
 
     def __init__(self, params, xp, filename):
-        self._xp = xp
+        self._xp = _require_device_namespace(xp)
         self._params = params
         self._filename = filename
         self._values = []
@@ -91,7 +91,7 @@ class DataTransferer:
     """Host <-> device copies (reference melvin/DataTransferer.py)."""
 
     def __init__(self, xp):
-        _require_device_namespace(xp)
+        self._xp = _require_device_namespace(xp)
 
     def to_host(self, data):
         return data.get() if hasattr(data, "get") else np.asarray(data)
@@ -107,6 +107,7 @@ class Simulation:
 
     def __init__(self, params, xp):
         self._params = params
+        xp = _require_device_namespace(xp)
         self._xp = xp
         self._data_trans = DataTransferer(xp)
         self._integrator = Integrator(params, xp)

@@ -39,6 +39,9 @@ def calc_kinetic_energy(ux, uz, xp, params):
     nx, nz = params.nx, params.nz
     sx = ux._cached_reduction(2) if hasattr(ux, "_cached_reduction") else None
     sz = uz._cached_reduction(2) if hasattr(uz, "_cached_reduction") else None
+    if sx is None or sz is None:
+        from .operators import _require_device_namespace
+        xp = _require_device_namespace(xp)
     if sx is None:
         sx = xp.sum_of_squares(ux.getp())
     if sz is None:

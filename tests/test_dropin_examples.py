@@ -38,12 +38,19 @@ CASES = {
                                     "dump_cadence": 6e-6}, 10),
     "vortex_pairs": ({"nx": 64, "nz": 32, "tracker_cadence": 1, "save_cadence": 1e-2,
                       "initial_dt": 1e-3}, 8),
+    # hard-codes `xp = np` (examples/resistive_tearing_instability.py:19-20): runs on the device under
+    # MELVIN_B200_NUMPY_IS_DEVICE=1 (without the switch numpy as xp raises BackendUnavailable)
+    "resistive_tearing_instability": ({"nx": 64, "nz": 64, "tracker_cadence": 1}, 8),
 }
+NUMPY_XP = {"resistive_tearing_instability"}
 
 
-def run(impl, script, overrides, steps, out):
+def run(impl, script, overrides, steps, out, numpy_is_device=False):
     env = dict(os.environ, PYTHONDONTWRITEBYTECODE="1")
     env.pop("PYTHONPATH", None)
+    env.pop("MELVIN_B200_NUMPY_IS_DEVICE", None)
+    if numpy_is_device:
+        env["MELVIN_B200_NUMPY_IS_DEVICE"] = "1"
     subprocess.run([sys.executable, RUNNER, "--impl", impl, "--script", script, "--overrides",
                     json.dumps(overrides), "--steps", str(steps), "--out", out],
                    check=True, env=env, timeout=600)
@@ -59,9 +66,14 @@ def test_reference_example_runs_unmodified(name, tmp_path):
     overrides, steps = CASES[name]
     script = os.path.join(REF, "examples", name + ".py")
     ours, ref = str(tmp_path / "ours"), str(tmp_path / "ref")
-    run("emu", script, overrides, steps, ours)
+    if name in NUMPY_XP:
+        with pytest.raises(subprocess.CalledProcessError):        # no CPU path: numpy as xp is refused ...
+            run("emu", script, overrides, steps, ours)
+    run("emu", script, overrides, steps, ours, numpy_is_device=name in NUMPY_XP)     # ... unless asked for
     run("reference", script, overrides, steps, ref)
     assert int(open(os.path.join(ours, "launches.txt")).read()) > 0
+    if name in NUMPY_XP:
+        assert "xp = numpy requested, computing on the device" in open(os.path.join(ours, "warnings.txt")).read()
     assert "precision='single' is computed in float64" in open(os.path.join(ours, "warnings.txt")).read()
     # the JSON parameter file the script wrote is the same, and reloads into the same Parameters
     pj = json.load(open(os.path.join(ours, "params.json")))
