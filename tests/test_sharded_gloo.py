@@ -24,10 +24,16 @@ def run_world(n, case, port, **extra_env):
     assert out.returncode == 0 and lines and lines[-1].endswith("OK"), out.stdout[-2000:] + out.stderr[-2000:]
 
 
+@pytest.fixture(scope="module", autouse=True)
+def emulation_build():
+    """build the emulation library ONCE, here, if it is stale (the ranks of a world must not race for it)"""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+    import emu_harness
+    emu_harness.lib()
+
+
 @pytest.mark.parametrize("world", [2, 4])          # (world 1: test_multi_field_steppers[ddc-1])
 def test_taylor_green_sharded_matches_reference_golden(world):
-    subprocess.run(["sh", os.path.join(ROOT, "tests", "emu", "build_emu.sh")], check=True,
-                   capture_output=True)
     run_world(world, "tg64", 29600 + world)
 
 
