@@ -451,6 +451,17 @@ def arange(*args, **kw):
     return DeviceArray(_backend.from_host(np.arange(*args, **kw)))
 
 
+def meshgrid(*xi, **kw):
+    """Set-up helper of the namespace (ArrayFactory.py:26 builds its mode-number matrices with it):
+    composed on the host, one upload per result."""
+    return [DeviceArray(_backend.from_host(g)) for g in np.meshgrid(*[asnumpy(x) for x in xi], **kw)]
+
+
+def concatenate(arrays, axis=0):
+    """Set-up helper of the namespace (ArrayFactory.py:12, SpectralTransformer.py:170-186)."""
+    return DeviceArray(_backend.from_host(np.concatenate([asnumpy(a) for a in arrays], axis=axis)))
+
+
 def max(a):   # noqa: A001  (NumPy name)
     return _reduce(_capi.RED_MAX, _as_dev(a))
 

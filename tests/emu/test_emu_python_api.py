@@ -73,6 +73,12 @@ def test_array_namespace():
     z[:, 1] = 1.0 + 2.0j
     assert z.get()[2, 1] == 1.0 + 2.0j and z.dtype == np.complex128
     assert float(np.float64(3.0) * A[2, 2]) == 3.0 * a[2, 2]
+    # set-up helpers the reference's own classes call on the namespace (ArrayFactory.py:8-26)
+    n = xp.concatenate((xp.arange(0, 4), xp.arange(-3, 0)))
+    N, M = xp.meshgrid(n, xp.arange(0, 3), indexing="ij")
+    Nn, Mn = np.meshgrid(np.concatenate((np.arange(0, 4), np.arange(-3, 0))), np.arange(0, 3), indexing="ij")
+    assert np.array_equal(N.get(), Nn) and np.array_equal(M.get(), Mn) and N.get().dtype == Nn.dtype
+    np.testing.assert_array_equal(xp.concatenate((A, B), axis=1).get(), np.concatenate((a, b), axis=1))
 
 
 def test_reference_unit_tests_run_on_the_dropin():
