@@ -207,6 +207,11 @@ class DeviceArray:
         DeviceArray(out._t)[...] = DeviceArray(self._touch()._t)
         return out
 
+    def take(self, indices, axis=None):
+        """numpy.ndarray.take (the reference's stencils use it for the periodic wrap,
+        SpatialDifferentiator.py:145-180; here a convenience of the namespace, gathered on the host)"""
+        return DeviceArray(_backend.from_host(np.take(self.get(), indices, axis=axis)))
+
     # -- views
     def __getitem__(self, idx):
         self._touch()

@@ -79,6 +79,7 @@ def test_array_namespace():
     Nn, Mn = np.meshgrid(np.concatenate((np.arange(0, 4), np.arange(-3, 0))), np.arange(0, 3), indexing="ij")
     assert np.array_equal(N.get(), Nn) and np.array_equal(M.get(), Mn) and N.get().dtype == Nn.dtype
     np.testing.assert_array_equal(xp.concatenate((A, B), axis=1).get(), np.concatenate((a, b), axis=1))
+    np.testing.assert_array_equal(A.take((-1, 0), axis=0).get(), a.take((-1, 0), axis=0))
 
 
 def test_reference_unit_tests_run_on_the_dropin():
