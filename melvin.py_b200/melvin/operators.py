@@ -120,9 +120,25 @@ class SpectralTransformer:
         if params.is_fully_spectral():
             self.to_physical = self.__to_physical_2d
             self.to_spectral = self.__to_spectral_2d
+            self._scale = self._scale_2d
         else:
             self.to_physical = self.__to_physical_1d
             self.to_spectral = self.__to_spectral_1d
+            self._scale = self._scale_1d
+
+    # The reference's third slot (SpectralTransformer.py:21-31): copy between the truncated spectrum and
+    # the full FFT layout.  The kernels prune / pad inside the transforms and never call it; kept for
+    # code that does (plain slice copies on either kind of array).
+    def _scale_2d(self, in_arr, out):
+        nn, nm = self._p.nn, self._p.nm
+        for rows in (slice(None, nn + 1), slice(-nn, None)):
+            out[rows, :nm] = in_arr[rows, :nm]
+
+    def _scale_1d(self, in_arr, out, axis):
+        if axis == 0:
+            out[:self._p.nn] = in_arr[:self._p.nn]
+        elif axis == 1:
+            out[:, :self._p.nm] = in_arr[:, :self._p.nm]
 
     _DEFAULT = [_CE, _CE]
 

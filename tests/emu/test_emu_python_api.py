@@ -105,6 +105,15 @@ def test_reference_unit_tests_run_on_the_dropin():
     np.testing.assert_array_almost_equal(spectral.get(), true_spectral)
     st.to_physical(spectral, physical, basis_functions=[CE, CE])
     np.testing.assert_array_almost_equal(physical.get(), true_physical)
+    # the third slot of the reference's transformer (SpectralTransformer.py:21-24): truncated <-> full layout
+    rng = np.random.default_rng(1)
+    full = rng.standard_normal((p.nx, p.nz // 2 + 1)) + 1j * rng.standard_normal((p.nx, p.nz // 2 + 1))
+    trunc = xp.zeros(spectral.shape, dtype=np.complex128)
+    st._scale(xp.array(full), trunc)
+    want = np.zeros(spectral.shape, complex)
+    want[: p.nn + 1, : p.nm] = full[: p.nn + 1, : p.nm]
+    want[-p.nn:, : p.nm] = full[-p.nn:, : p.nm]
+    assert np.array_equal(trunc.get(), want)
     # Variable_test.py:16-46, :76-100
     var = Variable(p, xp, st=st, sd=sd, array_factory=af, basis_functions=[CE, CE])
     var.setp(np.cos(2 * np.pi * X) * np.cos(2 * np.pi * Z))
