@@ -719,13 +719,17 @@ def gpu_arm(args, rank, world):
             for n in names:
                 p["o"][n].on_host(out=p["hosts"][n])                        # D2H, queued
 
-    for k in range(2 * n_members):
-        ensemble_pass(k)
+    # warm-up: at least two passes per member and one second of continuous traffic (the first CUDA process
+    # on a fresh box measured 5-10 % slower PCIe round trips than a warm one: r02d 1.57 vs r02c 1.41 ms)
+    n_warm, t_w = 0, time.perf_counter()
+    while n_warm < 2 * n_members or time.perf_counter() - t_w < 1.0:
+        ensemble_pass(n_warm)
+        n_warm += 1
     ens.drain()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for k in range(e2e_passes):
-        ensemble_pass(2 * n_members + k)
+        ensemble_pass(n_warm + k)
     ens.drain()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
