@@ -734,7 +734,7 @@ def gpu_arm(args, rank, world):
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     e2e = {"value": nx * nz * e2e_passes / e2e_s, "unit": UNIT, "h2d_bytes_per_step": sbytes,
-           "d2h_bytes_per_step": sbytes + 32, "steps": e2e_passes,
+           "d2h_bytes_per_step": sbytes + 32, "steps": e2e_passes, "warmup_passes": n_warm,
            "mode": f"streamed ensemble of {n_members} independent simulations (melvin/ensemble.py): every pass "
                    "uploads the member's state from pinned host memory, steps it and reads the new state back; "
                    "copies of one member overlap the step of another",
